@@ -1,0 +1,140 @@
+/*
+ * rsdf_b200.h -- C ABI of the B200-native ray-marched neural-SDF hot path.
+ *
+ * Drop-in boundary for RISE-SDF's operator imports.  Every entry point is
+ * `extern "C"`, takes plain device pointers + sizes + a cudaStream_t (as void*), allocates
+ * nothing, keeps no global state, and returns 0 on success or a cudaError_t / negative
+ * argument-error code.  All tensors are contiguous, row-major, float32 unless noted.
+ * The citation after each declaration is the reference interface the symbol replaces
+ * (paths relative to the RISE-SDF tree).
+ *
+ * Error codes: 0 ok; >0 cudaError_t from the launch; -1 bad argument (null pointer where
+ * data is required, unsupported size); -2 capacity exceeded.
+ */
+#ifndef RSDF_B200_H
+#define RSDF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSDF_MAX_LEVELS 32
+
+/* Multiresolution hash-grid geometry, computed once on the host
+ * (tiny-cuda-nn grid_scale()/grid_resolution(); rise_sdf_b200/tinycudann.py). */
+typedef struct rsdf_hashgrid_meta {
+    int32_t n_levels;
+    int32_t n_features;               /* 2 (the only value the reference configs use) */
+    float scale[RSDF_MAX_LEVELS];     /* exp2f(l*log2 pls)*base - 1 */
+    uint32_t res[RSDF_MAX_LEVELS];    /* ceil(scale)+1 */
+    uint32_t offset[RSDF_MAX_LEVELS + 1]; /* entry offsets, level-major */
+} rsdf_hashgrid_meta;
+
+const char *rsdf_version(void);
+/* last launch error string for a returned code */
+const char *rsdf_error_string(int code);
+
+/* ---------------------------------------------------------------- K1: march + compaction */
+/* lib/nerfacc/cuda/csrc/intersection.cu:69-145 `ray_aabb_intersect` */
+int rsdf_ray_aabb_intersect(const float *rays_o, const float *rays_d, const float *aabb_host6,
+                            int n_rays, float *t_min, float *t_max, void *stream);
+
+/* bool[res^3] -> bit-packed uint32 words (bit i of word w = cell 32*w+i); n_cells % 32 == 0 */
+int rsdf_grid_pack_bits(const uint8_t *grid_binary, int n_cells, uint32_t *bits, void *stream);
+
+/* lib/nerfacc/cuda/csrc/ray_marching.cu:194-289 `ray_marching`, first round (count) fused
+ * with the int32 cumsum: writes packed_info[n_rays,2] = (base, count) and *total (device or
+ * pinned-host int32).  grid_bits may be NULL (then grid_binary bool[rx,ry,rz] is read).
+ * scan_tmp: int32[n_rays + (n_rays+1023)/1024 + 1] scratch. */
+int rsdf_march_count(const float *rays_o, const float *rays_d, const float *t_min,
+                     const float *t_max, const float *roi_host6, const uint8_t *grid_binary,
+                     const uint32_t *grid_bits, int rx, int ry, int rz, float step_size,
+                     float cone_angle, int n_rays, int32_t *packed_info, int32_t *scan_tmp,
+                     int32_t *total, void *stream);
+
+/* second round (fill): ray_indices int64[S], t_starts/t_ends float32[S]; capacity = S */
+int rsdf_march_fill(const float *rays_o, const float *rays_d, const float *t_min,
+                    const float *t_max, const float *roi_host6, const uint8_t *grid_binary,
+                    const uint32_t *grid_bits, int rx, int ry, int rz, float step_size,
+                    float cone_angle, int n_rays, const int32_t *packed_info,
+                    int64_t *ray_indices, float *t_starts, float *t_ends, void *stream);
+
+/* lib/nerfacc/cuda/csrc/ray_marching.cu:322-363 `grid_query` (bool grid) */
+int rsdf_grid_query(const float *samples, const float *roi_host6, const uint8_t *grid_binary,
+                    int rx, int ry, int rz, int n_samples, uint8_t *out, void *stream);
+
+/* lib/nerfacc/pack.py `pack_info`: sorted ray_indices int64[S] -> packed_info int32[n_rays,2] */
+int rsdf_pack_info(const int64_t *ray_indices, int n_samples, int n_rays, int32_t *packed_info,
+                   void *stream);
+
+/* ---------------------------------------------------------------- K4: scan + accumulate */
+/* nerfacc.render_weight_from_alpha (models/neus.py:262, models/volrend.py:851);
+ * kernels lib/nerfacc/cuda/csrc/render_weight.cu:86-154, render_transmittance.cu:85-145.
+ * weights / trans may each be NULL. */
+int rsdf_weight_from_alpha_fwd(const int32_t *packed_info, const float *alphas, int n_rays,
+                               float *weights, float *trans, void *stream);
+/* grad wrt alphas given grad_weights and/or grad_trans (either may be NULL) */
+int rsdf_weight_from_alpha_bwd(const int32_t *packed_info, const float *alphas,
+                               const float *weights, const float *trans,
+                               const float *grad_weights, const float *grad_trans, int n_rays,
+                               float *grad_alphas, void *stream);
+/* nerfacc.accumulate_along_rays (models/neus.py:265-276): out[n_rays,D] = sum_i w_i v_i.
+ * values may be NULL (D must be 1).  Deterministic (no atomics). */
+int rsdf_accumulate_fwd(const int32_t *packed_info, const float *weights, const float *values,
+                        int n_rays, int D, float *out, void *stream);
+int rsdf_accumulate_bwd(const int64_t *ray_indices, const float *weights, const float *values,
+                        const float *grad_out, int n_samples, int D, float *grad_weights,
+                        float *grad_values, void *stream);
+
+/* Fused NeuS render (models/neus.py:128-150 get_alpha + :262-277): alpha with cos-annealing,
+ * per-ray transmittance scan, accumulation of rgb[3], normal[3], opacity, depth in ONE pass.
+ * out[n_rays,8] = (rgb3, normal3 (un-normalised), opacity, depth); alpha/weights [S] saved. */
+int rsdf_neus_render_fwd(const int32_t *packed_info, const float *rays_d, const float *t_starts,
+                         const float *t_ends, const float *sdf, const float *sdf_grad,
+                         const float *rgb, const float *inv_s /* device scalar */,
+                         float cos_anneal_ratio, int n_rays, float *alpha, float *weights,
+                         float *trans, float *out, void *stream);
+/* backward of the fused render: grad_out[n_rays,8] (+ optional direct grad on weights[S])
+ * -> grad_sdf[S], grad_sdf_grad[S,3], grad_rgb[S,3], grad_inv_s_per_ray[n_rays]
+ * (caller sums; keeps the pass atomic-free and deterministic). */
+int rsdf_neus_render_bwd(const int32_t *packed_info, const float *rays_d, const float *t_starts,
+                         const float *t_ends, const float *sdf, const float *sdf_grad,
+                         const float *rgb, const float *alpha, const float *weights,
+                         const float *trans, const float *grad_out,
+                         const float *grad_weights_extra, const float *inv_s,
+                         float cos_anneal_ratio, int n_rays, float *grad_sdf,
+                         float *grad_sdf_grad, float *grad_rgb, float *grad_inv_s_per_ray,
+                         void *stream);
+
+/* ---------------------------------------------------------------- K2: hash-grid encoding */
+/* tinycudann.Encoding(3, HashGrid).forward (models/network_utils.py:50,99).
+ * x[S,3] in [0,1]; table float32[n_params]; y[S,L*F]; dy_dx[S,L*F,3] optional (NULL to skip). */
+int rsdf_hashgrid_fwd(const float *x, const float *table, const rsdf_hashgrid_meta *meta,
+                      int n_samples, float *y, float *dy_dx, void *stream);
+/* dL/dtable += scatter(dL_dy) (atomic, warp-aggregated) */
+int rsdf_hashgrid_bwd_table(const float *x, const float *dL_dy, const rsdf_hashgrid_meta *meta,
+                            int n_samples, float *grad_table, void *stream);
+/* dL/dx[S,3] = sum_f dy_dx[s,f,:] * dL_dy[s,f] */
+int rsdf_hashgrid_bwd_input(const float *dy_dx, const float *dL_dy, int n_samples, int n_out,
+                            float *dL_dx, void *stream);
+/* second order (the lib/grid_sample_grad2 role; tcnn kernel_grid_backward_input_backward_*):
+ * given v = dL/d(dL_dx) [S,3]:
+ *   grad_table  += d/dtable  <v, dy_dx^T dL_dy>          (may be NULL)
+ *   grad_dL_dy[S,L*F] = dy_dx v                           (may be NULL)
+ *   grad_x[S,3]  = d/dx <v, dy_dx^T dL_dy> (mixed partials only)  (may be NULL) */
+int rsdf_hashgrid_bwd_bwd(const float *x, const float *table, const float *v, const float *dL_dy,
+                          const rsdf_hashgrid_meta *meta, int n_samples, float *grad_table,
+                          float *grad_dL_dy, float *grad_x, void *stream);
+
+/* tinycudann.Encoding(3, SphericalHarmonics): u[S,3] in [0,1] -> out[S,degree^2] */
+int rsdf_sh_fwd(const float *u, int n_samples, int degree, float *out, void *stream);
+/* grad wrt u */
+int rsdf_sh_bwd(const float *u, const float *grad_out, int n_samples, int degree, float *grad_u,
+                void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSDF_B200_H */

@@ -1,0 +1,100 @@
+"""ctypes binding of librsdf_b200.so (the C ABI declared in include/rsdf_b200.h).
+
+There is NO fallback: if the shared library is missing or a launch fails, a RuntimeError is
+raised.  Tensors cross the boundary as raw device pointers + the current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librsdf_b200.so")
+_lib = None
+
+c_p, c_i, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+MAX_LEVELS = 32
+
+
+class HashGridMetaC(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int32), ("n_features", ctypes.c_int32),
+                ("scale", ctypes.c_float * MAX_LEVELS), ("res", ctypes.c_uint32 * MAX_LEVELS),
+                ("offset", ctypes.c_uint32 * (MAX_LEVELS + 1))]
+
+
+# name -> argtypes (restype is int for all but the two string getters)
+_SIGS = {
+    "rsdf_ray_aabb_intersect": [c_p, c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_grid_pack_bits": [c_p, c_i, c_p, c_p],
+    "rsdf_march_count": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_p, c_p, c_p, c_p],
+    "rsdf_march_fill": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_p, c_p, c_p, c_p, c_p],
+    "rsdf_grid_query": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "rsdf_pack_info": [c_p, c_i, c_i, c_p, c_p],
+    "rsdf_weight_from_alpha_fwd": [c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_weight_from_alpha_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
+    "rsdf_accumulate_fwd": [c_p, c_p, c_p, c_i, c_i, c_p, c_p],
+    "rsdf_accumulate_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "rsdf_neus_render_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_p, c_p, c_p, c_p],
+    "rsdf_neus_render_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i,
+                             c_p, c_p, c_p, c_p, c_p],
+    "rsdf_hashgrid_fwd": [c_p, c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_hashgrid_bwd_table": [c_p, c_p, c_p, c_i, c_p, c_p],
+    "rsdf_hashgrid_bwd_input": [c_p, c_p, c_i, c_i, c_p, c_p],
+    "rsdf_hashgrid_bwd_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
+    "rsdf_sh_fwd": [c_p, c_i, c_i, c_p, c_p],
+    "rsdf_sh_bwd": [c_p, c_p, c_i, c_i, c_p, c_p],
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m rise_sdf_b200.build` "
+                "(there is no CPU / PyTorch fallback for the hot path)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.rsdf_version.restype = ctypes.c_char_p
+        L.rsdf_error_string.restype = ctypes.c_char_p
+        L.rsdf_error_string.argtypes = [c_i]
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = c_i
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return ["rsdf_version", "rsdf_error_string"] + list(_SIGS)
+
+
+def ptr(t):
+    """Device pointer of a contiguous tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "rsdf ops need contiguous tensors"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed: {lib().rsdf_error_string(rc).decode()} (code {rc})")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")  # lib/nerfacc/ray_marching.py:131-132
+
+
+def host6(t):
+    """6 floats on the host (roi / aabb) as a ctypes array."""
+    vals = [float(v) for v in (t.detach().cpu().tolist() if isinstance(t, torch.Tensor) else t)]
+    return (ctypes.c_float * 6)(*vals)

@@ -1,0 +1,111 @@
+"""Host-side mirror of models/geometry.py for the render path: `VolumeSDF` (the `volume-sdf`
+geometry of both configs) with the reference's call signature
+    forward(points, with_grad=True, with_feature=True, with_laplace=False)
+(models/geometry.py:206-292).  Encoding and scan kernels come from librsdf_b200.so.
+Isosurface extraction (models/geometry.py:31-191) is out of scope.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .nerfacc import ContractionType
+from .network_utils import Config, get_encoding, get_mlp, update_module_step
+
+
+def scale_anything(dat, inp_scale, tgt_scale):
+    """models/utils.py:109-114."""
+    dat = (dat - inp_scale[0]) / (inp_scale[1] - inp_scale[0])
+    return dat * (tgt_scale[1] - tgt_scale[0]) + tgt_scale[0]
+
+
+def contract_to_unisphere(x, radius, contraction_type):
+    """models/geometry.py:17-29 (AABB branch)."""
+    if contraction_type == ContractionType.AABB:
+        return scale_anything(x, (-radius, radius), (0, 1))
+    raise NotImplementedError("unbounded contraction belongs to the learned-background branch")
+
+
+class VolumeSDF(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config = Config(config)
+        self.radius = config.radius
+        self.contraction_type = ContractionType.AABB
+        self.n_output_dims = config.feature_dim
+        self.encoding = get_encoding(3, config.xyz_encoding_config)
+        self.network = get_mlp(self.encoding.n_output_dims, self.n_output_dims, config.mlp_network_config)
+        self.grad_type = config.grad_type
+        self._finite_difference_eps = None
+        self.finite_difference_eps = config.get("finite_difference_eps", 1e-3)
+
+    def forward(self, points, with_grad=True, with_feature=True, with_laplace=False):
+        analytic = with_grad and self.grad_type == "analytic"
+        with torch.set_grad_enabled(self.training or analytic):
+            if analytic:
+                if not self.training:
+                    points = points.clone()
+                points.requires_grad_(True)
+            points_ = points
+            points = contract_to_unisphere(points, self.radius, self.contraction_type)
+            out = self.network(self.encoding(points.view(-1, 3))).view(*points.shape[:-1], self.n_output_dims).float()
+            sdf, feature = out[..., 0], out
+            if with_grad:
+                if self.grad_type == "analytic":
+                    grad = torch.autograd.grad(sdf, points_, grad_outputs=torch.ones_like(sdf),
+                                               create_graph=True, retain_graph=True, only_inputs=True)[0]
+                elif self.grad_type == "finite_difference":
+                    eps = self._finite_difference_eps
+                    offsets = torch.as_tensor([[eps, 0.0, 0.0], [-eps, 0.0, 0.0], [0.0, eps, 0.0],
+                                               [0.0, -eps, 0.0], [0.0, 0.0, eps], [0.0, 0.0, -eps]]).to(points_)
+                    points_d_ = (points_[..., None, :] + offsets).clamp(-self.radius, self.radius)
+                    points_d = scale_anything(points_d_, (-self.radius, self.radius), (0, 1))
+                    points_d_sdf = self.network(self.encoding(points_d.view(-1, 3)))[..., 0] \
+                        .view(*points.shape[:-1], 6).float()
+                    grad = 0.5 * (points_d_sdf[..., 0::2] - points_d_sdf[..., 1::2]) / eps
+                    if with_laplace:
+                        # curvature probe (models/geometry.py:246-282)
+                        eps_c = 1e-4
+                        rand_directions = F.normalize(torch.rand_like(points_), dim=-1, eps=1e-6)
+                        normal = F.normalize(grad, dim=-1, eps=1e-6)
+                        tangent = torch.cross(normal, rand_directions, dim=-1)
+                        points_t_ = points_ + eps_c * tangent
+                        if not points_t_.requires_grad:
+                            points_t_ = points_t_.requires_grad_(True)
+                        points_t = contract_to_unisphere(points_t_, self.radius, self.contraction_type)
+                        sdf_t = self.network(self.encoding(points_t.view(-1, 3)))[..., 0].view(*points.shape[:-1]).float()
+                        grad_t = torch.autograd.grad(sdf_t, points_t_, grad_outputs=torch.ones_like(sdf_t),
+                                                     create_graph=True, retain_graph=True, only_inputs=True)[0]
+                        dot = torch.sum(F.normalize(grad, dim=-1, eps=1e-6) * F.normalize(grad_t, dim=-1, eps=1e-6), dim=-1)
+                        laplace = torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / np.pi
+        rv = [sdf]
+        if with_grad:
+            rv.append(grad)
+        if with_feature:
+            rv.append(feature)
+        if with_laplace:
+            assert self.grad_type == "finite_difference", \
+                "Laplace computation is only supported with grad_type='finite_difference'"
+            rv.append(laplace)
+        rv = [v if self.training else v.detach() for v in rv]
+        return rv[0] if len(rv) == 1 else rv
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.encoding, epoch, global_step)
+        update_module_step(self.network, epoch, global_step)
+        if self.grad_type == "finite_difference":
+            if isinstance(self.finite_difference_eps, float):
+                self._finite_difference_eps = self.finite_difference_eps
+            elif self.finite_difference_eps == "progressive":
+                hg = self.config.xyz_encoding_config
+                assert hg.otype == "ProgressiveBandHashGrid"
+                level = min(hg.start_level + max(global_step - hg.start_step, 0) // hg.update_steps, hg.n_levels)
+                grid_res = hg.base_resolution * hg.per_level_scale ** (level - 1)
+                self._finite_difference_eps = 2 * self.config.radius / grid_res
+            else:
+                raise ValueError(f"Unknown finite_difference_eps={self.finite_difference_eps}")
+
+    def regularizations(self, out):
+        if "normals_orientation_loss_map" in out:
+            return {"normal_orientation": out["normals_orientation_loss_map"].mean()}
+        return {}

@@ -1,0 +1,389 @@
+"""Drop-in for the `nerfacc` (0.5.3 API) and `lib.nerfacc` (vendored 0.3.5 API) symbols that
+RISE-SDF imports on its render path, backed by librsdf_b200.so.
+
+Import sites replaced:
+    models/neus.py:11-18, models/split_mixed_occ.py:12-18, models/volrend.py:10-14,
+    models/geometry.py:14
+Reference semantics followed:
+    lib/nerfacc/ray_marching.py:14-222, lib/nerfacc/grid.py:113-294,
+    lib/nerfacc/vol_rendering.py:132-198,396-520, lib/nerfacc/intersection.py:13-49,
+    lib/nerfacc/pack.py.
+`OccGridEstimator.sampling` (nerfacc 0.5.3; source not in the reference tree) is defined as the
+in-tree 0.3.5 `ray_marching` against the estimator's own AABB with outputs squeezed to [S]
+(SURVEY.md Appendix A.5).
+"""
+from enum import Enum
+from typing import Callable, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib as L
+
+
+class ContractionType(Enum):
+    """lib/nerfacc/contraction.py; only AABB is on the hot path."""
+    AABB = 0
+    UN_BOUNDED_TANH = 1
+    UN_BOUNDED_SPHERE = 2
+
+
+# ----------------------------------------------------------------------------------------
+# marching
+# ----------------------------------------------------------------------------------------
+@torch.no_grad()
+def ray_aabb_intersect(rays_o: Tensor, rays_d: Tensor, aabb: Tensor):
+    """lib/nerfacc/intersection.py:13-49 -> (t_min, t_max); miss = (1e10, 1e10), t_min >= 0."""
+    L.require_cuda(rays_o, rays_d)
+    if isinstance(aabb, Tensor) and aabb.dim() == 2:
+        raise NotImplementedError(
+            "nerfacc>=0.5 multi-box ray_aabb_intersect is only used by the learned-background "
+            "branch (models/neus.py:164), which is out of scope")
+    rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    n = rays_o.shape[0]
+    t_min = torch.empty(n, device=rays_o.device, dtype=torch.float32)
+    t_max = torch.empty_like(t_min)
+    L.call("rsdf_ray_aabb_intersect", L.ptr(rays_o), L.ptr(rays_d), L.host6(aabb), n,
+           L.ptr(t_min), L.ptr(t_max), L.stream())
+    return t_min, t_max
+
+
+def pack_bits(grid_binary: Tensor) -> Tensor:
+    g = grid_binary.contiguous().view(torch.uint8) if grid_binary.dtype == torch.bool else grid_binary.contiguous()
+    n = g.numel()
+    assert n % 32 == 0
+    bits = torch.empty(n // 32, device=g.device, dtype=torch.int32)
+    L.call("rsdf_grid_pack_bits", L.ptr(g), n, L.ptr(bits), L.stream())
+    return bits
+
+
+@torch.no_grad()
+def _march(rays_o, rays_d, t_min, t_max, roi_host, grid_binary, grid_bits, step, cone):
+    """== _C.ray_marching (lib/nerfacc/cuda/csrc/ray_marching.cu:194-289).
+    Returns packed_info int32[R,2], ray_indices int64[S], t_starts[S], t_ends[S]."""
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    rx, ry, rz = grid_binary.shape[-3:]
+    packed = torch.empty(n, 2, device=dev, dtype=torch.int32)
+    tmp = torch.empty(n + n // 1024 + 3, device=dev, dtype=torch.int32)
+    total = torch.zeros(1, device=dev, dtype=torch.int32)
+    gb = grid_binary.view(torch.uint8) if grid_binary.dtype == torch.bool else grid_binary
+    st = L.stream()
+    L.call("rsdf_march_count", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), roi_host,
+           L.ptr(gb), L.ptr(grid_bits), rx, ry, rz, float(step), float(cone), n, L.ptr(packed),
+           L.ptr(tmp), L.ptr(total), st)
+    S = int(total.item())   # the one host sync of the march (reference: ray_marching.cu:261)
+    ri = torch.empty(S, device=dev, dtype=torch.int64)
+    ts = torch.empty(S, device=dev, dtype=torch.float32)
+    te = torch.empty(S, device=dev, dtype=torch.float32)
+    if S > 0:
+        L.call("rsdf_march_fill", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), roi_host,
+               L.ptr(gb), L.ptr(grid_bits), rx, ry, rz, float(step), float(cone), n, L.ptr(packed),
+               L.ptr(ri), L.ptr(ts), L.ptr(te), st)
+    return packed, ri, ts, te
+
+
+@torch.no_grad()
+def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
+                 t_max: Optional[Tensor] = None, scene_aabb: Optional[Tensor] = None,
+                 grid=None, sigma_fn: Optional[Callable] = None, alpha_fn: Optional[Callable] = None,
+                 early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
+                 near_plane: Optional[float] = None, far_plane: Optional[float] = None,
+                 render_step_size: float = 1e-3, stratified: bool = False, cone_angle: float = 0.0,
+                 _return_packed: bool = False):
+    """lib/nerfacc/ray_marching.py:14-222 (vendored nerfacc 0.3.5 signature).
+    Returns ray_indices int64[S], t_starts [S,1], t_ends [S,1]."""
+    L.require_cuda(rays_o, rays_d)
+    if alpha_fn is not None and sigma_fn is not None:
+        raise ValueError("Only one of `alpha_fn` and `sigma_fn` should be provided.")
+    rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    if t_min is None or t_max is None:
+        if scene_aabb is not None:
+            t_min, t_max = ray_aabb_intersect(rays_o, rays_d, scene_aabb)
+        else:
+            t_min = torch.zeros_like(rays_o[..., 0])
+            t_max = torch.ones_like(rays_o[..., 0]) * 1e10
+    if near_plane is not None:
+        t_min = torch.clamp(t_min, min=near_plane)
+    if far_plane is not None:
+        t_max = torch.clamp(t_max, max=far_plane)
+    if stratified:
+        t_min = t_min + torch.rand_like(t_min) * render_step_size
+    if grid is not None:
+        if grid.contraction_type != ContractionType.AABB:
+            raise NotImplementedError("only ContractionType.AABB is on the hot path")
+        roi_host, gbin, gbits = grid.roi_host, grid.binary, grid.bits
+    else:
+        roi_host = L.host6([-1e10] * 3 + [1e10] * 3)
+        gbin = torch.ones(1, 1, 1, dtype=torch.bool, device=rays_o.device)
+        gbits = None
+    packed, ri, ts, te = _march(rays_o, rays_d, t_min.contiguous(), t_max.contiguous(), roi_host,
+                                gbin.contiguous(), gbits, render_step_size, cone_angle)
+    ts, te = ts[:, None], te[:, None]
+    if sigma_fn is not None or alpha_fn is not None:
+        if sigma_fn is not None:
+            sigmas = sigma_fn(ts, te, ri)
+            assert sigmas.shape == ts.shape, f"sigmas must have shape of (N, 1)! Got {sigmas.shape}"
+            alphas = 1.0 - torch.exp(-sigmas * (te - ts))
+        else:
+            alphas = alpha_fn(ts, te, ri)
+            assert alphas.shape == ts.shape, f"alphas must have shape of (N, 1)! Got {alphas.shape}"
+        masks = render_visibility(alphas, packed_info=packed, early_stop_eps=early_stop_eps,
+                                  alpha_thre=alpha_thre)
+        ri, ts, te = ri[masks], ts[masks], te[masks]
+        packed = None
+    if _return_packed:
+        return ri, ts, te, packed
+    return ri, ts, te
+
+
+@torch.no_grad()
+def pack_info(ray_indices: Tensor, n_rays: int) -> Tensor:
+    """lib/nerfacc/pack.py: sorted ray_indices -> packed_info int32[n_rays, 2] (base, count)."""
+    L.require_cuda(ray_indices)
+    ri = ray_indices.contiguous().long()
+    packed = torch.empty(n_rays, 2, device=ri.device, dtype=torch.int32)
+    L.call("rsdf_pack_info", L.ptr(ri), ri.numel(), n_rays, L.ptr(packed), L.stream())
+    return packed
+
+
+# ----------------------------------------------------------------------------------------
+# scan + accumulate (autograd)
+# ----------------------------------------------------------------------------------------
+class _WeightFromAlpha(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, packed, alphas):
+        alphas = alphas.contiguous()
+        n_rays = packed.shape[0]
+        w = torch.empty_like(alphas)
+        T = torch.empty_like(alphas)
+        L.call("rsdf_weight_from_alpha_fwd", L.ptr(packed), L.ptr(alphas), n_rays, L.ptr(w), L.ptr(T),
+               L.stream())
+        ctx.save_for_backward(packed, alphas, w, T)
+        return w, T
+
+    @staticmethod
+    def backward(ctx, gw, gT):
+        packed, alphas, w, T = ctx.saved_tensors
+        gw = gw.contiguous() if gw is not None else None
+        gT = gT.contiguous() if gT is not None else None
+        ga = torch.zeros_like(alphas)
+        L.call("rsdf_weight_from_alpha_bwd", L.ptr(packed), L.ptr(alphas), L.ptr(w), L.ptr(T), L.ptr(gw),
+               L.ptr(gT), packed.shape[0], L.ptr(ga), L.stream())
+        return None, ga
+
+
+def _packed_for(ray_indices, packed_info, n_rays):
+    if packed_info is not None:
+        return packed_info.contiguous().int()
+    if n_rays is None:
+        n_rays = int(ray_indices.max()) + 1 if ray_indices.numel() else 0
+    return pack_info(ray_indices, n_rays)
+
+
+def render_weight_from_alpha(alphas: Tensor, *, packed_info: Optional[Tensor] = None,
+                             ray_indices: Optional[Tensor] = None, n_rays: Optional[int] = None):
+    """nerfacc 0.5.3 form used at models/neus.py:262, models/volrend.py:105,264,851:
+    returns (weights, trans), both shaped like `alphas`, differentiable wrt alphas."""
+    assert ray_indices is not None or packed_info is not None, \
+        "Either ray_indices or packed_info should be provided."
+    L.require_cuda(alphas)
+    shape = alphas.shape
+    if alphas.numel() == 0:
+        return alphas, alphas
+    packed = _packed_for(ray_indices, packed_info, n_rays)
+    w, T = _WeightFromAlpha.apply(packed, alphas.reshape(-1).float())
+    return w.view(shape), T.view(shape)
+
+
+def render_transmittance_from_alpha(alphas, *, packed_info=None, ray_indices=None, n_rays=None):
+    return render_weight_from_alpha(alphas, packed_info=packed_info, ray_indices=ray_indices, n_rays=n_rays)[1]
+
+
+@torch.no_grad()
+def render_visibility(alphas: Tensor, *, ray_indices: Optional[Tensor] = None,
+                      packed_info: Optional[Tensor] = None, n_rays: Optional[int] = None,
+                      early_stop_eps: float = 1e-4, alpha_thre: float = 0.0) -> Tensor:
+    """lib/nerfacc/vol_rendering.py:453-520."""
+    _, T = render_weight_from_alpha(alphas, packed_info=packed_info, ray_indices=ray_indices, n_rays=n_rays)
+    vis = T >= early_stop_eps
+    if alpha_thre > 0:
+        vis = vis & (alphas >= alpha_thre)
+    return vis.reshape(alphas.shape[0], -1)[:, 0] if alphas.dim() > 1 else vis
+
+
+class _Accumulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, packed, ray_indices, weights, values):
+        n_rays = packed.shape[0]
+        weights = weights.contiguous()
+        D = 1 if values is None else values.shape[-1]
+        if values is not None:
+            values = values.contiguous()
+        out = torch.empty(n_rays, D, device=weights.device, dtype=torch.float32)
+        L.call("rsdf_accumulate_fwd", L.ptr(packed), L.ptr(weights), L.ptr(values), n_rays, D, L.ptr(out),
+               L.stream())
+        ctx.save_for_backward(ray_indices, weights, values)
+        ctx.D = D
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        ray_indices, weights, values = ctx.saved_tensors
+        go = go.contiguous()
+        S = weights.shape[0]
+        gw = torch.empty_like(weights) if ctx.needs_input_grad[2] else None
+        gv = torch.empty_like(values) if (values is not None and ctx.needs_input_grad[3]) else None
+        if gw is not None or gv is not None:
+            L.call("rsdf_accumulate_bwd", L.ptr(ray_indices), L.ptr(weights), L.ptr(values), L.ptr(go), S,
+                   ctx.D, L.ptr(gw), L.ptr(gv), L.stream())
+        return None, None, gw, gv
+
+
+def accumulate_along_rays(weights: Tensor, values: Optional[Tensor] = None,
+                          ray_indices: Optional[Tensor] = None, n_rays: Optional[int] = None,
+                          packed_info: Optional[Tensor] = None) -> Tensor:
+    """nerfacc 0.5.3 form (models/neus.py:265-276): weights [S] (or [S,1]), values [S,D] | None
+    -> [n_rays, D|1].  Deterministic segmented reduction (no atomics)."""
+    L.require_cuda(weights)
+    assert ray_indices is not None
+    w = weights.reshape(-1).float()
+    if values is not None:
+        assert values.dim() == 2 and values.shape[0] == w.shape[0], \
+            f"Invalid shapes: {values.shape} vs {weights.shape}"
+    if w.numel() == 0:
+        assert n_rays is not None
+        return torch.zeros((n_rays, 1 if values is None else values.shape[-1]), device=weights.device)
+    ri = ray_indices.contiguous().long()
+    packed = _packed_for(ri, packed_info, n_rays)
+    return _Accumulate.apply(packed, ri, w, None if values is None else values.float())
+
+
+def render_weight_from_density(*args, **kwargs):
+    raise NotImplementedError("density rendering is only used by the learned-background branch "
+                              "(models/neus.py:195-197): out of scope (SURVEY.md §8b)")
+
+
+# ----------------------------------------------------------------------------------------
+# occupancy grid
+# ----------------------------------------------------------------------------------------
+class OccGridEstimator(nn.Module):
+    """nerfacc 0.5.3 `OccGridEstimator(roi_aabb, resolution=128)` as used at models/neus.py:75-78.
+    Buffers keep the 0.5.3 names (`aabbs[1,6]`, `occs[R^3]`, `binaries[1,R,R,R]`) so reference
+    checkpoints load; the update rule is lib/nerfacc/grid.py:196-239."""
+
+    def __init__(self, roi_aabb, resolution: int = 128, levels: int = 1):
+        super().__init__()
+        if levels != 1:
+            raise NotImplementedError("multi-level grids are not used by RISE-SDF")
+        roi_aabb = torch.as_tensor(roi_aabb, dtype=torch.float32).flatten()
+        assert roi_aabb.shape == (6,)
+        self.n_cells = int(resolution) ** 3
+        self.register_buffer("resolution", torch.tensor([resolution] * 3, dtype=torch.int32))
+        self.register_buffer("aabbs", roi_aabb[None, :].clone())
+        self.register_buffer("occs", torch.zeros(self.n_cells))
+        self.register_buffer("binaries", torch.zeros(1, resolution, resolution, resolution, dtype=torch.bool))
+        self._res = int(resolution)
+        self.roi_host = L.host6(roi_aabb)
+        self._bits = None
+        self._bits_version = -1
+        self.contraction_type = ContractionType.AABB
+
+    # 0.3.5 `Grid` surface used by lib.nerfacc.ray_marching
+    @property
+    def binary(self):
+        return self.binaries[0]
+
+    @property
+    def roi_aabb(self):
+        return self.aabbs[0]
+
+    @property
+    def bits(self):
+        key = (self.binaries.data_ptr(), self.binaries._version)
+        if self._bits is None or self._bits_version != key:
+            self._bits = pack_bits(self.binaries)
+            self._bits_version = key
+        return self._bits
+
+    def _apply(self, fn, *a, **k):
+        self._bits = None
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def sampling(self, rays_o: Tensor, rays_d: Tensor, sigma_fn: Optional[Callable] = None,
+                 alpha_fn: Optional[Callable] = None, near_plane: float = 0.0, far_plane: float = 1e10,
+                 t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
+                 render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
+                 stratified: bool = False, cone_angle: float = 0.0, _return_packed: bool = False):
+        """-> (ray_indices int64[S], t_starts[S], t_ends[S]) sorted by ray then t."""
+        def wrap(fn):
+            if fn is None:
+                return None
+            return lambda ts, te, ri: fn(ts[:, 0], te[:, 0], ri).reshape(-1, 1)
+        out = ray_marching(rays_o, rays_d, t_min=t_min, t_max=t_max, scene_aabb=self.aabbs[0], grid=self,
+                           sigma_fn=wrap(sigma_fn), alpha_fn=wrap(alpha_fn), early_stop_eps=early_stop_eps,
+                           alpha_thre=min(alpha_thre, float(self.occs.mean())) if alpha_thre > 0 else 0.0,
+                           near_plane=near_plane, far_plane=far_plane, render_step_size=render_step_size,
+                           stratified=stratified, cone_angle=cone_angle, _return_packed=True)
+        ri, ts, te, packed = out
+        if _return_packed:
+            return ri, ts[:, 0], te[:, 0], packed
+        return ri, ts[:, 0], te[:, 0]
+
+    @torch.no_grad()
+    def _update(self, step: int, occ_eval_fn: Callable, occ_thre: float = 0.01, ema_decay: float = 0.95,
+                warmup_steps: int = 256, jitter: Optional[Tensor] = None):
+        dev = self.occs.device
+        r = self._res
+        if step < warmup_steps:
+            indices = torch.arange(self.n_cells, device=dev)
+        else:
+            n = self.n_cells // 4
+            uniform = torch.randint(self.n_cells, (n,), device=dev)
+            occupied = torch.nonzero(self.binaries.flatten())[:, 0]
+            if n < len(occupied):
+                occupied = occupied[torch.randint(len(occupied), (n,), device=dev)]
+            indices = torch.cat([uniform, occupied], dim=0)
+        coords = torch.stack([indices // (r * r), (indices // r) % r, indices % r], -1).float()
+        if jitter is None:
+            jitter = torch.rand_like(coords)
+        x = (coords + jitter.to(dev)) / r
+        roi = self.aabbs[0]
+        x = x * (roi[3:] - roi[:3]) + roi[:3]
+        occ = occ_eval_fn(x).squeeze(-1)
+        self.occs[indices] = torch.maximum(self.occs[indices] * ema_decay, occ)
+        self.binaries = (self.occs > torch.clamp(self.occs.mean(), max=occ_thre)).view(self.binaries.shape)
+        self._bits = None
+
+    @torch.no_grad()
+    def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2,
+                             ema_decay: float = 0.95, warmup_steps: int = 256, n: int = 16):
+        if not self.training:
+            raise RuntimeError("You should only call this function only during training. "
+                               "Please call _update() directly if you want to update the "
+                               "field during inference.")
+        if step % n == 0 and self.training:
+            self._update(step=step, occ_eval_fn=occ_eval_fn, occ_thre=occ_thre, ema_decay=ema_decay,
+                         warmup_steps=warmup_steps)
+
+    every_n_step = update_every_n_steps   # 0.3.5 name (lib/nerfacc/grid.py:241)
+
+    @torch.no_grad()
+    def query_occ(self, samples: Tensor) -> Tensor:
+        s = samples.contiguous().float()
+        out = torch.empty(s.shape[0], device=s.device, dtype=torch.uint8)
+        g = self.binaries.contiguous().view(torch.uint8)
+        r = self._res
+        L.call("rsdf_grid_query", L.ptr(s), self.roi_host, L.ptr(g), r, r, r, s.shape[0], L.ptr(out), L.stream())
+        return out.bool()
+
+
+class OccupancyGrid(OccGridEstimator):
+    """vendored-0.3.5 name (lib/nerfacc/grid.py:113); AABB contraction only."""
+
+    def __init__(self, roi_aabb, resolution=128, contraction_type=ContractionType.AABB):
+        if contraction_type != ContractionType.AABB:
+            raise NotImplementedError("contracted (unbounded) grids belong to the learned-background "
+                                      "branch: out of scope")
+        super().__init__(roi_aabb, resolution if isinstance(resolution, int) else int(resolution[0]))

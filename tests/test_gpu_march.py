@@ -1,0 +1,142 @@
+"""K1 parity: CUDA march / AABB / pack vs the C oracle (bit-exact), the reference's own compiled
+kernel (oracle/_ref, when present) and the committed golden vectors it produced."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import march as omarch
+from oracle import ref as oref
+from rise_sdf_b200 import nerfacc as rn
+from rise_sdf_b200 import _lib as L
+from rise_sdf_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+ROI = [-1.5] * 3 + [1.5] * 3
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def special_rays():
+    o = torch.tensor([[0, 0, -4], [0.2, 0.1, -4], [0, 0, 0], [0.3, -0.2, 0.1], [5, 5, 5], [0, 0, -4],
+                      [1.5, 0, -4], [-4, 1.49999, 0.3], [0, 4, 0]], dtype=torch.float32)
+    d = torch.tensor([[0, 0, 1], [0, 0, 1], [0.6, 0.8, 0], [0, 1, 0], [0, 0, 1], [1, 0, 0],
+                      [0, 0, 1], [1, 0, 0], [0.0, -1.0, 0.0]], dtype=torch.float32)
+    return torch.cat([o, d], -1)
+
+
+def rays_for(R, seed=11):
+    rays, _, _, _ = syn.training_rays(R, seed=seed)
+    if R >= 64:
+        sp = special_rays()
+        rays[: sp.shape[0]] = sp
+    return rays
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def run_ours(rays, grid, step, use_bits=True, near=None, far=None):
+    dev = "cuda"
+    o, d = rays[:, :3].contiguous().to(dev), rays[:, 3:].contiguous().to(dev)
+    g = grid.to(dev).contiguous()
+    tmin, tmax = rn.ray_aabb_intersect(o, d, torch.tensor(ROI))
+    gb = rn.pack_bits(g) if use_bits else None
+    packed, ri, ts, te = rn._march(o, d, tmin, tmax, L.host6(ROI), g, gb, step, 0.0)
+    return [t.cpu().numpy() for t in (tmin, tmax, packed, ri, ts, te)]
+
+
+@pytest.mark.parametrize("kind", ["ball", "shell", "ones", "zeros", "voxel", "random"])
+@pytest.mark.parametrize("R", [1, 4096])
+@pytest.mark.parametrize("use_bits", [True, False])
+def test_march_bit_exact_vs_oracle(kind, R, use_bits):
+    rays = rays_for(R)
+    grid = syn.analytic_grid(kind)
+    step = 1.732 * 2 * 1.5 / (128 if kind == "ones" else 1024)
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step, use_bits)
+    o, d = rays[:, :3].numpy(), rays[:, 3:].numpy()
+    otmin, otmax = omarch.ray_aabb_intersect(o, d, np.array(ROI, np.float32))
+    assert np.array_equal(bits(tmin), bits(otmin)) and np.array_equal(bits(tmax), bits(otmax))
+    pk, ori, ots, ote = omarch.ray_marching_raw(o, d, otmin, otmax, np.array(ROI, np.float32), grid.numpy(), step)
+    assert np.array_equal(packed, pk)
+    assert np.array_equal(ri, ori)
+    assert np.array_equal(bits(ts), bits(ots)) and np.array_equal(bits(te), bits(ote))
+
+
+@pytest.mark.parametrize("kind", ["ball", "shell", "random"])
+def test_march_bit_exact_vs_reference_kernel(kind):
+    C = oref.nerfacc_cuda()
+    if C is None:
+        pytest.skip("oracle/_ref/nerfacc_cuda.so not built")
+    rays = rays_for(8192, seed=5)
+    grid = syn.analytic_grid(kind)
+    step = 1.732 * 2 * 1.5 / 1024
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step)
+    o, d = rays[:, :3].contiguous().cuda(), rays[:, 3:].contiguous().cuda()
+    roi = torch.tensor(ROI, device="cuda")
+    rtmin, rtmax = C.ray_aabb_intersect(o, d, roi)
+    assert np.array_equal(bits(tmin), bits(rtmin.cpu().numpy()))
+    assert np.array_equal(bits(tmax), bits(rtmax.cpu().numpy()))
+    rp, rri, rts, rte = C.ray_marching(o, d, rtmin, rtmax, roi, grid.cuda(), C.ContractionType.AABB, step, 0.0)
+    assert np.array_equal(packed, rp.cpu().numpy())
+    assert np.array_equal(ri, rri.cpu().numpy())
+    assert np.array_equal(bits(ts), bits(rts[:, 0].cpu().numpy()))
+    assert np.array_equal(bits(te), bits(rte[:, 0].cpu().numpy()))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "march_*.npz"))))
+def test_march_vs_golden(path):
+    z = np.load(path)
+    rays = torch.from_numpy(np.concatenate([z["rays_o"], z["rays_d"]], 1))
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, torch.from_numpy(z["grid"]), float(z["step"]))
+    assert np.array_equal(packed, z["packed_info"]) and np.array_equal(ri, z["ray_indices"])
+    assert np.array_equal(bits(ts), bits(z["t_starts"])) and np.array_equal(bits(te), bits(z["t_ends"]))
+
+
+def test_frame_sized_march_properties():
+    """640 000 rays (one 800x800 frame): size-independent properties instead of the serial oracle."""
+    rays = syn.frame_rays(3)
+    grid = syn.analytic_grid("ball")
+    step = 1.732 * 2 * 1.5 / 1024
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step)
+    assert packed[:, 1].sum() == len(ri) and packed[-1, 0] + packed[-1, 1] == len(ri)
+    assert np.all(np.diff(ri) >= 0)
+    assert np.array_equal(packed[:, 0], np.concatenate([[0], np.cumsum(packed[:-1, 1])]))
+    assert np.array_equal(np.bincount(ri, minlength=len(rays)), packed[:, 1])
+    assert np.all(te > ts)
+    mid = (ts + te) * 0.5
+    pts = rays[ri, :3].numpy() + rays[ri, 3:].numpy() * mid[:, None]
+    assert np.all(omarch.grid_query(pts[::97], np.array(ROI, np.float32), grid.numpy()))
+    # a subset of rays re-marched by the oracle must agree bit for bit
+    sub = np.arange(0, len(rays), 1601)
+    o, d = rays[sub, :3].numpy(), rays[sub, 3:].numpy()
+    pk, ori, ots, ote = omarch.ray_marching_raw(o, d, tmin[sub], tmax[sub], np.array(ROI, np.float32), grid.numpy(), step)
+    assert np.array_equal(pk[:, 1], packed[sub, 1])
+    for k, r in enumerate(sub[:200]):
+        b, n = packed[r]
+        assert np.array_equal(bits(ts[b:b + n]), bits(ots[pk[k, 0]:pk[k, 0] + n]))
+
+
+def test_sampling_api_shapes_and_empty():
+    est = rn.OccGridEstimator(torch.tensor(ROI), 128).cuda()
+    rays = rays_for(256).cuda()
+    ri, ts, te = est.sampling(rays[:, :3].contiguous(), rays[:, 3:].contiguous(), render_step_size=0.01)
+    assert ri.numel() == 0 and ts.shape == (0,) and ri.dtype == torch.int64      # empty grid -> no samples
+    est.binaries = syn.analytic_grid("ball")[None].cuda()
+    ri, ts, te = est.sampling(rays[:, :3].contiguous(), rays[:, 3:].contiguous(), render_step_size=0.01,
+                              near_plane=3.0, far_plane=4.0)
+    assert ts.dim() == 1 and ts.min() >= 3.0 and te.max() <= 4.0 + 0.02
+    pk = rn.pack_info(ri, 256).cpu().numpy()
+    assert np.array_equal(pk, omarch.pack_info(ri.cpu().numpy(), 256))
+    # alpha_fn visibility filter == oracle's
+    def alpha_fn(t0, t1, idx):
+        return torch.full_like(t0, 0.3)
+    ri2, ts2, te2 = est.sampling(rays[:, :3].contiguous(), rays[:, 3:].contiguous(), render_step_size=0.01,
+                                 alpha_fn=alpha_fn)
+    ori, ots, ote = omarch.ray_marching(rays[:, :3].cpu().numpy(), rays[:, 3:].cpu().numpy(),
+                                        scene_aabb=np.array(ROI, np.float32), grid_roi=np.array(ROI, np.float32),
+                                        grid_binary=syn.analytic_grid("ball").numpy(), render_step_size=0.01,
+                                        alpha_fn=lambda a, b, c: np.full_like(a, 0.3), near_plane=0.0, far_plane=1e10)
+    assert np.array_equal(ri2.cpu().numpy(), ori) and np.array_equal(bits(ts2.cpu().numpy()), bits(ots))

@@ -1,0 +1,102 @@
+"""End-to-end parity of the neus render (BASELINE configs[0]/[1] shapes, reduced ray counts)
+against the CPU oracle: forward images within 1e-4 relative, training-step gradients per
+parameter group within 1e-3 rel-L2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import neus as oneus
+from rise_sdf_b200 import synthetic as syn
+from rise_sdf_b200.neus import NeuSModel, neus_blender_config
+from helpers import oracle_params_from_model, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def build(table_scale=None, fused=True, seed=0):
+    torch.manual_seed(seed)
+    m = NeuSModel(neus_blender_config(), fused_render=fused).cuda()
+    if table_scale is not None:
+        with torch.no_grad():
+            m.geometry.encoding.encoding.params.uniform_(-table_scale, table_scale)
+    return m
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_cfg0_forward_uniform_samples(fused):
+    """configs[0]: all-ones grid, 128 uniform samples/ray, forward only."""
+    m = build(fused=fused).eval()
+    m.render_step_size = 1.732 * 2 * 1.5 / 128
+    m.occupancy_grid.binaries = torch.ones_like(m.occupancy_grid.binaries)
+    rays, _, _, bg = syn.training_rays(384, seed=1)
+    m.background_color = bg.cuda()
+    m.config["ray_chunk"] = 256   # exercise chunk_batch with a ragged tail
+    out = m(rays.cuda())
+    P = oracle_params_from_model(m)
+    ref = oneus.forward(P, rays, np.ones((128,) * 3, bool), m.render_step_size, 1.0, background=bg)
+    assert int(out["num_samples"].sum()) == ref["num_samples"]
+    for k in ("comp_rgb", "comp_normal", "opacity", "depth"):
+        a, b = out[k].cpu().numpy(), ref[k].detach().numpy()
+        assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1.0), k
+    assert np.abs(out["comp_rgb_full"].cpu().numpy() - ref["comp_rgb_full"].detach().numpy()).max() <= 1e-4
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_cfg1_train_step_grads(fused):
+    """configs[1] at 256 rays: occupancy-grid march, eikonal via 2nd-order grads, all losses."""
+    m = build(table_scale=0.05, fused=fused).train()
+    m.randomized = False
+    m.cos_anneal_ratio = 0.37
+    grid = syn.analytic_grid("ball")
+    m.occupancy_grid.binaries = grid[None].cuda()
+    m.render_step_size = 1.732 * 2 * 1.5 / 256
+    rays, rgb, fg, bg = syn.training_rays(256, seed=2)
+    m.background_color = bg.cuda()
+    out = m(rays.cuda())
+    loss, parts = oneus.loss({k: v for k, v in out.items()}, rgb.cuda(), fg.cuda())
+    loss.backward()
+
+    P = oracle_params_from_model(m)
+    for t in P.tensors():
+        t.requires_grad_(True)
+    ref = oneus.forward(P, rays, grid.numpy(), m.render_step_size, 0.37, background=bg, training=True,
+                        create_graph=True)
+    rloss, rparts = oneus.loss(ref, rgb, fg)
+    rloss.backward()
+    assert abs(float(loss) - float(rloss)) <= 1e-4 * abs(float(rloss))
+    for k in parts:
+        assert abs(float(parts[k]) - float(rparts[k])) <= 2e-4 * max(abs(float(rparts[k])), 1e-3), k
+    sd = dict(m.named_parameters())
+    checks = [("geometry.encoding.encoding.params", P.table), ("variance.variance", P.variance)]
+    for i, layer in enumerate(P.geo_mlp):
+        for name, t in layer.items():
+            checks.append((f"geometry.network.layers.{2 * i}.{name}", t))
+    for i, layer in enumerate(P.tex_mlp):
+        for name, t in layer.items():
+            checks.append((f"texture.network.layers.{2 * i}.{name}", t))
+    for name, t in checks:
+        g = sd[name].grad
+        assert g is not None, name
+        e = rel_l2(g.cpu().numpy(), t.grad.numpy())
+        assert e <= 1e-3, (name, e)
+
+
+def test_occupancy_update_matches_oracle():
+    """occ_eval_fn (models/neus.py:101-112) on 20k points + the EMA/threshold rule of
+    lib/nerfacc/grid.py:196-239 (warm-up branch, shared jitter) with an analytic occupancy."""
+    m = build().train()
+    P = oracle_params_from_model(m)
+    x = (torch.rand(20000, 3, generator=torch.Generator().manual_seed(4)) * 2 - 1) * 1.5
+    got = m.occ_eval_fn(x.cuda()).cpu()
+    want = oneus.occ_eval_fn(P, m.render_step_size)(x)
+    assert got.shape == (20000, 1) and float((got - want).abs().max()) <= 2e-6
+    jit = torch.rand(128 ** 3, 3, generator=torch.Generator().manual_seed(9))
+    fn = lambda p: (0.02 * torch.exp(-4.0 * (p.norm(dim=-1, keepdim=True) - 0.8).abs()))
+    for step in (0, 16):
+        m.occupancy_grid._update(step, fn, occ_thre=0.001, jitter=jit)
+    occs = torch.zeros(128 ** 3)
+    for step in (0, 16):
+        occs, binary = oneus.grid_update(occs, step, fn, [-1.5] * 3 + [1.5] * 3, occ_thre=0.001, jitter=jit)
+    assert float((m.occupancy_grid.occs.cpu() - occs).abs().max()) <= 1e-7
+    assert int((m.occupancy_grid.binaries[0].cpu() != binary).sum()) <= 4
+    assert 0.05 < float(binary.float().mean()) < 0.9
