@@ -35,7 +35,11 @@ def rays_for(R, seed=11):
 
 
 def bits(a):
-    return np.ascontiguousarray(a).view(np.uint32)
+    """bit pattern with NaNs canonicalised (0/0 on the slab planes: CPU and GPU emit different
+    NaN payloads; the value class is what the reference's comparisons see)."""
+    a = np.ascontiguousarray(a, dtype=np.float32).copy()
+    a[np.isnan(a)] = np.float32(np.nan)
+    return a.view(np.uint32)
 
 
 def run_ours(rays, grid, step, use_bits=True, near=None, far=None):
