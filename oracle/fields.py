@@ -181,19 +181,37 @@ def mlp_layers_from_state(state, prefix):
 # ----------------------------------------------------------------------------------------
 # VolumeSDF / VolumeRadiance / alpha
 # ----------------------------------------------------------------------------------------
+def cuda_scalar_div(x, s):
+    """`tensor / python_scalar` AS THE REFERENCE EXECUTES IT: the reference only ever runs on
+    CUDA, where PyTorch evaluates a float32 tensor divided by a scalar as a multiplication by
+    the float32 reciprocal (probed on the B200 box with scripts/probe_div.py: 25% of the
+    results differ from true division by one ulp, 0% from x * fl32(1/s)).  The contraction
+    `scale_anything` (models/utils.py:109-114) feeds the hash-grid cell lookup, where one ulp
+    of x01 moves the fine-level interpolation weights by ~1e-4, so the oracle follows the
+    CUDA semantics here."""
+    if x.dtype == torch.float32:
+        return x * float(np.float32(1.0) / np.float32(s))
+    return x / s
+
+
+def scale_to_unit(p, radius):
+    return cuda_scalar_div(p - (-radius), radius - (-radius)) * (1 - 0) + 0
 def sdf_field(points, table, meta, mlp, radius, level_mask=None, with_grad=True,
-              create_graph=False, include_xyz=True):
+              create_graph=False, include_xyz=True, dtype=None):
     """VolumeSDF.forward, grad_type='analytic' (models/geometry.py:206-228).
     points [S,3] world.  Returns sdf [S], grad [S,3] (d sdf / d world point), feature [S,48]."""
     p = points
     if with_grad:
         p = points.detach().clone().requires_grad_(True) if not points.requires_grad else points
-    x01 = (p - (-radius)) / (radius - (-radius))
+    # `dtype` = arithmetic type of everything downstream of the (always fp32-faithful) cell
+    # lookup; float64 gives a rounding-free yardstick for gradient comparisons.
+    dtype = dtype or points.dtype
+    x01 = cuda_scalar_div(p - (-radius), radius - (-radius))
     x01 = x01 * (1 - 0) + 0
-    enc = hash_encode(x01, table, meta)
+    enc = hash_encode(x01, table, meta, dtype=dtype)
     if level_mask is not None:
         enc = enc * level_mask
-    h = torch.cat([x01 * 2.0 + (-1.0), enc], -1) if include_xyz else enc
+    h = torch.cat([(x01 * 2.0 + (-1.0)).to(dtype), enc], -1) if include_xyz else enc
     out = vanilla_mlp(h, mlp, "softplus100")
     sdf = out[:, 0]
     if not with_grad:
@@ -206,7 +224,7 @@ def sdf_field(points, table, meta, mlp, radius, level_mask=None, with_grad=True,
 def sdf_field_fd(points, table, meta, mlp, radius, eps, level_mask=None):
     """grad_type='finite_difference' (models/geometry.py:229-244)."""
     def f(pw):
-        x01 = (pw + radius) / (2 * radius)
+        x01 = scale_to_unit(pw, radius)
         enc = hash_encode(x01, table, meta)
         if level_mask is not None:
             enc = enc * level_mask
@@ -216,7 +234,7 @@ def sdf_field_fd(points, table, meta, mlp, radius, eps, level_mask=None):
                         dtype=points.dtype)
     pd = (points[:, None, :] + offs).clamp(-radius, radius)
     sd = f(pd.view(-1, 3))[:, 0].view(-1, 6)
-    grad = 0.5 * (sd[:, 0::2] - sd[:, 1::2]) / eps
+    grad = cuda_scalar_div(0.5 * (sd[:, 0::2] - sd[:, 1::2]), eps)
     return out[:, 0], grad, out
 
 

@@ -31,6 +31,13 @@ class NeusParams:
     def inv_s(self):
         return torch.exp(self.variance * 10.0)
 
+    def to(self, dtype):
+        """Copy with every learnable tensor cast to `dtype` (leaf tensors)."""
+        cast = lambda t: t.detach().to(dtype).clone()
+        return NeusParams(cast(self.table), [{k: cast(v) for k, v in l.items()} for l in self.geo_mlp],
+                          [{k: cast(v) for k, v in l.items()} for l in self.tex_mlp], cast(self.variance),
+                          self.meta, self.radius, self.sh_degree)
+
 
 def make_params(seed=42, table_scale=1e-4, base_resolution=16, n_neurons=128, variance=0.3):
     gen = torch.Generator().manual_seed(seed)
@@ -80,7 +87,7 @@ def occ_eval_fn(P, render_step_size):
 
 
 def forward(P, rays, grid_binary, render_step_size, cos_anneal_ratio=1.0, background=None,
-            jitter=None, training=False, create_graph=False):
+            jitter=None, training=False, create_graph=False, dtype=torch.float32):
     """NeuSModel.forward_ on CPU.  rays [R,6] float32 torch tensor."""
     n_rays = rays.shape[0]
     rays_o, rays_d = rays[:, :3], rays[:, 3:6]
@@ -93,15 +100,17 @@ def forward(P, rays, grid_binary, render_step_size, cos_anneal_ratio=1.0, backgr
     t_starts, t_ends = torch.from_numpy(ts), torch.from_numpy(te)
     t_o, t_d = rays_o[ray_indices], rays_d[ray_indices]
     midpoints = (t_starts + t_ends)[:, None] / 2.0
-    positions = t_o + t_d * midpoints
-    dists = t_ends - t_starts
+    positions = t_o + t_d * midpoints          # fp32, as the product computes them
+    dists = (t_ends - t_starts).to(dtype)
+    t_d, midpoints = t_d.to(dtype), midpoints.to(dtype)
     if len(ri) == 0:
         z = torch.zeros
         out = {"comp_rgb": z(n_rays, 3), "comp_normal": z(n_rays, 3), "opacity": z(n_rays, 1),
                "depth": z(n_rays, 1), "num_samples": 0}
     else:
         sdf, sdf_grad, feature = fields.sdf_field(positions, P.table, P.meta, P.geo_mlp, P.radius,
-                                                  with_grad=True, create_graph=create_graph)
+                                                  with_grad=True, create_graph=create_graph, dtype=dtype)
+        sdf_grad = sdf_grad.to(dtype)
         normal = F.normalize(sdf_grad, p=2, dim=-1)
         alpha = fields.get_alpha(sdf, normal, t_d, dists, P.inv_s.view(1, 1), cos_anneal_ratio)
         rgb = fields.radiance(feature, t_d, normal, P.tex_mlp, P.sh_degree)
@@ -119,7 +128,7 @@ def forward(P, rays, grid_binary, render_step_size, cos_anneal_ratio=1.0, backgr
     out["rays_valid"] = out["opacity"] > 0
     out["ray_indices"], out["t_starts"], out["t_ends"] = ray_indices, t_starts, t_ends
     if background is not None:
-        out["comp_rgb_full"] = out["comp_rgb"] + background[None, :] * (1.0 - out["opacity"])
+        out["comp_rgb_full"] = out["comp_rgb"] + background[None, :].to(dtype) * (1.0 - out["opacity"])
     return out
 
 

@@ -41,9 +41,11 @@ def test_scan_forward_vs_serial_oracle():
     pk = omarch.pack_info(ri, n)
     w0, T0 = omarch.weight_from_alpha(pk, a)
     w, T = rn.render_weight_from_alpha(torch.tensor(a).cuda(), ray_indices=torch.tensor(ri).cuda(), n_rays=n)
-    # tree-ordered product vs serial product: <= 8 ulp relative, exact zeros preserved
-    np.testing.assert_allclose(T.cpu().numpy(), T0, rtol=1e-6, atol=1e-30)
-    np.testing.assert_allclose(w.cpu().numpy(), w0, rtol=1e-6, atol=1e-30)
+    # tree-ordered product vs the reference's serial product over up to 1024 factors: the two
+    # roundings differ by O(sqrt(n)) ulp -> stated tolerance 1e-5 relative, exact zeros preserved
+    np.testing.assert_allclose(T.cpu().numpy(), T0, rtol=1e-5, atol=1e-30)
+    np.testing.assert_allclose(w.cpu().numpy(), w0, rtol=1e-5, atol=1e-30)
+    assert np.array_equal(T.cpu().numpy() == 0, T0 == 0)
 
 
 def test_scan_backward_vs_oracles():
@@ -88,8 +90,8 @@ def test_scan_vs_reference_kernels():
     w_ref = C.weight_from_alpha_forward_naive(pk, at[:, None].contiguous())[:, 0]
     T_ref = C.transmittance_from_alpha_forward_naive(pk, at[:, None].contiguous())[:, 0]
     w, T = rn.render_weight_from_alpha(at, packed_info=pk)
-    np.testing.assert_allclose(w.cpu().numpy(), w_ref.cpu().numpy(), rtol=1e-6, atol=1e-30)
-    np.testing.assert_allclose(T.cpu().numpy(), T_ref.cpu().numpy(), rtol=1e-6, atol=1e-30)
+    np.testing.assert_allclose(w.cpu().numpy(), w_ref.cpu().numpy(), rtol=1e-5, atol=1e-30)
+    np.testing.assert_allclose(T.cpu().numpy(), T_ref.cpu().numpy(), rtol=1e-5, atol=1e-30)
 
 
 @pytest.mark.parametrize("D", [1, 3, 8, 24])
