@@ -82,8 +82,35 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per C-ABI entry point (for bench.py's gpu_launches count)
+LAUNCHES = {"rsdf_march_count": 4}
+STATS = {"enabled": False, "launches": 0, "timed": set(), "events": {}}
+
+
+def stats_reset(enabled=True, timed=()):
+    """bench.py hook: count launches and (for the entry points in `timed`) bracket each call with
+    CUDA events on the launching stream.  Off by default; costs nothing when disabled."""
+    STATS.update(enabled=enabled, launches=0, timed=set(timed), events={})
+
+
+def stats_times_ms():
+    """name -> (n_calls, total_ms); call after a device synchronize."""
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in STATS["events"].items()}
+
+
 def call(name, *args):
-    rc = getattr(lib(), name)(*args)
+    if STATS["enabled"]:
+        STATS["launches"] += LAUNCHES.get(name, 1)
+        if name in STATS["timed"]:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = getattr(lib(), name)(*args)
+            b.record()
+            STATS["events"].setdefault(name, []).append((a, b))
+        else:
+            rc = getattr(lib(), name)(*args)
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed: {lib().rsdf_error_string(rc).decode()} (code {rc})")
 

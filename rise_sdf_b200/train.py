@@ -1,0 +1,75 @@
+"""The training step around the render hot path: loss block of systems/neus.py:98-135
+(rgb MSE on valid rays, eikonal, mask BCE, sparsity; weights from configs/neus-blender.yaml:83-91),
+Adam with the per-group learning rates of configs/neus-blender.yaml:92-104, and -- for N>1
+GPUs -- the DDP-equivalent gradient exchange of launch.py:84-97: ONE flat fp32 bucket
+(hash table || MLPs || variance) all-reduced with NCCL and averaged.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def binary_cross_entropy(inp, target):
+    """systems/criterions.py:155-159."""
+    return -(target * torch.log(inp) + (1 - target) * torch.log(1 - inp)).mean()
+
+
+def neus_loss(out, rgb, fg_mask, lambda_rgb_mse=10.0, lambda_mask=0.1, lambda_eikonal=0.1,
+              lambda_sparsity=0.01, sparsity_scale=1.0):
+    valid = out["rays_valid_full"][..., 0]
+    loss_rgb = F.mse_loss(out["comp_rgb_full"][valid], rgb[valid])
+    loss_eik = ((torch.linalg.norm(out["sdf_grad_samples"], ord=2, dim=-1) - 1.0) ** 2).mean()
+    opacity = torch.clamp(out["opacity"].squeeze(-1), 1e-3, 1 - 1e-3)
+    loss_mask = binary_cross_entropy(opacity, fg_mask.float())
+    loss_sparse = torch.exp(-sparsity_scale * out["sdf_samples"].abs()).mean()
+    loss = (loss_rgb * lambda_rgb_mse + loss_eik * lambda_eikonal + loss_mask * lambda_mask
+            + loss_sparse * lambda_sparsity)
+    return loss, {"rgb_mse": loss_rgb, "eikonal": loss_eik, "mask": loss_mask, "sparsity": loss_sparse}
+
+
+class FlatGradBucket:
+    """All parameters' gradients as views into one contiguous fp32 buffer, so the data-parallel
+    exchange is a single NCCL all-reduce instead of DDP's 25 MB buckets."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.mul_(1.0 / dist.get_world_size())
+
+
+class NeusTrainer:
+    def __init__(self, model, lr=0.01, lr_variance=0.001):
+        self.model = model
+        groups = [
+            {"params": list(model.geometry.parameters()), "lr": lr},
+            {"params": [p for p in model.texture.parameters() if p.numel() > 0], "lr": lr},
+            {"params": list(model.variance.parameters()), "lr": lr_variance},
+        ]
+        self.bucket = FlatGradBucket([p for g in groups for p in g["params"]])
+        self.opt = torch.optim.Adam(groups, lr=lr, betas=(0.9, 0.99), eps=1e-15)
+        self.global_step = 0
+
+    def step(self, rays, rgb, fg_mask, background, optimize=True):
+        m = self.model
+        m.background_color = background
+        self.bucket.zero()
+        out = m(rays)
+        loss, parts = neus_loss(out, rgb, fg_mask)
+        loss.backward()
+        self.bucket.all_reduce_mean()
+        if optimize:
+            self.opt.step()
+        self.global_step += 1
+        return loss, out

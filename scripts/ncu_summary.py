@@ -1,0 +1,55 @@
+"""Summarise ncu outputs into small text files under profiles/ (the .ncu-rep itself is scratch).
+  python scripts/ncu_summary.py launches gpurun_out/launches_r01.csv > profiles/launches_r01.txt
+  python scripts/ncu_summary.py full gpurun_out/prof_x.ncu-rep > profiles/prof_x.txt
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "launch__registers_per_thread",
+        "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__grid_size",
+        "launch__block_size", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+        "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+        "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+        "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct"]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg, tot = collections.defaultdict(lambda: [0, 0.0]), 0.0
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        ms = v / 1e6 if row["Metric Unit"] == "ns" else (v / 1e3 if row["Metric Unit"] == "us" else v)
+        name = re.sub(r"\(.*", "", row["Kernel Name"])[:90]
+        agg[name][0] += 1
+        agg[name][1] += ms
+        tot += ms
+    print(f"# {path}: {sum(a[0] for a in agg.values())} launches, {tot:.3f} ms (serialised, cold cache: compare SHARES)")
+    for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:<92s} {n:5d} {ms:9.3f} ms {100 * ms / tot:5.1f}%")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    for r in rows[2:]:
+        print("----", r[idx["Kernel Name"]][:100])
+        for w in WANT:
+            if w in idx:
+                print(f"  {w:<72s} {r[idx[w]]} {units[idx[w]]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
