@@ -134,6 +134,15 @@ int rsdf_sh_fwd(const float *u, int n_samples, int degree, float *out, void *str
 int rsdf_sh_bwd(const float *u, const float *grad_out, int n_samples, int degree, float *grad_u,
                 void *stream);
 
+/* ---------------------------------------------------------------- K3: tensor-core MLPs */
+/* nn.Linear weight W[N][K] fp32 (models/network_utils.py:127) -> bf16 hi/lo "tile image" blob
+ * (UMMA canonical no-swizzle layout, N_pad x K_pad, multiples of 16); blob bytes = 4*N_pad*K_pad. */
+int rsdf_mlp_pack_weight(const float *W, int N, int K, int N_pad, int K_pad, void *blob, void *stream);
+/* self-test of the tcgen05 operand roles (see csrc/mlp_tc.cu); mode 0: C=A*W^T, 1: C=A*W,
+ * 2: C+=A^T*Y */
+int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *Y, float *C, int S,
+                      int d_a, int d_b, int w_rows_pad, int w_cols_pad, int grid, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
