@@ -138,6 +138,25 @@ int rsdf_sh_bwd(const float *u, const float *grad_out, int n_samples, int degree
 /* nn.Linear weight W[N][K] fp32 (models/network_utils.py:127) -> bf16 hi/lo "tile image" blob
  * (UMMA canonical no-swizzle layout, N_pad x K_pad, multiples of 16); blob bytes = 4*N_pad*K_pad. */
 int rsdf_mlp_pack_weight(const float *W, int N, int K, int N_pad, int K_pad, void *blob, void *stream);
+/* Fused forward MLP chain on tcgen05 (replaces the nn.Linear/activation launches of VanillaMLP,
+ * models/network_utils.py:122-125, in inference paths).  Activations never leave the SM. */
+#define RSDF_MLP_MAX_LAYERS 8
+typedef struct rsdf_mlp_layer {
+    const void *blob;    /* rsdf_mlp_pack_weight output (device) */
+    const float *bias;   /* [n] device, may be NULL */
+    int32_t n, n_pad, k_pad;
+    int32_t act;         /* 0 none, 1 relu, 2 softplus(beta=100, threshold 20), 3 sigmoid */
+} rsdf_mlp_layer;
+typedef struct rsdf_mlp_fwd_params {
+    int32_t n_layers, n_in, n_samples, out_w;
+    rsdf_mlp_layer layer[RSDF_MLP_MAX_LAYERS];
+    const float *in[3];       /* up to 3 row-major fp32 segments, concatenated along features */
+    int32_t in_w[3];
+    float in_scale[3], in_shift[3];   /* x*scale+shift applied while staging */
+    float *out;               /* [n_samples, out_w] */
+} rsdf_mlp_fwd_params;
+int rsdf_mlp_fwd(const rsdf_mlp_fwd_params *params_host, void *stream);
+
 /* self-test of the tcgen05 operand roles (see csrc/mlp_tc.cu); mode 0: C=A*W^T, 1: C=A*W,
  * 2: C+=A^T*Y */
 int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *Y, float *C, int S,

@@ -45,6 +45,7 @@ _SIGS = {
     "rsdf_sh_fwd": [c_p, c_i, c_i, c_p, c_p],
     "rsdf_sh_bwd": [c_p, c_p, c_i, c_i, c_p, c_p],
     "rsdf_mlp_pack_weight": [c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "rsdf_mlp_fwd": [c_p, c_p],
     "rsdf_tc_gemm_test": [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 

@@ -58,3 +58,54 @@ def test_weight_gradient_role(S, Fb):
     L.call("rsdf_tc_gemm_test", 2, L.ptr(X), None, L.ptr(Y), L.ptr(C), S, 128, Fb, 0, 0, 4, L.stream())
     torch.cuda.synchronize()
     assert err(C, X.double().cpu().T @ Y.double().cpu()) <= 3e-5
+
+
+# ------------------------------------------------------------------ fused forward MLP chain
+def _mlp(dim_in, dim_out, hidden, sphere, n_neurons=128):
+    from rise_sdf_b200.network_utils import VanillaMLP
+    torch.manual_seed(dim_in + dim_out)
+    m = VanillaMLP(dim_in, dim_out, {"n_neurons": n_neurons, "n_hidden_layers": hidden, "sphere_init": sphere,
+                                     "weight_norm": sphere, "output_activation": "none"}).cuda()
+    if sphere:
+        with torch.no_grad():
+            m.layers[0].weight_v[:, 3:].normal_(0.0, 0.05)
+    return m
+
+
+@pytest.mark.parametrize("dim_in,dim_out,hidden,sphere,S,width", [
+    (35, 48, 2, True, 5000, 128),     # geometry MLP (Softplus-100, weight-norm)
+    (67, 3, 4, False, 4097, 128),     # neus radiance MLP
+    (84, 6, 4, False, 1000, 128),     # split albedo
+    (84, 1, 2, False, 777, 128),      # split roughness
+    (73, 3, 4, False, 300, 128),      # split env
+    (35, 48, 2, True, 640, 64),       # width-64 variant named by the north star
+])
+def test_fused_mlp_forward(dim_in, dim_out, hidden, sphere, S, width):
+    from rise_sdf_b200.fused_mlp import PackedMLP
+    m = _mlp(dim_in, dim_out, hidden, sphere, width)
+    g = torch.Generator().manual_seed(S)
+    x = (torch.rand(S, dim_in, generator=g) * 2 - 1).cuda()
+    if sphere:
+        x[:, 3:] *= 0.1
+    with torch.no_grad():
+        ref = m.double()(x.double()).double().cpu() if False else None
+    m64 = _mlp(dim_in, dim_out, hidden, sphere, width).double()
+    m64.load_state_dict({k: v.double() for k, v in m.state_dict().items()})
+    with torch.no_grad():
+        h = x.double()
+        for layer in m64.layers:
+            h = layer(h)
+        ref = h.cpu()
+    out = PackedMLP(m)(x)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert float((out.double().cpu() - ref).abs().max()) <= 3e-5 * max(scale, 1.0)
+    # segmented inputs + affine staging + sigmoid output == cat + torch
+    a, b = x[:, :10].contiguous(), x[:, 10:].contiguous()
+    out2 = PackedMLP(m, out_act="sigmoid")([a, b], scales=[2.0, 1.0], shifts=[-1.0, 0.0])
+    with torch.no_grad():
+        h = torch.cat([a.double() * 2 - 1, b.double()], -1)
+        for layer in m64.layers:
+            h = layer(h)
+        ref2 = torch.sigmoid(h).cpu()
+    assert float((out2.double().cpu() - ref2).abs().max()) <= 3e-5
