@@ -134,6 +134,36 @@ int rsdf_sh_fwd(const float *u, int n_samples, int degree, float *out, void *str
 int rsdf_sh_bwd(const float *u, const float *grad_out, int n_samples, int degree, float *grad_u,
                 void *stream);
 
+/* ---------------------------------------------------------------- K5: split-sum lookups + prefilter */
+/* nvdiffrast.torch.texture(tex[1,H,W,C], uv[1,S,1,2], filter_mode='linear', boundary_mode='clamp')
+ * (models/texture.py:340: FG LUT).  C in {1,2,3}. */
+int rsdf_tex2d_fwd(const float *tex, int H, int W, int C, const float *uv, int n, float *out, void *stream);
+int rsdf_tex2d_bwd(const float *tex, int H, int W, int C, const float *uv, const float *grad_out, int n,
+                   float *grad_tex /* atomic +=, may be NULL */, float *grad_uv /* may be NULL */, void *stream);
+/* nvdiffrast.torch.texture(..., boundary_mode='cube'), filter 'linear' (n_levels == 1 or bias NULL)
+ * or 'linear-mipmap-linear' with an explicit mip stack and per-sample mip_level_bias
+ * (lib/pbr/light.py:194-206).  levels_host: HOST array of n_levels DEVICE pointers to
+ * [6,res_l,res_l,3] maps; dirs [n,3]; out [n,3]. */
+int rsdf_cube_sample_fwd(const float *const *levels_host, const int *res_host, int n_levels,
+                         const float *dirs, const float *mip_level_bias, int n, float *out, void *stream);
+/* grads: texels (atomic += into grad_levels_host[l], entries may be NULL), mip_level_bias [n],
+ * dirs [n,3] (either may be NULL) */
+int rsdf_cube_sample_bwd(const float *const *levels_host, float *const *grad_levels_host,
+                         const int *res_host, int n_levels, const float *dirs, const float *mip_level_bias,
+                         const float *grad_out, int n, float *grad_bias, float *grad_dirs, void *stream);
+/* lib/renderutils cubemap prefilter (lib/renderutils/c_src/cubemap.cu:110-350, ops.py:391-458).
+ * table: float4[6*res*res] (direction, solid angle) built by rsdf_cubemap_texel_table.
+ * transposed=0: forward; transposed=1: backward as a deterministic gather (src = grad_out). */
+int rsdf_cubemap_texel_table(int res, float *table, void *stream);
+int rsdf_diffuse_cubemap(const float *table, const float *src /* [6,res,res,3] */, int res, int transposed,
+                         float *dst /* [6,res,res,3] */, void *stream);
+/* specular_bounds(res, cutoff) -> float[6,res,res,24]; corner_scratch: float4[6*((res+15)/16+1)^2] */
+int rsdf_specular_bounds(const float *table, int res, float costheta_cutoff, float *corner_scratch,
+                         float *bounds, void *stream);
+/* forward: dst [6,res,res,4] = (sum rgb*w, sum w); backward: dst [6,res,res,3] from src = grad [6,res,res,3] */
+int rsdf_specular_cubemap(const float *table, const float *bounds, const float *src, int res, float roughness,
+                          float costheta_cutoff, int transposed, float *dst, void *stream);
+
 /* ---------------------------------------------------------------- K3: tensor-core MLPs */
 /* nn.Linear weight W[N][K] fp32 (models/network_utils.py:127) -> bf16 hi/lo "tile image" blob
  * (UMMA canonical no-swizzle layout, N_pad x K_pad, multiples of 16); blob bytes = 4*N_pad*K_pad. */

@@ -44,6 +44,14 @@ _SIGS = {
     "rsdf_hashgrid_bwd_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     "rsdf_sh_fwd": [c_p, c_i, c_i, c_p, c_p],
     "rsdf_sh_bwd": [c_p, c_p, c_i, c_i, c_p, c_p],
+    "rsdf_tex2d_fwd": [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p],
+    "rsdf_tex2d_bwd": [c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_cube_sample_fwd": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p],
+    "rsdf_cube_sample_bwd": [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_cubemap_texel_table": [c_i, c_p, c_p],
+    "rsdf_diffuse_cubemap": [c_p, c_p, c_i, c_i, c_p, c_p],
+    "rsdf_specular_bounds": [c_p, c_i, c_f, c_p, c_p, c_p],
+    "rsdf_specular_cubemap": [c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p],
     "rsdf_mlp_pack_weight": [c_p, c_i, c_i, c_i, c_i, c_p, c_p],
     "rsdf_mlp_fwd": [c_p, c_p],
     "rsdf_tc_gemm_test": [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

@@ -321,8 +321,9 @@ int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *
 }
 
 
-int rsdf_mlp_fwd(const void *params_host, void *stream) {
+int rsdf_mlp_fwd(const rsdf_mlp_fwd_params *params_host, void *stream) {
     if (!params_host) return RSDF_EBADARG;
+    static_assert(sizeof(MlpFwdParams) == sizeof(rsdf_mlp_fwd_params), "C-ABI struct mismatch");
     const MlpFwdParams &p = *reinterpret_cast<const MlpFwdParams *>(params_host);
     if (p.S == 0) return 0;
     if (p.n_layers < 1 || p.n_layers > MLP_MAX_LAYERS || p.n_in < 1 || p.n_in > 3 || !p.out) return RSDF_EBADARG;

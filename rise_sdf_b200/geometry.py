@@ -41,7 +41,10 @@ class VolumeSDF(nn.Module):
 
     def forward(self, points, with_grad=True, with_feature=True, with_laplace=False):
         analytic = with_grad and self.grad_type == "analytic"
-        with torch.set_grad_enabled(self.training or analytic):
+        # The reference enables grad whenever self.training (models/geometry.py:208), even when the
+        # caller sits under no_grad (occupancy update, sampling's alpha_fn) and the graph is thrown
+        # away.  Same numbers, no wasted graph: only build it if it can be used.
+        with torch.set_grad_enabled((self.training and torch.is_grad_enabled()) or analytic):
             if analytic:
                 if not self.training:
                     points = points.clone()

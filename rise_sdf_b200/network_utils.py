@@ -175,8 +175,16 @@ class VanillaMLP(nn.Module):
         return out
 
     def forward(self, x):
+        if x.is_cuda and not torch.is_grad_enabled() and x.dim() == 2:
+            # inference: the whole chain runs in one fused tcgen05 kernel (csrc/mlp_tc.cu)
+            if self._packed is None:
+                from .fused_mlp import PackedMLP
+                self._packed = PackedMLP(self)
+            return self.output_activation(self._packed(x))
         x = self.layers(x.float())
         return self.output_activation(x)
+
+    _packed = None
 
     def make_linear(self, dim_in, dim_out, is_first, is_last):
         layer = nn.Linear(dim_in, dim_out, bias=True)

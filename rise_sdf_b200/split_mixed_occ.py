@@ -1,0 +1,263 @@
+"""Host-side mirror of models/split_mixed_occ.py (`SplitMixedOCCModel`): split-sum PBR render of
+the neural SDF -- primary march with the alpha_fn visibility filter, 7/24-channel shading
+accumulate, reflection secondary rays, optional third bounce when relighting, normal-orientation
+regulariser and the sRGB composite (models/split_mixed_occ.py:179-456).  Callee ops run on
+librsdf_b200.so: K1 march (nerfacc.py), K2 hash grid (tinycudann.py), K3 fused MLPs in inference
+(network_utils.VanillaMLP -> fused_mlp.py), K4 scan/accumulate (nerfacc.py), K5 texture lookups and
+cube-map prefilter (nvdiffrast.py, renderutils.py, light.py).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .geometry import VolumeSDF
+from .light import EnvironmentLightMipCube, rgb_to_srgb
+from .nerfacc import ContractionType, OccGridEstimator, accumulate_along_rays
+from .network_utils import Config, update_module_step
+from .neus import VarianceNetwork, chunk_batch
+from .texture import VolumeMixedMipSplitOcc
+from .volrend import rendering_with_normals_sdf, secondary_rendering
+
+
+def split_mixed_occ_config(n_neurons=128):
+    """configs/split-mixed-occ-tensoir.yaml:29-136 as a plain dict."""
+    mlp = lambda h: {"otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none",
+                     "n_neurons": n_neurons, "n_hidden_layers": h}
+    return Config({
+        "name": "split-mixed-occ", "indirect_pred": True, "relighting_threshold": 0.3, "radius": 1.5,
+        "num_samples_per_ray": 1024, "num_samples_per_secondary_ray": 96, "train_num_rays": 256,
+        "max_train_num_rays": 4096, "grid_prune": True, "grid_prune_occ_thre": 0.001,
+        "dynamic_ray_sampling": True, "batch_image_sampling": True, "randomized": True, "ray_chunk": 4096,
+        "cos_anneal_end": 10000, "learned_background": False, "split_sum_kick_in_step": 10000,
+        "background_color": "random",
+        "variance": {"init_val": 0.3, "modulate": False},
+        "geometry": {
+            "name": "volume-sdf", "radius": 1.5, "feature_dim": 48, "grad_type": "finite_difference",
+            "finite_difference_eps": "progressive",
+            "xyz_encoding_config": {"otype": "ProgressiveBandHashGrid", "n_levels": 16, "start_level": 6,
+                                    "start_step": 6000, "update_steps": 500, "n_features_per_level": 2,
+                                    "log2_hashmap_size": 19, "base_resolution": 32,
+                                    "per_level_scale": 1.447269237440378, "include_xyz": True},
+            "mlp_network_config": {"otype": "VanillaMLP", "activation": "ReLU", "output_activation": "none",
+                                   "n_neurons": n_neurons, "n_hidden_layers": 2, "sphere_init": True,
+                                   "sphere_init_radius": 0.5, "weight_norm": True},
+        },
+        "texture": {
+            "name": "volume-mixed-mip-split-occ", "input_feature_dim": 48, "other_dim": 3, "sample_size": 8,
+            "dir_encoding_config": {"otype": "SphericalHarmonics", "degree": 5, "reflected": True},
+            "metallic_mlp_network_config": mlp(2), "albedo_mlp_network_config": mlp(4),
+            "spec_mlp_network_config": mlp(4), "roughness_mlp_network_config": mlp(2),
+            "secondary_mlp_network_config": mlp(4),
+            "xyz_encoding_config": {"otype": "VanillaFrequency", "n_frequencies": 6},
+            "color_activation": "sigmoid",
+        },
+        "light": {"name": "envlight-mip-cube",
+                  "envlight_config": {"hdr_filepath": None, "clamp": True, "nmf_format": False, "scale": 0.5,
+                                      "bias": 0.25, "base_res": 512}},
+    })
+
+
+class SplitMixedOCCModel(nn.Module):
+    def __init__(self, config, latlong=None, fg_lut=None):
+        super().__init__()
+        self.config = config = Config(config)
+        self.geometry = VolumeSDF(config.geometry)
+        self.texture = VolumeMixedMipSplitOcc(config.texture, fg_lut=fg_lut)
+        self.emitter = EnvironmentLightMipCube(config.light, latlong=latlong)
+        self.geometry.contraction_type = ContractionType.AABB
+        self.variance = VarianceNetwork(config.variance)
+        r = config.radius
+        self.register_buffer("scene_aabb", torch.as_tensor([-r, -r, -r, r, r, r], dtype=torch.float32))
+        if config.grid_prune:
+            self.occupancy_grid = OccGridEstimator(roi_aabb=self.scene_aabb, resolution=128)
+        self.randomized = config.randomized
+        self.background_color = None
+        self.render_step_size = 1.732 * 2 * config.radius / config.num_samples_per_ray
+        self.num_samples_per_secondary_ray = config.get("num_samples_per_secondary_ray", 96)
+        self.secondary_near_plane = config.get("secondary_near_plane", 0.05)
+        self.secondary_far_plane = config.get("secondary_far_plane", 1.5)
+        self.secondary_shader_chunk = config.get("secondary_shader_chunk", 160000)
+        self.cos_anneal_ratio = 1.0
+        self.stage = 0
+
+    # ------------------------------------------------------------------ schedule
+    def occ_eval_fn(self, x):
+        sdf = self.geometry(x, with_grad=False, with_feature=False)
+        inv_s = self.variance(torch.zeros([1, 3]))[:, :1].clip(1e-6, 1e6)
+        inv_s = inv_s.expand(sdf.shape[0], 1)
+        prev_cdf = torch.sigmoid((sdf[..., None] + self.render_step_size * 0.5) * inv_s)
+        next_cdf = torch.sigmoid((sdf[..., None] - self.render_step_size * 0.5) * inv_s)
+        return ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).view(-1, 1).clip(0.0, 1.0)
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.geometry, epoch, global_step)
+        update_module_step(self.texture, epoch, global_step)
+        update_module_step(self.variance, epoch, global_step)
+        cos_anneal_end = self.config.get("cos_anneal_end", 0)
+        self.cos_anneal_ratio = 1.0 if cos_anneal_end == 0 else min(1.0, global_step / cos_anneal_end)
+        if self.training and self.config.grid_prune:
+            self.occupancy_grid.update_every_n_steps(step=global_step, occ_eval_fn=self.occ_eval_fn,
+                                                     occ_thre=self.config.get("grid_prune_occ_thre", 0.01))
+        self.stage = 1 if global_step >= self.config.split_sum_kick_in_step else 0
+
+    def get_alpha(self, sdf, normal, dirs, dists):
+        """models/split_mixed_occ.py:151-177 (identical to models/neus.py:128-150)."""
+        inv_s = self.variance(torch.zeros([1, 3]))[:, :1].clip(1e-6, 1e6)
+        inv_s = inv_s.expand(sdf.shape[0], 1)
+        true_cos = (dirs * normal).sum(-1, keepdim=True)
+        iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - self.cos_anneal_ratio)
+                     + F.relu(-true_cos) * self.cos_anneal_ratio)
+        estimated_next_sdf = sdf[..., None] + iter_cos * dists.reshape(-1, 1) * 0.5
+        estimated_prev_sdf = sdf[..., None] - iter_cos * dists.reshape(-1, 1) * 0.5
+        prev_cdf = torch.sigmoid(estimated_prev_sdf * inv_s)
+        next_cdf = torch.sigmoid(estimated_next_sdf * inv_s)
+        p = prev_cdf - next_cdf
+        c = prev_cdf
+        return ((p + 1e-5) / (c + 1e-5)).view(-1).clip(0.0, 1.0)
+
+    def _alpha_fn(self, rays_o, rays_d):
+        def alpha_fn(t_starts, t_ends, ray_indices):
+            t_origins = rays_o[ray_indices]
+            t_dirs = rays_d[ray_indices]
+            positions = t_origins + t_dirs * (t_starts + t_ends)[..., None] / 2.0
+            if t_origins.shape[0] == 0:
+                return torch.zeros((0,), device=t_origins.device)
+            sdf, sdf_grad = self.geometry(positions, with_grad=True, with_feature=False)
+            normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
+            dists = (t_ends - t_starts)[..., None]
+            return self.get_alpha(sdf, normal, t_dirs, dists)
+        return alpha_fn
+
+    def compute_indirect_radiance(self, rays_o, rays_d):
+        n_rays = rays_o.shape[0]
+        alpha_fn = self._alpha_fn(rays_o, rays_d)
+        with torch.no_grad():
+            step = (self.secondary_far_plane - self.secondary_near_plane) / (self.num_samples_per_secondary_ray - 1)
+            ray_indices, t_starts, t_ends = self.occupancy_grid.sampling(
+                rays_o, rays_d, alpha_fn=alpha_fn, near_plane=self.secondary_near_plane,
+                far_plane=self.secondary_far_plane, render_step_size=step, stratified=False)
+            acc_map, depth_map, _ = secondary_rendering(t_starts, t_ends, ray_indices=ray_indices, n_rays=n_rays,
+                                                        alpha_fn=alpha_fn, chunk_size=self.secondary_shader_chunk)
+        return 1.0 - acc_map, depth_map
+
+    # ------------------------------------------------------------------ render
+    def forward_(self, rays, relighting=False):
+        n_rays = rays.shape[0]
+        rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
+        fd_train = self.config.geometry.grad_type == "finite_difference" and self.training
+        alpha_fn = self._alpha_fn(rays_o, rays_d)
+
+        def rgb_normal_alpha_fn(t_starts, t_ends, ray_indices):
+            t_origins = rays_o[ray_indices]
+            t_dirs = rays_d[ray_indices]
+            positions = t_origins + t_dirs * (t_starts + t_ends)[..., None] / 2.0
+            if fd_train:
+                sdf, sdf_grad, feature, sdf_laplace = self.geometry(positions, with_grad=True, with_feature=True,
+                                                                    with_laplace=True)
+            else:
+                sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
+            normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
+            dists = (t_ends - t_starts)[..., None]
+            alphas = self.get_alpha(sdf, normal, t_dirs, dists)
+            colors = self.texture(feature, t_dirs, normal, positions, self.emitter, self.stage)
+            if fd_train:
+                return colors, normal, alphas, sdf, sdf_grad, sdf_laplace
+            return colors, normal, alphas, sdf, sdf_grad
+
+        ray_indices, t_starts, t_ends = self.occupancy_grid.sampling(
+            rays_o, rays_d, alpha_fn=alpha_fn, render_step_size=self.render_step_size,
+            stratified=self.randomized, cone_angle=0.0, alpha_thre=0.0)
+        rgb_map, normal_map, acc_map, depth_map, extras = rendering_with_normals_sdf(
+            t_starts, t_ends, ray_indices=ray_indices, n_rays=n_rays, rgb_alpha_fn=rgb_normal_alpha_fn,
+            render_bkgd=None, has_laplace=fd_train, color_dim=7 if self.stage == 0 else 24)
+
+        valid_indices = torch.nonzero(acc_map > 0.5)[..., 0]
+        rgb_map = rgb_map.clone()      # the reference writes through slices of rgb_map in place
+        diff_rgb_map, spec_rgb_map, blend_map = rgb_map[..., :3], rgb_map[..., 3:6], rgb_map[..., 6:7]
+        if self.stage != 0:
+            diff_rgb_pbr_map, spec_rgb_pbr_map = rgb_map[..., 7:10], rgb_map[..., 10:13]
+            spec_ref_map, spec_light_map = rgb_map[..., 13:16], rgb_map[..., 16:19]
+            albedo_map, metallic_map, roughness_map = rgb_map[..., 19:22], rgb_map[..., 22:23], rgb_map[..., 23:]
+
+        if valid_indices.numel() > 0 and self.config.indirect_pred:
+            secondary_rays_o = rays_o[valid_indices] + depth_map[valid_indices] * rays_d[valid_indices]
+            wo = -rays_d[valid_indices]
+            nm = normal_map[valid_indices]
+            secondary_rays_d = 2 * torch.sum(wo * nm, dim=-1, keepdim=True) * nm - wo
+            tr, secondary_depth = self.compute_indirect_radiance(secondary_rays_o.detach().contiguous(),
+                                                                 secondary_rays_d.detach().contiguous())
+            tr = tr.clamp(0, 1).detach()
+            secondary_depth = secondary_depth.detach()
+            _, secondary_feature = self.geometry(secondary_rays_o, with_grad=False, with_feature=True)
+            secondary_rgb = self.texture.secondary_shading(secondary_feature, secondary_rays_d, nm)
+            spec_rgb_map[valid_indices] = tr * spec_rgb_map[valid_indices] + (1 - tr) * secondary_rgb
+            if self.stage != 0:
+                if not relighting:
+                    spec_rgb_pbr_map[valid_indices] = tr * spec_rgb_pbr_map[valid_indices] + (1 - tr) * secondary_rgb
+                else:
+                    roughness_mask = (roughness_map[valid_indices] <= self.config.relighting_threshold)[..., 0]
+                    third_rays_o = secondary_rays_o[roughness_mask] + secondary_depth[roughness_mask] * secondary_rays_d[roughness_mask]
+                    _, third_grad, third_feature = self.geometry(third_rays_o, with_grad=True, with_feature=True)
+                    third_normal = F.normalize(third_grad, p=2, dim=-1, eps=1e-6)
+                    third_rgb = self.texture.secondary_shading_pbr(third_feature, secondary_rays_d[roughness_mask],
+                                                                   third_normal, third_rays_o, self.emitter)
+                    slv = spec_light_map[valid_indices]
+                    slv[roughness_mask] = tr[roughness_mask] * slv[roughness_mask] + (1 - tr[roughness_mask]) * third_rgb
+                    spec_light_map[valid_indices] = slv
+                    spec_rgb_pbr_map = spec_ref_map * spec_light_map
+
+        rgb_full = diff_rgb_map + spec_rgb_map
+        out = {
+            "comp_rgb": rgb_full, "comp_diffuse_rgb": diff_rgb_map, "comp_spec_rgb": spec_rgb_map,
+            "comp_blend": blend_map, "comp_normal": normal_map, "opacity": acc_map, "depth": depth_map,
+            "rays_valid": acc_map > 0,
+            "num_samples": torch.as_tensor([len(t_starts)], dtype=torch.int32, device=rays.device),
+        }
+        if self.stage != 0:
+            rgb_pbr_map = diff_rgb_pbr_map + spec_rgb_pbr_map
+            out.update({"comp_rgb_phys": rgb_pbr_map, "comp_diffuse_rgb_phys": diff_rgb_pbr_map,
+                        "comp_spec_rgb_phys": spec_rgb_pbr_map, "comp_albedo": albedo_map,
+                        "comp_metallic": metallic_map, "comp_roughness": roughness_map})
+        if self.training:
+            weights = extras["weights"]
+            out.update({"sdf_samples": extras["sdf"], "sdf_grad_samples": extras["sdf_grad"],
+                        "weights": weights.view(-1), "ray_indices": ray_indices.view(-1)})
+            if self.config.geometry.grad_type == "finite_difference":
+                out["sdf_laplace_samples"] = extras["sdf_laplace"]
+            if ray_indices.numel() > 0:
+                orient = torch.sum(rays_d[ray_indices] * extras["normals"], dim=-1, keepdim=True).clamp(min=0)
+                out["normals_orientation_loss_map"] = accumulate_along_rays(
+                    weights, values=orient, ray_indices=ray_indices, n_rays=n_rays)
+            else:
+                out["normals_orientation_loss_map"] = torch.zeros_like(rgb_full[..., :1])
+
+        bg = self.background_color[None, :]
+        out_bg = {"comp_rgb": bg.expand(*rgb_full.shape), "num_samples": torch.zeros_like(out["num_samples"]),
+                  "rays_valid": torch.zeros_like(out["rays_valid"])}
+        out_full = {
+            "comp_rgb": rgb_to_srgb(out["comp_rgb"] + out_bg["comp_rgb"] * (1.0 - out["opacity"])).clamp(0, 1),
+            "num_samples": out["num_samples"] + out_bg["num_samples"],
+            "rays_valid": out["rays_valid"] | out_bg["rays_valid"],
+        }
+        if self.stage != 0:
+            out_bg["comp_rgb_phys"] = bg.expand(*rgb_pbr_map.shape)
+            comp = lambda x, b: rgb_to_srgb(x + b * (1.0 - out["opacity"])).clamp(0, 1)
+            out_full.update({"comp_rgb_phys": comp(out["comp_rgb_phys"], out_bg["comp_rgb_phys"]),
+                             "comp_spec_rgb": comp(out["comp_spec_rgb"], out_bg["comp_rgb"]),
+                             "comp_spec_rgb_phys": comp(out["comp_spec_rgb_phys"], out_bg["comp_rgb_phys"])})
+        return {**out, **{k + "_bg": v for k, v in out_bg.items()}, **{k + "_full": v for k, v in out_full.items()}}
+
+    def forward(self, rays, relighting=False):
+        if self.training:
+            out = self.forward_(rays, relighting=relighting)
+        else:
+            out = chunk_batch(self.forward_, self.config.ray_chunk, True, rays, relighting)
+        return {**out, "inv_s": self.variance.inv_s}
+
+    def train(self, mode=True):
+        self.randomized = mode and self.config.randomized
+        return super().train(mode=mode)
+
+    def eval(self):
+        self.randomized = False
+        return super().eval()

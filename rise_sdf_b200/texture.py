@@ -4,6 +4,7 @@
 import torch
 import torch.nn as nn
 
+from . import nvdiffrast as dr
 from .network_utils import Config, get_activation, get_encoding, get_mlp, update_module_step
 
 
@@ -29,6 +30,113 @@ class VolumeRadiance(nn.Module):
 
     def update_step(self, epoch, global_step):
         update_module_step(self.encoding, epoch, global_step)
+
+    def regularizations(self, out):
+        return {}
+
+
+class VolumeMixedMipSplitOcc(nn.Module):
+    """models/texture.py:234-434 (`volume-mixed-mip-split-occ`): five MLPs (albedo 6, roughness 1,
+    metallic 2, env 3, secondary 3) on [feature48 | VanillaFrequency(pos) 36 | SH5(dir) 25], and the
+    split-sum combine against the prefiltered env light + the 256x256 FG LUT.  Output channel order
+    of forward() is the reference's (models/texture.py:345):
+    [diff3, spec3, blend1, diff_pbr3, spec_pbr3, spec_ref3, spec_light3, albedo3, metallic1, roughness1]."""
+
+    def __init__(self, config, fg_lut=None):
+        super().__init__()
+        self.config = config = Config(config)
+        self.n_dir_dims = config.get("n_dir_dims", 3)
+        self.n_pos_dims = config.get("n_pos_dims", 3)
+        self.n_output_dims = 3
+        self.dir_encoding = get_encoding(self.n_dir_dims, config.dir_encoding_config)
+        self.xyz_encoding = get_encoding(self.n_pos_dims, config.xyz_encoding_config)
+        fdim = config.input_feature_dim
+        dn, xn = self.dir_encoding.n_output_dims, self.xyz_encoding.n_output_dims
+        self.secondary_network = get_mlp(fdim + config.other_dim + dn, 3, config.secondary_mlp_network_config)
+        self.albedo_network = get_mlp(fdim + xn, 6, config.albedo_mlp_network_config)
+        self.roughness_network = get_mlp(fdim + xn, 1, config.roughness_mlp_network_config)
+        self.env_network = get_mlp(fdim + dn, 3, config.spec_mlp_network_config)
+        self.metallic_network = get_mlp(fdim + xn, 2, config.metallic_mlp_network_config)
+        if fg_lut is None:
+            # the reference loads load/bsdf/bsdf_256_256.bin (models/texture.py:285); offline we
+            # integrate the same split-sum table synthetically (same [1,256,256,2] layout)
+            from .synthetic import bsdf_lut
+            fg_lut = bsdf_lut()
+        self.register_buffer("FG_LUT", fg_lut.float().reshape(1, 256, 256, 2).contiguous())
+
+    def _act(self, x):
+        if "color_activation" in self.config:
+            return get_activation(self.config.color_activation)(x)
+        return x
+
+    def _fg(self, NoV, roughness):
+        fg_uv = torch.cat([torch.clamp(NoV, min=0.0, max=1.0), torch.clamp(roughness, min=0.0, max=1.0)], -1)
+        pn = fg_uv.shape[0]
+        return dr.texture(self.FG_LUT, fg_uv.reshape(1, pn, 1, 2).contiguous(), filter_mode="linear",
+                          boundary_mode="clamp").reshape(pn, 2)
+
+    def forward(self, features, dirs, normals, positions, emitter, stage=0, *args):
+        if dirs.shape[0] == 0:
+            return torch.zeros((0, 3), device=dirs.device)
+        wi = -dirs
+        wo = torch.sum(wi * normals, -1, keepdim=True) * normals * 2 - wi
+        NoV = torch.sum(normals * wi, -1, keepdim=True)
+        xyz_embd = self.xyz_encoding(positions.view(-1, self.n_pos_dims))
+        network_inp = torch.cat([features.view(-1, features.shape[-1]), xyz_embd], dim=-1)
+        albedo = self.albedo_network(network_inp).view(*features.shape[:-1], 6).float()
+        diff_rgb, albedo = albedo[..., :3], albedo[..., 3:]
+        roughness = self.roughness_network(network_inp).view(*features.shape[:-1], 1).float()
+        metallic = self.metallic_network(network_inp).view(*features.shape[:-1], 2).float()
+        blend, metallic = metallic[..., :1], metallic[..., 1:]
+        wo_enc = self.dir_encoding(((wo + 1.0) / 2.0).view(-1, self.n_dir_dims))
+        spec_rgb = self.env_network(torch.cat([features, wo_enc], dim=-1)).view(*features.shape[:-1], 3).float()
+        albedo, diff_rgb, blend = self._act(albedo), self._act(diff_rgb), self._act(blend)
+        metallic, roughness, spec_rgb = self._act(metallic), self._act(roughness), self._act(spec_rgb)
+        spec_rgb = blend * spec_rgb
+        diff_rgb = (1 - blend) * diff_rgb
+        if stage == 0:
+            return torch.cat([diff_rgb, spec_rgb, blend], dim=-1)
+        diffuse_albedo = (1 - metallic) * albedo
+        diffuse_light = emitter.eval_mip(normals)
+        diff_rgb_pbr = diffuse_albedo * diffuse_light
+        specular_albedo = 0.04 * (1 - metallic) + metallic * albedo
+        specular_light = emitter.eval_mip(wo, specular=True, roughness=roughness)
+        fg_lookup = self._fg(NoV, roughness)
+        specular_ref = specular_albedo * fg_lookup[:, 0:1] + fg_lookup[:, 1:2]
+        spec_rgb_pbr = specular_ref * specular_light
+        return torch.cat([diff_rgb, spec_rgb, blend, diff_rgb_pbr, spec_rgb_pbr, specular_ref, specular_light,
+                          albedo, metallic, roughness], dim=-1)
+
+    def secondary_shading(self, features, rays_d, *args):
+        rays_d = (rays_d + 1.0) / 2.0
+        dirs_embd = self.dir_encoding(rays_d.view(-1, self.n_dir_dims))
+        network_inp = torch.cat([features.view(-1, features.shape[-1]), dirs_embd]
+                                + [arg.view(-1, arg.shape[-1]) for arg in args], dim=-1)
+        color = self.secondary_network(network_inp).view(*network_inp.shape[:-1], self.n_output_dims).float()
+        return self._act(color)
+
+    def secondary_shading_pbr(self, features, dirs, normals, positions, emitter):
+        if dirs.shape[0] == 0:
+            return torch.zeros((0, 3), device=dirs.device)
+        wi = -dirs
+        NoV = torch.sum(normals * wi, -1, keepdim=True)
+        xyz_embd = self.xyz_encoding(positions.view(-1, self.n_pos_dims))
+        network_inp = torch.cat([features.view(-1, features.shape[-1]), xyz_embd], dim=-1)
+        albedo = self.albedo_network(network_inp).view(*features.shape[:-1], 6).float()[..., 3:]
+        roughness = self.roughness_network(network_inp).view(*features.shape[:-1], 1).float()
+        metallic = self.metallic_network(network_inp).view(*features.shape[:-1], 2).float()[..., 1:]
+        albedo, metallic, roughness = self._act(albedo), self._act(metallic), self._act(roughness)
+        diffuse_albedo = (1 - metallic) * albedo
+        diff_rgb_pbr = diffuse_albedo * emitter.eval_mip(normals)
+        specular_albedo = 0.04 * (1 - metallic) + metallic * albedo
+        specular_light = emitter.eval_mip(dirs, specular=True, roughness=roughness)
+        fg_lookup = self._fg(NoV, roughness)
+        specular_ref = specular_albedo * fg_lookup[:, 0:1] + fg_lookup[:, 1:2]
+        return diff_rgb_pbr + specular_ref * specular_light
+
+    def update_step(self, epoch, global_step):
+        update_module_step(self.dir_encoding, epoch, global_step)
+        update_module_step(self.xyz_encoding, epoch, global_step)
 
     def regularizations(self, out):
         return {}
