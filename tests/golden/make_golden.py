@@ -48,3 +48,29 @@ def main(out_dir):
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden")
+
+
+def cubemap_golden(out_dir):
+    """tests/golden/cubemap_*.npz from the reference's renderutils plugin (lib/renderutils/c_src/cubemap.cu)."""
+    P = oref.renderutils_plugin()
+    assert P is not None
+    from oracle import textures as ot
+    g = torch.Generator().manual_seed(11)
+    cube = torch.rand(6, 16, 16, 3, generator=g) * 0.5 + 0.25
+    go = torch.randn(6, 16, 16, 3, generator=g)
+    d_out = P.diffuse_cubemap_fwd(cube.cuda())
+    d_g = P.diffuse_cubemap_bwd(cube.cuda(), go.cuda().contiguous())
+    rec = dict(cube16=cube.numpy(), go16=go.numpy(), diffuse_fwd=d_out.cpu().numpy(), diffuse_bwd=d_g.cpu().numpy())
+    for N, rough in [(16, 1.0), (32, 0.08)]:
+        c = torch.rand(6, N, N, 3, generator=g) * 0.5 + 0.25
+        cut = ot.ndf_cutoff(rough, 0.99)
+        b = P.specular_bounds(N, cut)
+        raw = P.specular_cubemap_fwd(c.cuda(), b, rough, cut)
+        rec.update({f"spec{N}_cube": c.numpy(), f"spec{N}_rough": np.float32(rough), f"spec{N}_cut": np.float64(cut),
+                    f"spec{N}_bounds": b.cpu().numpy().astype(np.int16), f"spec{N}_raw": raw.cpu().numpy()})
+    np.savez_compressed(os.path.join(out_dir, "cubemap_prefilter.npz"), **rec)
+    print("cubemap golden written")
+
+
+if __name__ == "__main__":
+    cubemap_golden(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden")
