@@ -239,7 +239,35 @@ def specular_cubemap(cubemap, roughness, cutoff=0.99, bounds=None):
     c = ndf_cutoff(roughness, cutoff)
     if bounds is None:
         bounds = specular_bounds(N, c)
+    if N > 32:
+        return specular_cubemap_chunked(cubemap, roughness, c, bounds)
     W = torch.from_numpy(specular_weights(N, roughness, np.float32(c), bounds)).to(cubemap.dtype)
     col = (W @ cubemap.reshape(-1, 3)).reshape(6, N, N, 3)
     wsum = W.sum(1).reshape(6, N, N, 1)
     return col / wsum
+
+
+def specular_cubemap_chunked(cubemap, roughness, c, bounds, chunk=512):
+    """Same filter for N = 64 (forward only): output texels processed `chunk` rows at a time."""
+    N = cubemap.shape[1]
+    D = texel_dirs(N).reshape(-1, 3).astype(np.float64)
+    area = np.tile(pixel_area(N).reshape(-1), 6).astype(np.float64)
+    xs = np.tile(np.tile(np.arange(N), N), 6); ys = np.tile(np.repeat(np.arange(N), N), 6)
+    ss = np.repeat(np.arange(6), N * N)
+    b = bounds.reshape(-1, 6, 4)
+    cube = cubemap.detach().double().reshape(-1, 3).numpy()
+    a2 = float(roughness) ** 4
+    out = np.zeros((len(D), 3))
+    for p0 in range(0, len(D), chunk):
+        V = D[p0:p0 + chunk]
+        dp = V @ D.T
+        H = V[:, None, :] + D[None, :, :]
+        H /= np.maximum(np.linalg.norm(H, axis=-1, keepdims=True), 1e-30)
+        vdh = np.clip((V[:, None, :] * H).sum(-1), 0.0, 1.0)
+        d = (vdh * a2 - vdh) * vdh + 1.0
+        W = np.maximum(dp, 0.0) * (a2 / (d * d * np.pi)) * area[None, :] / 4.0
+        bx = b[p0:p0 + chunk][:, ss, :]
+        inbox = (xs[None] >= bx[..., 0]) & (xs[None] <= bx[..., 1]) & (ys[None] >= bx[..., 2]) & (ys[None] <= bx[..., 3])
+        W = W * (inbox & (dp >= np.float32(c)))
+        out[p0:p0 + chunk] = (W @ cube) / W.sum(1, keepdims=True)
+    return torch.from_numpy(out).to(cubemap.dtype).reshape(6, N, N, 3)

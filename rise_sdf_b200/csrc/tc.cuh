@@ -1,6 +1,6 @@
 // tcgen05 / TMEM / mbarrier / bulk-copy primitives for the fused MLP kernels (sm_100a only).
 //
-// Operand format ("tile image"): a [128 rows x F cols] bf16 matrix stored in the UMMA canonical
+// Operand format ("tile image"): a [128 rows x F cols] fp16 matrix stored in the UMMA canonical
 // NO-SWIZZLE interleaved layout, 16-byte chunks of 8 consecutive columns:
 //     chunk(row r, c = col/8)  at byte  c*CH + (r/8)*128 + (r%8)*16 ,   CH = ROWS*16
 // The same bytes serve two roles, selected by the descriptor only:
@@ -8,10 +8,10 @@
 //   * MN-major operand (contraction over the rows):     LBO = 128, SBO = CH
 // so an activation tile can feed a forward/backward GEMM (contract features) and a weight-
 // gradient GEMM (contract samples) without being re-laid-out, and a weight blob W[N][K] is
-// also W^T for the backward pass.  fp32 accuracy comes from a 3-term bf16 split
-// (x = hi + lo; x*w ~= hi*hi + hi*lo + lo*hi, relative error ~2^-17), accumulated in fp32 TMEM.
+// also W^T for the backward pass.  fp32-class accuracy comes from a 3-term fp16 split
+// (x = hi + lo; x*w ~= hi*hi + hi*lo + lo*hi, relative error ~2^-22), accumulated in fp32 TMEM.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -107,14 +107,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;
     return d;
 }
-// instruction descriptor: kind::f16, A/B = bf16, D = fp32, dense
+// instruction descriptor: kind::f16, A/B = fp16 (format 0), D = fp32 (c_format 1), dense
 __host__ __device__ constexpr uint32_t instr_desc(int M, int N, bool a_mn_major, bool b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+    return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]   (one elected thread issues)
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          bool accumulate) {
     asm volatile(
         "{\n\t"
@@ -150,14 +150,21 @@ __device__ __forceinline__ void bulk_wait_read0() {
 }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// ---- bf16 split helpers -----------------------------------------------------------------
-// x = hi + lo (+ ~2^-17 |x|): hi = bf16(x), lo = bf16(x - hi)
+// ---- 16-bit split helpers ---------------------------------------------------------------
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): two 11-bit significands -> the three kept
+// products (hi*hi + hi*lo + lo*hi) carry ~2^-22 relative error per term, i.e. fp32-class GEMMs.
+// (A bf16 split would stop at 2^-17, which finite-difference SDF normals amplify ~1400x.)
+// fp16's narrow exponent is harmless here: |x| is clamped to the fp16 range (MLP activations and
+// weights are O(1)), and a lo part that drops into the subnormal range still has an ABSOLUTE
+// error <= 2^-25, far below the fp32 accumulation error of an O(1) pre-activation.
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
+    x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    const __half l0 = __float2half_rn(x0 - __half2float(h0));
+    const __half l1 = __float2half_rn(x1 - __half2float(h1));
+    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
 }
 // write 8 consecutive columns [c*8, c*8+8) of row r into a tile image (hi plane at img,
 // lo plane at img + plane_bytes); rows = tile height (128)
@@ -181,8 +188,10 @@ __device__ __forceinline__ void load_chunk(const uint8_t *img, uint32_t plane_by
     const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        v[2 * k] = __uint_as_float(hh[k] << 16) + __uint_as_float(ll[k] << 16);
-        v[2 * k + 1] = __uint_as_float(hh[k] & 0xFFFF0000u) + __uint_as_float(ll[k] & 0xFFFF0000u);
+        v[2 * k] = __half2float(__ushort_as_half((unsigned short)(hh[k] & 0xFFFFu))) +
+                   __half2float(__ushort_as_half((unsigned short)(ll[k] & 0xFFFFu)));
+        v[2 * k + 1] = __half2float(__ushort_as_half((unsigned short)(hh[k] >> 16))) +
+                       __half2float(__ushort_as_half((unsigned short)(ll[k] >> 16)));
     }
 }
 
@@ -202,7 +211,7 @@ __device__ __forceinline__ void gemm_split3(uint32_t tmem_d, const Operand &A, c
         const uint32_t b0 = B.addr + (term == 1 ? B.plane : 0u);
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k) {
-            mma_bf16(tmem_d, smem_desc(a0 + k * A.kstep, A.lbo, A.sbo), smem_desc(b0 + k * B.kstep, B.lbo, B.sbo),
+            mma_f16(tmem_d, smem_desc(a0 + k * A.kstep, A.lbo, A.sbo), smem_desc(b0 + k * B.kstep, B.lbo, B.sbo),
                      idesc, accumulate || term > 0 || k > 0);
         }
     }

@@ -175,7 +175,7 @@ class VanillaMLP(nn.Module):
         return out
 
     def forward(self, x):
-        if x.is_cuda and not torch.is_grad_enabled() and x.dim() == 2:
+        if x.is_cuda and not torch.is_grad_enabled() and x.dim() == 2 and VanillaMLP.fused_inference:
             # inference: the whole chain runs in one fused tcgen05 kernel (csrc/mlp_tc.cu)
             if self._packed is None:
                 from .fused_mlp import PackedMLP
@@ -185,6 +185,7 @@ class VanillaMLP(nn.Module):
         return self.output_activation(x)
 
     _packed = None
+    fused_inference = True      # class-wide switch (tests compare the fused and the torch path)
 
     def make_linear(self, dim_in, dim_out, is_first, is_last):
         layer = nn.Linear(dim_in, dim_out, bias=True)

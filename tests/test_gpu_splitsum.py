@@ -143,3 +143,81 @@ def test_specular_cubemap_vs_reference(N, roughness):
         (ref * go.double()).sum().backward()
         assert float((out.detach().cpu() - ref.detach()).abs().max()) <= 2e-5 * float(ref.abs().max())
         assert float((cc.grad.cpu() - c0.grad).abs().max()) <= 1e-4 * float(c0.grad.abs().max())
+
+
+# ------------------------------------------------------------------ end-to-end split-sum render
+def _split_model(base_res=64):
+    from rise_sdf_b200.split_mixed_occ import SplitMixedOCCModel, split_mixed_occ_config
+    torch.manual_seed(0)
+    cfg = split_mixed_occ_config()
+    cfg["light"]["envlight_config"]["base_res"] = base_res
+    m = SplitMixedOCCModel(cfg).cuda()
+    with torch.no_grad():
+        m.geometry.network.layers[0].weight_v[:, 3:].normal_(0.0, 0.05)
+        m.variance.variance.fill_(0.5)
+        m.geometry.encoding.encoding.encoding.params.uniform_(-0.02, 0.02)
+    return m
+
+
+@pytest.mark.parametrize("relighting", [False, True])
+def test_split_sum_render_vs_oracle(relighting):
+    """configs[2]/[3] shape at 192 rays, stage 1 (+ third bounce when relighting), eval mode
+    (fused tcgen05 MLPs).  Finite-difference normals amplify every rounding of the SDF MLP by
+    1/(2 eps) ~ 1400x and the reflection bounce starts AT the surface, so the tolerances are the
+    measured fp32-vs-fp32 noise floor of this configuration (scripts/diag_split2.py), not 1e-4:
+    geometry/material channels <= 1e-3, colour channels 99% of rays <= 1e-2 and mean <= 1e-3."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    from helpers import split_oracle_params
+    from oracle import split as osplit
+    from rise_sdf_b200 import synthetic as syn
+    m = _split_model().eval()
+    m.update_step(0, 20000)
+    assert m.stage == 1
+    with torch.no_grad():
+        m.emitter.build_mips()
+    rays, _, _, bg = syn.training_rays(192, seed=3)
+    m.background_color = bg.cuda()
+    grid = syn.analytic_grid("ball")
+    m.occupancy_grid.binaries = grid[None].cuda()
+    m.render_step_size = 1.732 * 2 * 1.5 / 256
+    with torch.no_grad():
+        out = m(rays.cuda(), relighting=relighting)
+    P = split_oracle_params(m)
+    osplit.build_mips(P)
+    for a, b, tol in zip(m.emitter.specular, P.specular, (2e-3, 1e-5, 1e-5)):
+        assert float((a.detach().cpu() - b).abs().max()) <= tol     # level 0: fp32 NDF cancellation (see oracle test)
+    assert float((m.emitter.diffuse.detach().cpu() - P.diffuse).abs().max()) <= 1e-5
+    P.specular = [t.detach().cpu() for t in m.emitter.specular]
+    ref = osplit.forward(P, rays, grid.numpy(), m.render_step_size, stage=1, relighting=relighting, background=bg)
+    assert abs(int(out["num_samples"].sum()) - ref["num_samples"]) <= 2
+    for k in ("comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic"):
+        e = (out[k].cpu() - ref[k]).abs()
+        assert float(e.max()) <= 1e-3 * max(float(ref[k].abs().max()), 1.0), (k, float(e.max()))
+    for k in ("comp_rgb", "comp_rgb_phys", "comp_rgb_full", "comp_rgb_phys_full"):
+        e = (out[k].cpu() - ref[k]).abs().max(-1).values
+        assert float(e.mean()) <= 1e-3 and float(torch.quantile(e, 0.99)) <= 2e-2, (k, float(e.mean()), float(e.max()))
+    assert out["comp_rgb_phys"].shape == (192, 3) and out["comp_rgb_full"].min() >= 0 and out["comp_rgb_full"].max() <= 1
+
+
+def test_split_sum_training_step_runs_and_reaches_every_parameter_group():
+    from rise_sdf_b200 import synthetic as syn
+    m = _split_model().train()
+    m.update_step(0, 20000)
+    m.randomized = False
+    m.emitter.build_mips()
+    rays, rgb, _, bg = syn.training_rays(256, seed=4)
+    m.background_color = bg.cuda()
+    m.occupancy_grid.binaries = syn.analytic_grid("ball")[None].cuda()
+    m.render_step_size = 1.732 * 2 * 1.5 / 256
+    out = m(rays.cuda())
+    loss = ((out["comp_rgb_full"] - rgb.cuda()) ** 2).mean() + ((out["comp_rgb_phys_full"] - rgb.cuda()) ** 2).mean() \
+        + 0.1 * ((out["sdf_grad_samples"].norm(dim=-1) - 1) ** 2).mean() + 0.01 * out["sdf_laplace_samples"].mean() \
+        + out["normals_orientation_loss_map"].mean()
+    loss.backward()
+    for name in ("geometry.encoding.encoding.encoding.params", "emitter.base", "variance.variance",
+                 "texture.albedo_network.layers.0.weight", "texture.roughness_network.layers.0.weight",
+                 "texture.env_network.layers.0.weight", "texture.metallic_network.layers.0.weight",
+                 "texture.secondary_network.layers.0.weight", "geometry.network.layers.0.weight_v"):
+        g = dict(m.named_parameters())[name].grad
+        assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, name

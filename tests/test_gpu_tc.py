@@ -1,5 +1,5 @@
 """tcgen05 building blocks: every operand role the fused MLP kernels use, checked against
-fp64 matmul.  The 3-term bf16 split must deliver ~fp32 accuracy (<= 3e-5 of the row scale)."""
+fp64 matmul.  The 3-term bf16 split must deliver ~fp32 accuracy (<= 2e-6 of the row scale)."""
 import numpy as np
 import pytest
 import torch
@@ -32,7 +32,7 @@ def test_linear_forward_role(S, K, N):
     C = torch.full((S, N), float("nan"), device="cuda")
     L.call("rsdf_tc_gemm_test", 0, L.ptr(A), L.ptr(pack(W)), None, L.ptr(C), S, K, N, pad16(N), pad16(K), 8, L.stream())
     torch.cuda.synchronize()
-    assert err(C, A.double().cpu() @ W.double().cpu().T) <= 3e-5
+    assert err(C, A.double().cpu() @ W.double().cpu().T) <= 2e-6
 
 
 @pytest.mark.parametrize("S,K,N", [(128, 128, 128), (777, 35, 128), (640, 128, 48)])
@@ -44,7 +44,7 @@ def test_transposed_weight_role(S, K, N):
     C = torch.full((S, K), float("nan"), device="cuda")
     L.call("rsdf_tc_gemm_test", 1, L.ptr(G), L.ptr(pack(W)), None, L.ptr(C), S, N, K, pad16(N), pad16(K), 8, L.stream())
     torch.cuda.synchronize()
-    assert err(C, G.double().cpu() @ W.double().cpu()) <= 3e-5
+    assert err(C, G.double().cpu() @ W.double().cpu()) <= 2e-6
 
 
 @pytest.mark.parametrize("S,Fb", [(128, 128), (1000, 48), (5000, 80), (3000, 16)])
@@ -57,7 +57,7 @@ def test_weight_gradient_role(S, Fb):
     C = torch.zeros(128, Fb, device="cuda")
     L.call("rsdf_tc_gemm_test", 2, L.ptr(X), None, L.ptr(Y), L.ptr(C), S, 128, Fb, 0, 0, 4, L.stream())
     torch.cuda.synchronize()
-    assert err(C, X.double().cpu().T @ Y.double().cpu()) <= 3e-5
+    assert err(C, X.double().cpu().T @ Y.double().cpu()) <= 1e-5   # fp32 accumulation over up to 40 tiles
 
 
 # ------------------------------------------------------------------ fused forward MLP chain
@@ -99,7 +99,7 @@ def test_fused_mlp_forward(dim_in, dim_out, hidden, sphere, S, width):
     out = PackedMLP(m)(x)
     torch.cuda.synchronize()
     scale = float(ref.abs().max())
-    assert float((out.double().cpu() - ref).abs().max()) <= 3e-5 * max(scale, 1.0)
+    assert float((out.double().cpu() - ref).abs().max()) <= 2e-6 * max(scale, 1.0)
     # segmented inputs + affine staging + sigmoid output == cat + torch
     a, b = x[:, :10].contiguous(), x[:, 10:].contiguous()
     out2 = PackedMLP(m, out_act="sigmoid")([a, b], scales=[2.0, 1.0], shifts=[-1.0, 0.0])
@@ -108,4 +108,4 @@ def test_fused_mlp_forward(dim_in, dim_out, hidden, sphere, S, width):
         for layer in m64.layers:
             h = layer(h)
         ref2 = torch.sigmoid(h).cpu()
-    assert float((out2.double().cpu() - ref2).abs().max()) <= 3e-5
+    assert float((out2.double().cpu() - ref2).abs().max()) <= 2e-6
