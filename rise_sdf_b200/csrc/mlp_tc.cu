@@ -152,149 +152,6 @@ tc_gemm_test_kernel(int mode, const float *__restrict__ A, const uint8_t *__rest
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// Fused forward MLP chain:  out = act_L( ... act_1( cat(in0,in1,in2) W_1^T + b_1 ) ... W_L^T + b_L )
-// One persistent CTA per SM, 128 threads, thread t owns sample row t of the current 128-sample
-// tile.  The activation tile lives in shared memory as a bf16 hi/lo tile image and is updated IN
-// PLACE by each layer's epilogue (the layer's MMAs have drained by then); the accumulator lives in
-// TMEM; layer weights stream L2 -> smem through a 2-deep ring of bulk async copies so layer l+1's
-// blob lands while layer l computes.  No activation ever touches HBM between layers.
-// ---------------------------------------------------------------------------------------------
-constexpr int MLP_MAX_LAYERS = 8;
-struct MlpLayerDesc {
-    const uint8_t *blob;   // hi plane | lo plane, n_pad x k_pad
-    const float *bias;     // [n] or null
-    int n, n_pad, k_pad, act;   // act: 0 none, 1 relu, 2 softplus(beta=100), 3 sigmoid
-};
-struct MlpFwdParams {
-    int n_layers, n_in, S, out_w;
-    MlpLayerDesc layer[MLP_MAX_LAYERS];
-    const float *in[3];
-    int in_w[3];
-    float in_scale[3], in_shift[3];   // affine applied while staging (e.g. 2*x-1)
-    float *out;
-};
-
-__device__ __forceinline__ float act_apply(float z, int act) {
-    if (act == 1) return fmaxf(z, 0.0f);
-    if (act == 2) { const float t = 100.0f * z; return t > 20.0f ? z : log1pf(expf(t)) * 0.01f; }
-    if (act == 3) return 1.0f / (1.0f + expf(-z));
-    return z;
-}
-
-struct MlpSmem {
-    uint64_t bar_w[2], bar_mma;
-    uint32_t tmem_slot;
-};
-
-__global__ void __launch_bounds__(128, 1) mlp_fwd_kernel(const MlpFwdParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *a_img = smem;                       // 64 KB
-    uint8_t *w_img[2] = {smem + 65536, smem + 131072};
-    MlpSmem *sm = reinterpret_cast<MlpSmem *>(smem + 196608);
-    const int tid = threadIdx.x, warp = tid >> 5;
-
-    if (tid == 0) {
-        tc::mbar_init(&sm->bar_w[0], 1);
-        tc::mbar_init(&sm->bar_w[1], 1);
-        tc::mbar_init(&sm->bar_mma, 1);
-        tc::mbar_fence_init();
-    }
-    if (warp == 0) tc::tmem_alloc(&sm->tmem_slot, 128);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem = sm->tmem_slot;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-
-    const int n_tiles = (p.S + TM - 1) / TM;
-    const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int total_jobs = my_tiles * p.n_layers;      // (tile, layer) pairs this CTA runs
-    uint32_t w_phase[2] = {0, 0}, mma_phase = 0;
-
-    auto issue_w = [&](int job) {     // thread 0 only
-        const MlpLayerDesc &L = p.layer[job % p.n_layers];
-        const uint32_t bytes = 4u * (uint32_t)L.n_pad * (uint32_t)L.k_pad;
-        tc::mbar_expect_tx(&sm->bar_w[job & 1], bytes);
-        tc::bulk_g2s(w_img[job & 1], L.blob, bytes, &sm->bar_w[job & 1]);
-    };
-    if (tid == 0 && total_jobs > 0) issue_w(0);
-
-    int job = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int s = tile * TM + tid;
-        // ---- stage the input row (concatenated segments) as a tile image -----------------------
-        {
-            const int k_pad0 = p.layer[0].k_pad;
-            const uint32_t plane = TM * k_pad0 * 2;
-            for (int c = 0; c < k_pad0 / 8; ++c) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    int k = c * 8 + j;
-                    float x = 0.0f;
-                    if (s < p.S) {
-#pragma unroll
-                        for (int g = 0; g < 3; ++g) {
-                            if (g < p.n_in) {
-                                if (k >= 0 && k < p.in_w[g])
-                                    x = fmaf(__ldg(p.in[g] + (size_t)s * p.in_w[g] + k), p.in_scale[g], p.in_shift[g]);
-                                k -= p.in_w[g];
-                            }
-                        }
-                    }
-                    v[j] = x;
-                }
-                tc::store_chunk(a_img, plane, TM, tid, c, v);
-            }
-        }
-        for (int l = 0; l < p.n_layers; ++l, ++job) {
-            const MlpLayerDesc &L = p.layer[l];
-            tc::fence_async_smem();
-            __syncthreads();                       // A image complete; previous epilogue's TMEM reads done
-            if (tid == 0) {
-                tc::mbar_wait(&sm->bar_w[job & 1], w_phase[job & 1]);
-                tc::tc_fence_after();
-                const uint32_t idesc = tc::instr_desc(128, L.n_pad, false, false);
-                tc::gemm_split3(tmem, tc::op_kmajor(tc::smem_u32(a_img), TM * L.k_pad * 2, TM),
-                                tc::op_kmajor(tc::smem_u32(w_img[job & 1]), (uint32_t)L.n_pad * L.k_pad * 2, L.n_pad),
-                                L.k_pad / 16, idesc, false);
-                tc::mma_commit(&sm->bar_mma);
-                if (job + 1 < total_jobs) issue_w(job + 1);   // other ring slot: its last reader has drained
-            }
-            w_phase[job & 1] ^= (tid == 0) ? 1u : 0u;
-            tc::mbar_wait(&sm->bar_mma, mma_phase);
-            mma_phase ^= 1;
-            tc::tc_fence_after();
-            // ---- epilogue: bias + activation; next layer's A image (in place) or the output ----
-            const bool last = (l == p.n_layers - 1);
-            const uint32_t next_plane = last ? 0u : TM * L.n_pad * 2;
-            for (int c0 = 0; c0 < L.n_pad; c0 += 16) {
-                float v[16];
-                tc::tmem_ld16(tmem + lane_base + c0, v);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = c0 + j;
-                    const float b = (L.bias && n < L.n) ? __ldg(L.bias + n) : 0.0f;
-                    v[j] = n < L.n ? act_apply(v[j] + b, L.act) : 0.0f;
-                }
-                if (!last) {
-                    tc::store_chunk(a_img, next_plane, TM, tid, c0 / 8, v);
-                    tc::store_chunk(a_img, next_plane, TM, tid, c0 / 8 + 1, v + 8);
-                } else if (s < p.S) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < p.out_w) p.out[(size_t)s * p.out_w + c0 + j] = v[j];
-                }
-            }
-            tc::tc_fence_before();
-        }
-    }
-    __syncthreads();
-    if (warp == 0) tc::tmem_free(tmem, 128);
-}
-
 }  // namespace
 
 extern "C" {
@@ -321,29 +178,5 @@ int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *
 }
 
 
-int rsdf_mlp_fwd(const rsdf_mlp_fwd_params *params_host, void *stream) {
-    if (!params_host) return RSDF_EBADARG;
-    static_assert(sizeof(MlpFwdParams) == sizeof(rsdf_mlp_fwd_params), "C-ABI struct mismatch");
-    const MlpFwdParams &p = *reinterpret_cast<const MlpFwdParams *>(params_host);
-    if (p.S == 0) return 0;
-    if (p.n_layers < 1 || p.n_layers > MLP_MAX_LAYERS || p.n_in < 1 || p.n_in > 3 || !p.out) return RSDF_EBADARG;
-    int kin = 0;
-    for (int g = 0; g < p.n_in; ++g) kin += p.in_w[g];
-    if (kin > p.layer[0].k_pad) return RSDF_EBADARG;
-    for (int l = 0; l < p.n_layers; ++l) {
-        const MlpLayerDesc &L = p.layer[l];
-        if (!L.blob || L.n_pad % 16 || L.k_pad % 16 || L.n_pad > 128 || L.k_pad > 128 || L.n > L.n_pad) return RSDF_EBADARG;
-        if (l > 0 && L.k_pad != p.layer[l - 1].n_pad) return RSDF_EBADARG;
-    }
-    if (p.out_w > p.layer[p.n_layers - 1].n_pad) return RSDF_EBADARG;
-    const size_t sm = 196608 + 64;
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return (int)e;
-    const int n_tiles = (p.S + TM - 1) / TM;
-    const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
-    mlp_fwd_kernel<<<grid, 128, sm, (cudaStream_t)stream>>>(p);
-    RSDF_LAUNCH_CHECK();
-    return 0;
-}
 
 }  // extern "C"

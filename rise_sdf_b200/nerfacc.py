@@ -205,6 +205,8 @@ def render_visibility(alphas: Tensor, *, ray_indices: Optional[Tensor] = None,
                       packed_info: Optional[Tensor] = None, n_rays: Optional[int] = None,
                       early_stop_eps: float = 1e-4, alpha_thre: float = 0.0) -> Tensor:
     """lib/nerfacc/vol_rendering.py:453-520."""
+    if alphas.numel() == 0:
+        return torch.zeros(0, dtype=torch.bool, device=alphas.device)
     _, T = render_weight_from_alpha(alphas, packed_info=packed_info, ray_indices=ray_indices, n_rays=n_rays)
     vis = T >= early_stop_eps
     if alpha_thre > 0:

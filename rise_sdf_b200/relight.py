@@ -1,0 +1,53 @@
+"""Relighting render (BASELINE configs[3]; systems/split_occ.py:331-458): 800x800 frames of a
+split-sum model under new environment maps, pixels sharded across GPUs with NO communication
+(SURVEY.md §8e): the frame is cut into `tile`-ray tiles dealt round-robin to ranks (the object
+is centred, so row blocks would be imbalanced); every rank holds the full model, occupancy grid,
+prefiltered mip pyramids and LUT, renders its tiles and keeps the result sharded (an optional
+all_gather assembles the frame)."""
+import torch
+
+from . import synthetic as syn
+from .light import blender_latlong_to_cubemap
+
+
+class EnvSet:
+    """Prefiltered pyramids for a list of lat-long HDR maps (built once per map: `base` is frozen
+    when relighting, unlike training where build_mips runs every step)."""
+
+    def __init__(self, model, latlongs):
+        self.model = model
+        self.maps = []
+        em = model.emitter
+        with torch.no_grad():
+            for img in latlongs:
+                em.base.data = blender_latlong_to_cubemap(img.to(em.base.device).float(), [512, 512])
+                em.build_mips()
+                self.maps.append(([t.detach().clone() for t in em.specular], em.diffuse.detach().clone()))
+
+    def use(self, i):
+        self.model.emitter.specular, self.model.emitter.diffuse = self.maps[i]
+
+
+def my_tiles(n_rays, tile, rank, world):
+    return [(s, min(s + tile, n_rays)) for k, s in enumerate(range(0, n_rays, tile)) if k % world == rank]
+
+
+@torch.no_grad()
+def render_frame_shard(model, rays, envs, rank=0, world=1, tile=32768, keys=("comp_rgb_phys_full",)):
+    """Render this rank's tiles of one frame under every env map.  rays: [H*W, 6] on the device.
+    Returns {env_index: {key: [n_my_rays, C]}} plus the tile list."""
+    tiles = my_tiles(rays.shape[0], tile, rank, world)
+    out = {}
+    for e in range(len(envs.maps)):
+        envs.use(e)
+        parts = {k: [] for k in keys}
+        for a, b in tiles:
+            o = model.forward_(rays[a:b], relighting=True)
+            for k in keys:
+                parts[k].append(o[k])
+        out[e] = {k: torch.cat(v) if v else torch.zeros(0, 3, device=rays.device) for k, v in parts.items()}
+    return out, tiles
+
+
+def synthetic_envs():
+    return [syn.env_latlong("bridge", seed=1), syn.env_latlong("city", seed=2)]
