@@ -1,0 +1,51 @@
+"""N>1 host logic on CPU with gloo, world size 2: the flat gradient bucket all-reduce
+(DDP equivalence: mean of per-rank grads) and the no-communication pixel sharding of relighting."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rise_sdf_b200.relight import my_tiles
+    from rise_sdf_b200.train import FlatGradBucket
+    torch.manual_seed(0)                                   # identical "weights" on every rank
+    params = [torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.tensor(0.3))]
+    bucket = FlatGradBucket(params)
+    bucket.zero()
+    x = torch.full((3,), float(rank + 1))                  # per-rank data
+    loss = (params[0] @ x).sum() * (rank + 1) + (params[1] ** 2).sum() * (rank + 2) + params[2] * (rank + 5)
+    loss.backward()
+    assert params[0].grad.data_ptr() == bucket.flat.data_ptr()      # grads really live in the flat buffer
+    local = bucket.flat.clone()
+    bucket.all_reduce_mean()
+    tiles = my_tiles(640000, 32768, rank, world)
+    q.put((rank, local, bucket.flat.clone(), tiles))
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_and_tile_sharding():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    [p.join(30) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    mean = (res[0][1] + res[1][1]) / 2
+    for r in range(world):
+        assert torch.allclose(res[r][2], mean, rtol=1e-6, atol=1e-7)          # == DDP's averaged gradient
+    assert not torch.allclose(res[0][1], res[1][1])
+    covered = sorted(res[0][3] + res[1][3])
+    assert covered[0][0] == 0 and covered[-1][1] == 640000
+    assert all(a[1] == b[0] for a, b in zip(covered[:-1], covered[1:]))       # disjoint, complete cover
+    assert abs(len(res[0][3]) - len(res[1][3])) <= 1                          # balanced round-robin
