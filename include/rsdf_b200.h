@@ -187,6 +187,16 @@ typedef struct rsdf_mlp_fwd_params {
 } rsdf_mlp_fwd_params;
 int rsdf_mlp_fwd(const rsdf_mlp_fwd_params *params_host, void *stream);
 
+/* Streaming tensor-core GEMMs for the MLP TRAINING path (replace cuBLAS under nn.Linear and its
+ * autograd: models/network_utils.py:122-127).  fp32 rows in/out, 3-term fp16 split, fp32 accumulate.
+ *   rsdf_mm_stream: Y[S,N] = act(X[S,K] * op(W) + bias).  blob = rsdf_mlp_pack_weight(W[rows,cols]);
+ *     transposed=0: W is [N=rows, K=cols], Y = X W^T;  transposed=1: W is [K=rows, N=cols], Y = X W
+ *     (the same blob through the MN-major descriptor view).  bias may be NULL; act as in rsdf_mlp_layer.
+ *   rsdf_mm_tn: G[Fa,Fb] += A[S,Fa]^T * B[S,Fb]  (atomic accumulation; caller zeroes G). */
+int rsdf_mm_stream(const float *X, const void *blob, const float *bias, float *Y, int S, int K, int N,
+                   int rows_pad, int cols_pad, int transposed, int act, void *stream);
+int rsdf_mm_tn(const float *A, const float *B, float *G, int S, int Fa, int Fb, void *stream);
+
 /* self-test of the tcgen05 operand roles (see csrc/mlp_tc.cu); mode 0: C=A*W^T, 1: C=A*W,
  * 2: C+=A^T*Y */
 int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *Y, float *C, int S,

@@ -181,11 +181,23 @@ class VanillaMLP(nn.Module):
                 from .fused_mlp import PackedMLP
                 self._packed = PackedMLP(self)
             return self.output_activation(self._packed(x))
+        if x.is_cuda and x.dim() == 2 and VanillaMLP.tc_training:
+            # training: every GEMM of forward / backward / double-backward runs on tcgen05
+            # (csrc/gemm_stream.cu) through differentiable primitives; activations stay in torch
+            from . import tc_autograd as tca
+            h = x.float()
+            ws = self.effective_weights()
+            for i, (W, b) in enumerate(ws):
+                h = tca.linear(h, W, b)
+                if i + 1 < len(ws):
+                    h = F.softplus(h, beta=100) if self.sphere_init else F.relu(h)
+            return self.output_activation(h)
         x = self.layers(x.float())
         return self.output_activation(x)
 
     _packed = None
-    fused_inference = True      # class-wide switch (tests compare the fused and the torch path)
+    fused_inference = True      # class-wide switches (tests compare the kernel and the torch paths)
+    tc_training = True
 
     def make_linear(self, dim_in, dim_out, is_first, is_last):
         layer = nn.Linear(dim_in, dim_out, bias=True)

@@ -109,3 +109,43 @@ def test_fused_mlp_forward(dim_in, dim_out, hidden, sphere, S, width):
             h = layer(h)
         ref2 = torch.sigmoid(h).cpu()
     assert float((out2.double().cpu() - ref2).abs().max()) <= 2e-6
+
+
+# ------------------------------------------------------------------ training-path GEMMs + autograd
+def test_mm_primitives_first_and_second_order():
+    """mm_nt / mm_nn / mm_tn vs fp64 torch matmul: values, gradients and gradients of gradients."""
+    from rise_sdf_b200 import tc_autograd as tca
+    g = torch.Generator().manual_seed(0)
+    S, K, N = 3000, 35, 128
+    x = torch.randn(S, K, generator=g); W = torch.randn(N, K, generator=g) * 0.3
+    c = torch.randn(S, K, generator=g); gy = torch.randn(S, N, generator=g)
+
+    def run(xx, WW, f_nt):
+        y = f_nt(xx, WW)
+        (gx,) = torch.autograd.grad((torch.tanh(y) * gy.to(y)).sum(), xx, create_graph=True)
+        loss = (gx * c.to(gx)).sum() + (y ** 2).sum() * 0.1
+        gW, gx2 = torch.autograd.grad(loss, [WW, xx])
+        return y.detach(), gx.detach(), gW, gx2
+
+    xc, Wc = x.cuda().requires_grad_(True), W.cuda().requires_grad_(True)
+    got = run(xc, Wc, tca.mm_nt)
+    x0, W0 = x.double().requires_grad_(True), W.double().requires_grad_(True)
+    want = run(x0, W0, lambda a, b: a @ b.T)
+    for a, b, name in zip(got, want, ("y", "gx", "gW(2nd order)", "gx(2nd order)")):
+        e = float((a.double().cpu() - b).abs().max() / b.abs().max())
+        assert e <= 5e-6, (name, e)
+    # mm_tn and mm_nn directly
+    A = torch.randn(5000, 128, generator=g).cuda(); B = torch.randn(5000, 48, generator=g).cuda()
+    assert err(tca.mm_tn(A, B), A.double().cpu().T @ B.double().cpu()) <= 1e-5
+    assert err(tca.mm_tn(B, A), B.double().cpu().T @ A.double().cpu()) <= 1e-5     # Fa < 128 (padded M)
+    Wn = torch.randn(48, 128, generator=g).cuda()
+    assert err(tca.mm_nn(B, Wn), B.double().cpu() @ Wn.double().cpu()) <= 2e-6
+    assert tca.mm_nt(torch.zeros(0, 35, device="cuda"), Wc).shape == (0, 128)
+
+
+def test_mm_stream_ragged_and_large():
+    from rise_sdf_b200 import tc_autograd as tca
+    g = torch.Generator().manual_seed(1)
+    for S in (1, 127, 129, 148 * 128 + 5, 300000):
+        x = torch.randn(S, 67, generator=g).cuda(); W = torch.randn(128, 67, generator=g).cuda()
+        assert err(tca.mm_nt(x, W), x.double().cpu() @ W.double().cpu().T) <= 2e-6, S
