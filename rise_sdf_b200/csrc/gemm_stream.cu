@@ -9,9 +9,16 @@
 // d(tn) -> nt + nn), so torch autograd can recurse through them for the second-order terms the
 // analytic-normal / eikonal path needs (models/geometry.py:224-228) while every flop stays on tcgen05.
 //
-// rsdf_mm_stream: persistent CTA per SM, 256 threads (2 per sample row).  The small matrix is
-// resident in smem for the whole kernel; sample tiles stream through a software pipeline:
-//     stage X(t+1) (regs -> fp16 hi/lo tile image) -> issue MMA(t+1) into TMEM buffer (t+1)&1
+// Dynamic range: operands are split into fp16 hi/lo halves (tc.cuh), and back-propagated
+// gradients are ~1/S ~ 1e-7 per sample -- far below fp16's normal range.  Every streamed tile is
+// therefore rescaled by an exact power of two before the split (per sample ROW for nt/nn, where
+// the scale factors out of the row's dot products and is undone in the epilogue; per TILE for tn,
+// where the tile's partial product is undone while it is added to an fp32 register accumulator),
+// so the result is invariant to the magnitude of the inputs (tests: loss*2^20 gives grads*2^20).
+//
+// rsdf_mm_stream: persistent CTA per SM, 256 threads.  The small matrix is resident in smem for the
+// whole kernel; sample tiles stream through a software pipeline:
+//     stage X(t+1) (regs -> scaled fp16 hi/lo tile image) -> issue MMA(t+1) into TMEM buffer (t+1)&1
 //     -> issue the global loads of X(t+2) into registers -> epilogue of tile t from TMEM buffer t&1
 // so the tensor pipe and the HBM loads both run underneath the epilogue.  fp32 rows in, fp32 rows out.
 #include "common.cuh"
@@ -26,6 +33,9 @@ struct StreamSmem {
     uint64_t bar_w, bar_mma[2];
     uint32_t tmem_slot, pad;
     float bias[128];
+    float row_inv[3][128];      // per-row 1/scale, ring of 3 (written at it, read at it+1, reused at it+3)
+    float red[8];
+    float tile_inv[2];
 };
 
 template <int ACT>
@@ -36,14 +46,23 @@ __device__ __forceinline__ float act_apply(float z) {
     return z;
 }
 
-// Each row is shared by two threads (half = 0/1); a thread handles the 16-byte chunks c = half, half+2, ...
-// of a k_pad-wide row: 8 floats per chunk.
-template <int MAXCH>
-__device__ __forceinline__ void load_row_regs(const float *__restrict__ X, int s, int S, int K, int k_pad, int half,
-                                              float (&r)[MAXCH][8]) {
+// power of two that brings |m| to ~2^13 (fp16 max is 2^16): scale and its exact inverse
+__device__ __forceinline__ void pow2_scale(float m, float &scale, float &inv) {
+    if (!(m > 0.0f) || !isfinite(m)) { scale = 1.0f; inv = 1.0f; return; }
+    int ex = (int)((__float_as_uint(m) >> 23) & 0xFFu) - 127;     // floor(log2 m) (denormals -> -127)
+    int k = 13 - ex;
+    k = max(-100, min(100, k));
+    scale = __uint_as_float((uint32_t)(127 + k) << 23);
+    inv = __uint_as_float((uint32_t)(127 - k) << 23);
+}
+
+// Staging map: warp w stages rows 16w..16w+15; lanes (2i, 2i+1) share row 16w+i and take the
+// 16-byte chunks c = parity, parity+2, ...  (a warp reads 16 consecutive rows: fully coalesced).
+__device__ __forceinline__ void load_row_regs(const float *__restrict__ X, int s, int S, int K, int k_pad, int parity,
+                                              float (&r)[8][8]) {
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
-        const int c = half + 2 * i;
+    for (int i = 0; i < 8; ++i) {
+        const int c = parity + 2 * i;
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[i][j] = 0.0f;
         if (c * 8 < k_pad && s < S) {
@@ -62,19 +81,32 @@ __device__ __forceinline__ void load_row_regs(const float *__restrict__ X, int s
     }
 }
 
-template <int MAXCH>
-__device__ __forceinline__ void store_row_image(uint8_t *img, int k_pad, int row, int half, const float (&r)[MAXCH][8]) {
+__device__ __forceinline__ float regs_absmax(const float (&r)[8][8]) {
+    float m = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m = fmaxf(m, fabsf(r[i][j]));
+    return m;
+}
+
+__device__ __forceinline__ void store_row_image(uint8_t *img, int k_pad, int row, int parity, float (&r)[8][8],
+                                                float scale) {
     const uint32_t plane = TM * k_pad * 2;
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
-        const int c = half + 2 * i;
-        if (c * 8 < k_pad) tc::store_chunk(img, plane, TM, row, c, r[i]);
+    for (int i = 0; i < 8; ++i) {
+        const int c = parity + 2 * i;
+        if (c * 8 < k_pad) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[i][j] *= scale;
+            tc::store_chunk(img, plane, TM, row, c, r[i]);
+        }
     }
 }
 
 template <int ACT>
 __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int n_pad, int N, int half, const float *bias,
-                                              float *__restrict__ yrow, bool row_ok) {
+                                              float inv, float *__restrict__ yrow, bool row_ok) {
     const int n_chunks = n_pad / 16, split = (n_chunks + 1) / 2;
     const int c_begin = half == 0 ? 0 : split, c_end = half == 0 ? split : n_chunks;
     for (int c = c_begin; c < c_end; ++c) {
@@ -87,16 +119,16 @@ __device__ __forceinline__ void epilogue_rows(uint32_t taddr, int n_pad, int N, 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float4 o;
-                    o.x = act_apply<ACT>(v[4 * q] + bias[c0 + 4 * q]);
-                    o.y = act_apply<ACT>(v[4 * q + 1] + bias[c0 + 4 * q + 1]);
-                    o.z = act_apply<ACT>(v[4 * q + 2] + bias[c0 + 4 * q + 2]);
-                    o.w = act_apply<ACT>(v[4 * q + 3] + bias[c0 + 4 * q + 3]);
+                    o.x = act_apply<ACT>(fmaf(v[4 * q], inv, bias[c0 + 4 * q]));
+                    o.y = act_apply<ACT>(fmaf(v[4 * q + 1], inv, bias[c0 + 4 * q + 1]));
+                    o.z = act_apply<ACT>(fmaf(v[4 * q + 2], inv, bias[c0 + 4 * q + 2]));
+                    o.w = act_apply<ACT>(fmaf(v[4 * q + 3], inv, bias[c0 + 4 * q + 3]));
                     reinterpret_cast<float4 *>(yrow + c0)[q] = o;
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if (c0 + j < N) yrow[c0 + j] = act_apply<ACT>(v[j] + bias[c0 + j]);
+                    if (c0 + j < N) yrow[c0 + j] = act_apply<ACT>(fmaf(v[j], inv, bias[c0 + j]));
             }
         }
     }
@@ -112,7 +144,8 @@ mm_stream_kernel(const float *__restrict__ X, const uint8_t *__restrict__ blob, 
     uint8_t *x_img[2] = {smem + 65536, smem + 131072};       // 2 x 64 KB
     StreamSmem *sm = reinterpret_cast<StreamSmem *>(smem + 196608);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+    const int quad = warp & 3, half = warp >> 2, erow = quad * 32 + lane;     // epilogue map (TMEM lanes)
+    const int srow = warp * 16 + (lane >> 1), parity = lane & 1;              // staging map
     const int k_pad = transposed ? rows_pad : cols_pad;      // contraction length (padded)
     const int n_pad = transposed ? cols_pad : rows_pad;      // output width (padded)
 
@@ -138,7 +171,7 @@ mm_stream_kernel(const float *__restrict__ X, const uint8_t *__restrict__ blob, 
     const int n_tiles = (S + TM - 1) / TM;
     float regs[8][8];                                        // this thread's half row of the NEXT tile
     int t_next = blockIdx.x;
-    if (t_next < n_tiles) load_row_regs<8>(X, t_next * TM + row, S, K, k_pad, half, regs);
+    if (t_next < n_tiles) load_row_regs(X, t_next * TM + srow, S, K, k_pad, parity, regs);
     uint32_t phase[2] = {0, 0};
     int it = 0;
     int t_prev = -1;                                         // tile whose MMA is in flight / done
@@ -147,10 +180,15 @@ mm_stream_kernel(const float *__restrict__ X, const uint8_t *__restrict__ blob, 
         const int t_cur = t_next;                            // tile to stage + launch now
         const bool have_cur = t_cur < n_tiles;
         if (have_cur) {
-            store_row_image<8>(x_img[it & 1], k_pad, row, half, regs);
+            float m = regs_absmax(regs);
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            float scale, inv;
+            pow2_scale(m, scale, inv);
+            if (parity == 0) sm->row_inv[it % 3][srow] = inv;
+            store_row_image(x_img[it & 1], k_pad, srow, parity, regs, scale);
             tc::fence_async_smem();
         }
-        __syncthreads();   // image complete; also: epilogue (it-2) finished reading TMEM buffer it&1
+        __syncthreads();   // image + row scales complete; epilogue (it-2) done with TMEM buffer it&1
         if (have_cur && tid == 0) {
             if (!w_ready) tc::mbar_wait(&sm->bar_w, 0);
             tc::tc_fence_after();
@@ -164,21 +202,22 @@ mm_stream_kernel(const float *__restrict__ X, const uint8_t *__restrict__ blob, 
         w_ready = true;
         // prefetch the rows of the tile after this one while the MMA runs
         t_next = t_cur + gridDim.x;
-        if (have_cur && t_next < n_tiles) load_row_regs<8>(X, t_next * TM + row, S, K, k_pad, half, regs);
+        if (have_cur && t_next < n_tiles) load_row_regs(X, t_next * TM + srow, S, K, k_pad, parity, regs);
         // epilogue of the previous tile
         if (t_prev >= 0) {
             const int b = (it - 1) & 1;
             tc::mbar_wait(&sm->bar_mma[b], phase[b]);
             phase[b] ^= 1;
             tc::tc_fence_after();
-            const int s = t_prev * TM + row;
+            const int s = t_prev * TM + erow;
             float *yrow = Y + (size_t)s * N;
+            const float inv = sm->row_inv[(it - 1) % 3][erow];
             const uint32_t taddr = tmem + lane_off + (uint32_t)(b * 128);
             switch (act) {
-                case 1: epilogue_rows<1>(taddr, n_pad, N, half, sm->bias, yrow, s < S); break;
-                case 2: epilogue_rows<2>(taddr, n_pad, N, half, sm->bias, yrow, s < S); break;
-                case 3: epilogue_rows<3>(taddr, n_pad, N, half, sm->bias, yrow, s < S); break;
-                default: epilogue_rows<0>(taddr, n_pad, N, half, sm->bias, yrow, s < S); break;
+                case 1: epilogue_rows<1>(taddr, n_pad, N, half, sm->bias, inv, yrow, s < S); break;
+                case 2: epilogue_rows<2>(taddr, n_pad, N, half, sm->bias, inv, yrow, s < S); break;
+                case 3: epilogue_rows<3>(taddr, n_pad, N, half, sm->bias, inv, yrow, s < S); break;
+                default: epilogue_rows<0>(taddr, n_pad, N, half, sm->bias, inv, yrow, s < S); break;
             }
             tc::tc_fence_before();
         }
@@ -190,77 +229,123 @@ mm_stream_kernel(const float *__restrict__ X, const uint8_t *__restrict__ blob, 
     if (warp == 0) tc::tmem_free(tmem, 256);
 }
 
-// G[Fa, Fb] += A^T B over this CTA's sample tiles; M side = Fa padded to 128 lanes.
+__device__ __forceinline__ float block_absmax(float m, float *red, int warp, int lane) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < THREADS / 32; ++w) r = fmaxf(r, red[w]);
+    __syncthreads();
+    return r;
+}
+
+// G[Fa, Fb] += A^T B over this CTA's sample tiles; M side = Fa padded to 128 lanes.  Each tile is
+// scaled by exact powers of two (one for A, one for B), its product lands in one of two TMEM
+// buffers and is added, un-scaled, to an fp32 register accumulator while the next tile's MMA runs.
 __global__ void __launch_bounds__(THREADS, 1)
 mm_tn_kernel(const float *__restrict__ A, const float *__restrict__ B, float *__restrict__ G, int S, int Fa, int Fb) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a_img = smem, *b_img = smem + 65536;
     StreamSmem *sm = reinterpret_cast<StreamSmem *>(smem + 131072);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quad = warp & 3, half = warp >> 2, row = quad * 32 + lane;
+    const int quad = warp & 3, half = warp >> 2, erow = quad * 32 + lane;
+    const int srow = warp * 16 + (lane >> 1), parity = lane & 1;
     const int b_pad = (Fb + 15) / 16 * 16;
     if (tid == 0) {
         tc::mbar_init(&sm->bar_mma[0], 1);
+        tc::mbar_init(&sm->bar_mma[1], 1);
         tc::mbar_fence_init();
     }
-    if (warp == 0) tc::tmem_alloc(&sm->tmem_slot, 128);
+    if (warp == 0) tc::tmem_alloc(&sm->tmem_slot, 256);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = sm->tmem_slot;
-    // the A image always spans 128 feature columns (zero padded) so that M = 128
-    const int n_tiles = (S + TM - 1) / TM;
-    uint32_t phase = 0;
-    int it = 0;
-    float ra[8][8], rb[8][8];
-    int tile = blockIdx.x;
-    if (tile < n_tiles) {
-        load_row_regs<8>(A, tile * TM + row, S, Fa, 128, half, ra);
-        load_row_regs<8>(B, tile * TM + row, S, Fb, b_pad, half, rb);
-    }
-    for (; tile < n_tiles; tile += gridDim.x, ++it) {
-        if (it > 0) {                                        // previous MMA must have drained the images
-            tc::mbar_wait(&sm->bar_mma[0], phase);
-            phase ^= 1;
+    const uint32_t taddr0 = tmem + ((uint32_t)(quad * 32) << 16);
+    const int n_chunks = b_pad / 16, split = (n_chunks + 1) / 2;
+    const int c_begin = half == 0 ? 0 : split, c_end = half == 0 ? split : n_chunks;
+
+    float acc[4][16];                                       // <= 64 output columns per thread
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = 0.0f;
+
+    auto drain = [&](int b) {                               // add TMEM buffer b (un-scaled) to acc
+        const float inv = sm->tile_inv[b];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c_begin + i;
+            if (c < c_end) {
+                float v[16];
+                tc::tmem_ld16(taddr0 + (uint32_t)(b * 128) + c * 16, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(v[j], inv, acc[i][j]);
+            }
         }
-        store_row_image<8>(a_img, 128, row, half, ra);
-        store_row_image<8>(b_img, b_pad, row, half, rb);
+    };
+
+    const int n_tiles = (S + TM - 1) / TM;
+    uint32_t phase[2] = {0, 0};
+    int it = 0;
+    float ra[8][8];
+    int tile = blockIdx.x;
+    if (tile < n_tiles) load_row_regs(A, tile * TM + srow, S, Fa, 128, parity, ra);
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        // the images are single-buffered: the previous tile's MMA must have finished reading them
+        if (it > 0) {
+            tc::mbar_wait(&sm->bar_mma[b ^ 1], phase[b ^ 1]);
+            phase[b ^ 1] ^= 1;
+            tc::tc_fence_after();
+        }
+        float rb[8][8];
+        load_row_regs(B, tile * TM + srow, S, Fb, b_pad, parity, rb);
+        float sa, ia, sb, ib;
+        pow2_scale(block_absmax(regs_absmax(ra), sm->red, warp, lane), sa, ia);
+        store_row_image(a_img, 128, srow, parity, ra, sa);
+        pow2_scale(block_absmax(regs_absmax(rb), sm->red, warp, lane), sb, ib);
+        store_row_image(b_img, b_pad, srow, parity, rb, sb);
+        if (tid == 0) sm->tile_inv[b] = ia * ib;
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
             tc::tc_fence_after();
             const uint32_t idesc = tc::instr_desc(128, b_pad, true, true);
-            tc::gemm_split3(tmem, tc::op_mnmajor(tc::smem_u32(a_img), TM * 128 * 2, TM),
-                            tc::op_mnmajor(tc::smem_u32(b_img), TM * b_pad * 2, TM), TM / 16, idesc, it > 0);
-            tc::mma_commit(&sm->bar_mma[0]);
+            tc::gemm_split3(tmem + (uint32_t)(b * 128), tc::op_mnmajor(tc::smem_u32(a_img), TM * 128 * 2, TM),
+                            tc::op_mnmajor(tc::smem_u32(b_img), TM * b_pad * 2, TM), TM / 16, idesc, false);
+            tc::mma_commit(&sm->bar_mma[b]);
         }
         const int nt = tile + gridDim.x;
-        if (nt < n_tiles) {
-            load_row_regs<8>(A, nt * TM + row, S, Fa, 128, half, ra);
-            load_row_regs<8>(B, nt * TM + row, S, Fb, b_pad, half, rb);
+        if (nt < n_tiles) load_row_regs(A, nt * TM + srow, S, Fa, 128, parity, ra);
+        if (it > 0) {                                        // previous tile's product -> accumulator
+            drain(b ^ 1);
+            tc::tc_fence_before();
         }
     }
     if (it > 0) {
-        tc::mbar_wait(&sm->bar_mma[0], phase);
+        const int b = (it - 1) & 1;
+        tc::mbar_wait(&sm->bar_mma[b], phase[b]);
         tc::tc_fence_after();
-        // lanes = Fa features; the two halves split the Fb columns
-        const int n_chunks = b_pad / 16, split = (n_chunks + 1) / 2;
-        const int c_begin = half == 0 ? 0 : split, c_end = half == 0 ? split : n_chunks;
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16);
-        for (int c = c_begin; c < c_end; ++c) {
-            float v[16];
-            tc::tmem_ld16(taddr + c * 16, v);
-            tc::tmem_ld_wait();
-            if (row < Fa) {
+        drain(b);
+        tc::tc_fence_before();
+        if (erow < Fa) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c * 16 + j < Fb) atomicAdd(&G[(size_t)row * Fb + c * 16 + j], v[j]);
+            for (int i = 0; i < 4; ++i) {
+                const int c = c_begin + i;
+                if (c < c_end) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c * 16 + j < Fb) atomicAdd(&G[(size_t)erow * Fb + c * 16 + j], acc[i][j]);
+                }
             }
         }
-        tc::tc_fence_before();
     }
     __syncthreads();
-    if (warp == 0) tc::tmem_free(tmem, 128);
+    if (warp == 0) tc::tmem_free(tmem, 256);
 }
 
 }  // namespace

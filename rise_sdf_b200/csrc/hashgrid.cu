@@ -34,8 +34,11 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t cx, uint32_t cy, uint32_
     index += cx * stride; stride *= res;                      // dim 0 (stride=1 <= size always)
     if (stride <= size) { index += cy * stride; stride *= res;
         if (stride <= size) { index += cz * stride; stride *= res; } }
-    if (size < stride) index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
-    return index % size;
+    if (size < stride) {
+        index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+        return (size & (size - 1u)) == 0u ? index & (size - 1u) : index % size;   // == index % size
+    }
+    return index >= size ? index % size : index;
 }
 
 struct Cell {
@@ -69,21 +72,46 @@ __device__ __forceinline__ void gather8(const float *table, const Cell &c, uint3
     }
 }
 
+// L2 residency: the 50-58 MB table is re-read ~50x per pass while 0.5 KB/sample of outputs stream
+// through once.  Table gathers carry an evict_last policy and the outputs use evict-first stores,
+// so the output stream cannot push the table out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float2 ldg2_keep(const float *table, uint32_t entry, uint64_t pol) {
+    float2 v;
+    asm("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+        : "=f"(v.x), "=f"(v.y) : "l"(reinterpret_cast<const float2 *>(table) + entry), "l"(pol));
+    return v;
+}
+
+// Forward.  CTA = FW_S consecutive samples x 16 level-warps: warp w walks levels w, w+16, ...; lane =
+// sample, so a warp's 8 gathers of a coarse level coalesce into a handful of sectors and no thread
+// holds more than one level's corners (40 registers -> 3 CTAs = 48 warps per SM, vs. 24 before).
+// The [sample][feature] transposition goes through a 16 KB padded smem tile and leaves as
+// full-row 8-byte streaming stores.
+constexpr int FW_S = 32;
+constexpr int FW_THREADS = 512;
+
 template <bool WITH_GRAD>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(FW_THREADS, 3)
 hashgrid_fwd_kernel(const float *__restrict__ x, const float *__restrict__ table, const Meta m,
                     int n_samples, float *__restrict__ y, float *__restrict__ dy_dx) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int n_out = m.n_levels * NFEAT;
-    float *sy = smem;                                   // [TILE_S][n_out+1]
-    float *sg = smem + TILE_S * (n_out + 1);            // [TILE_S][3*n_out+1]
-    const int ls = threadIdx.x / TILE_S;                // level slice 0/1
-    const int t = threadIdx.x % TILE_S;
-    const int s = blockIdx.x * TILE_S + t;
+    const int ys = n_out + 2, gs = 3 * n_out + 2;       // even row strides: float2 slots, 2-way max
+    float *sy = smem;                                   // [FW_S][ys]
+    float *sg = smem + FW_S * ys;                       // [FW_S][gs]
+    const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int s0 = blockIdx.x * FW_S;
+    const int s = s0 + t;
     const bool ok = s < n_samples;
+    const uint64_t pol = l2_keep_policy();
     float px = 0.f, py = 0.f, pz = 0.f;
-    if (ok) { px = x[3 * s]; py = x[3 * s + 1]; pz = x[3 * s + 2]; }
-    for (int l = ls; l < m.n_levels; l += THREADS / TILE_S) {
+    if (ok) { px = __ldg(x + 3 * s); py = __ldg(x + 3 * s + 1); pz = __ldg(x + 3 * s + 2); }
+    for (int l = warp; l < m.n_levels; l += FW_THREADS / 32) {
         const float scale = m.scale[l];
         const uint32_t res = m.res[l], off = m.offset[l], size = m.offset[l + 1] - off;
         float r0 = 0.f, r1 = 0.f;
@@ -91,7 +119,11 @@ hashgrid_fwd_kernel(const float *__restrict__ x, const float *__restrict__ table
         if (ok) {
             const Cell c = locate(px, py, pz, scale);
             float2 v[8];
-            gather8(table, c, res, size, off, v);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t idx = grid_index(c.c[0] + (k & 1), c.c[1] + ((k >> 1) & 1), c.c[2] + (k >> 2), res, size);
+                v[k] = ldg2_keep(table, off + idx, pol);
+            }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float wx = (k & 1) ? c.w[0] : 1.0f - c.w[0];
@@ -111,27 +143,29 @@ hashgrid_fwd_kernel(const float *__restrict__ x, const float *__restrict__ table
                 }
             }
         }
-        sy[t * (n_out + 1) + 2 * l] = r0;
-        sy[t * (n_out + 1) + 2 * l + 1] = r1;
+        *reinterpret_cast<float2 *>(sy + t * ys + 2 * l) = make_float2(r0, r1);
         if (WITH_GRAD) {
-            float *q = sg + t * (3 * n_out + 1) + 6 * l;   // [f][d] order: (f0:x,y,z),(f1:x,y,z)
-            q[0] = g[0][0]; q[1] = g[1][0]; q[2] = g[2][0];
-            q[3] = g[0][1]; q[4] = g[1][1]; q[5] = g[2][1];
+            float2 *q = reinterpret_cast<float2 *>(sg + t * gs + 6 * l);   // (f0:x,y,z),(f1:x,y,z)
+            q[0] = make_float2(g[0][0], g[1][0]);
+            q[1] = make_float2(g[2][0], g[0][1]);
+            q[2] = make_float2(g[1][1], g[2][1]);
         }
     }
     __syncthreads();
-    // coalesced write-back of the tile
-    const int s0 = blockIdx.x * TILE_S;
-    const int rows = min(TILE_S, n_samples - s0);
-    for (int i = threadIdx.x; i < rows * n_out; i += THREADS) {
-        const int r = i / n_out, c = i - r * n_out;
-        y[(size_t)s0 * n_out + i] = sy[r * (n_out + 1) + c];
+    // coalesced streaming write-back of the tile (8-byte slots; rows are contiguous in HBM)
+    const int rows = min(FW_S, n_samples - s0);
+    const int h = n_out / 2;
+    float2 *yo = reinterpret_cast<float2 *>(y + (size_t)s0 * n_out);
+    for (int i = threadIdx.x; i < rows * h; i += FW_THREADS) {
+        const int r = i / h, c = i - r * h;
+        __stcs(yo + i, *reinterpret_cast<const float2 *>(sy + r * ys + 2 * c));
     }
     if (WITH_GRAD) {
-        const int n3 = 3 * n_out;
-        for (int i = threadIdx.x; i < rows * n3; i += THREADS) {
-            const int r = i / n3, c = i - r * n3;
-            dy_dx[(size_t)s0 * n3 + i] = sg[r * (n3 + 1) + c];
+        const int h3 = 3 * h;
+        float2 *go = reinterpret_cast<float2 *>(dy_dx + (size_t)s0 * 3 * n_out);
+        for (int i = threadIdx.x; i < rows * h3; i += FW_THREADS) {
+            const int r = i / h3, c = i - r * h3;
+            __stcs(go + i, *reinterpret_cast<const float2 *>(sg + r * gs + 2 * c));
         }
     }
 }
@@ -391,14 +425,13 @@ int rsdf_hashgrid_fwd(const float *x, const float *table, const rsdf_hashgrid_me
     Meta m;
     if (!x || !table || !y || !load_meta(meta, m)) return RSDF_EBADARG;
     const int n_out = m.n_levels * NFEAT;
-    const int blocks = rsdf_div_up(n_samples, TILE_S);
+    const int blocks = rsdf_div_up(n_samples, FW_S);
     if (dy_dx) {
-        const size_t sm = sizeof(float) * TILE_S * ((n_out + 1) + (3 * n_out + 1));
-        cudaFuncSetAttribute(hashgrid_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        hashgrid_fwd_kernel<true><<<blocks, THREADS, sm, (cudaStream_t)stream>>>(x, table, m, n_samples, y, dy_dx);
+        const size_t sm = sizeof(float) * FW_S * ((n_out + 2) + (3 * n_out + 2));
+        hashgrid_fwd_kernel<true><<<blocks, FW_THREADS, sm, (cudaStream_t)stream>>>(x, table, m, n_samples, y, dy_dx);
     } else {
-        const size_t sm = sizeof(float) * TILE_S * (n_out + 1);
-        hashgrid_fwd_kernel<false><<<blocks, THREADS, sm, (cudaStream_t)stream>>>(x, table, m, n_samples, y, nullptr);
+        const size_t sm = sizeof(float) * FW_S * (n_out + 2);
+        hashgrid_fwd_kernel<false><<<blocks, FW_THREADS, sm, (cudaStream_t)stream>>>(x, table, m, n_samples, y, nullptr);
     }
     RSDF_LAUNCH_CHECK();
     return 0;

