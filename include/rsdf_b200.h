@@ -197,6 +197,34 @@ int rsdf_mm_stream(const float *X, const void *blob, const float *bias, float *Y
                    int rows_pad, int cols_pad, int transposed, int act, void *stream);
 int rsdf_mm_tn(const float *A, const float *B, float *G, int S, int Fa, int Fb, void *stream);
 
+/* Fused SDF-field MLP for the training path: h0[n_in<=48] -> 128 -> 128 -> n_out<=48 with
+ * Softplus(beta=100) (VolumeSDF's VanillaMLP, models/geometry.py:206-228, models/network_utils.py:109-157)
+ * TOGETHER WITH g0 = d out[:,0] / d h0, the analytic input gradient the reference takes with
+ * torch.autograd.grad(sdf, points, create_graph=True) (models/geometry.py:224-228), and the full backward
+ * of both (second-order terms of the eikonal / normal-dependent losses included).
+ *   blobs: rsdf_mlp_pack_weight(W1[128,n_in], N_pad=128, K_pad=48), (W2[128,128], 128, 128),
+ *          (W3[n_out,128], N_pad=48, K_pad=128);  w3_row0 = W3[0,:] in fp32.
+ *   inputs: h0 = cat(in0[S,w0] * scale0 + shift0, in1[S,w1]),  w0 + w1 == n_in.
+ *   fwd: out[S,n_out], g0[S,n_in] (g0 may be NULL: plain forward).
+ *   bwd: cotangents g_out[S,n_out], g_g0[S,n_in] (may be NULL) -> g_in[S,n_in] = d/d h0 (may be NULL) and
+ *        gW1[128,n_in], gb1[128], gW2[128,128], gb2[128], gW3[n_out,128], gb3[n_out], accumulated
+ *        atomically (caller zeroes).  The forward is recomputed; nothing but h0 is kept between passes.
+ *        Cotangents are rescaled per sample by powers of two inside the kernel (fp16 operand range). */
+typedef struct rsdf_sdf_mlp {
+    const void *w1_blob, *w2_blob, *w3_blob;
+    const float *b1, *b2, *b3, *w3_row0;
+    int32_t n_in, n_out;
+} rsdf_sdf_mlp;
+int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
+                     const float *in1, int w1, int n_samples, float *out, float *g0, void *stream);
+int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
+                     const float *in1, int w1, int n_samples, const float *g_out, const float *g_g0,
+                     const uint32_t *amax_bits /* rsdf_absmax2(g_out, g_g0) */, float *g_in, float *gW1,
+                     float *gb1, float *gW2, float *gb2, float *gW3, float *gb3, void *stream);
+/* *out_bits = float bits of max(|a|, |b|) (device scalar; either array may be empty; 16-byte aligned).
+ * The fp16-split kernels derive their power-of-two cotangent scaling from it. */
+int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uint32_t *out_bits, void *stream);
+
 /* self-test of the tcgen05 operand roles (see csrc/mlp_tc.cu); mode 0: C=A*W^T, 1: C=A*W,
  * 2: C+=A^T*Y */
 int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *Y, float *C, int S,

@@ -23,6 +23,11 @@ class HashGridMetaC(ctypes.Structure):
                 ("offset", ctypes.c_uint32 * (MAX_LEVELS + 1))]
 
 
+class SdfMlpC(ctypes.Structure):
+    _fields_ = [("w1_blob", c_p), ("w2_blob", c_p), ("w3_blob", c_p), ("b1", c_p), ("b2", c_p), ("b3", c_p),
+                ("w3_row0", c_p), ("n_in", ctypes.c_int32), ("n_out", ctypes.c_int32)]
+
+
 # name -> argtypes (restype is int for all but the two string getters)
 _SIGS = {
     "rsdf_ray_aabb_intersect": [c_p, c_p, c_p, c_i, c_p, c_p, c_p],
@@ -56,6 +61,9 @@ _SIGS = {
     "rsdf_mlp_fwd": [c_p, c_p],
     "rsdf_mm_stream": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "rsdf_mm_tn": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "rsdf_sdf_mlp_fwd": [c_p, c_p, c_i, c_f, c_f, c_p, c_i, c_i, c_p, c_p, c_p],
+    "rsdf_sdf_mlp_bwd": [c_p, c_p, c_i, c_f, c_f, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "rsdf_absmax2": [c_p, ctypes.c_longlong, c_p, ctypes.c_longlong, c_p, c_p],
     "rsdf_tc_gemm_test": [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 

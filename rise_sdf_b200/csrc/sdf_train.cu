@@ -1,0 +1,639 @@
+// K3t -- the SDF field MLP of VolumeSDF (models/geometry.py:206-228) for the TRAINING path, fused:
+//     h0[n_in<=48] -> Linear(128) -> Softplus(100) -> Linear(128) -> Softplus(100) -> Linear(n_out<=48)
+// (VanillaMLP with sphere_init, models/network_utils.py:109-157; both RISE-SDF configs use 35 -> 128 -> 128 -> 48)
+// together with the ANALYTIC input gradient of its first output (sdf = out[:,0]) that the reference
+// obtains with torch.autograd.grad(sdf, points, create_graph=True) (models/geometry.py:224-228), and the
+// complete backward of both -- i.e. including the second-order terms the eikonal loss and the
+// normal-dependent shading push back through that gradient.
+//
+//   forward kernel :  out = MLP(h0),   g0 = d out[:,0] / d h0 = W1^T (s1 . (W2^T (s2 . W3[0,:]))),  s = softplus'
+//   backward kernel:  given d/d out and d/d g0  ->  d/d h0, d/d W1,b1,W2,b2,W3,b3   (forward recomputed)
+//
+// "Transposed" tcgen05 formulation: the MMA's M axis (128 TMEM lanes) carries the 128 hidden FEATURES and
+// the N axis carries a tile of 64 SAMPLES, D[feature, sample] = W[feature, :] * X[:, sample]:
+//   * weights are the A operand straight from their rsdf_mlp_pack_weight blobs (K-major = W, MN-major
+//     view = W^T), all three resident in shared memory for the whole persistent kernel (112 KB);
+//   * activations are fp16 hi/lo tile images with rows = features and 16-byte chunks of 8 SAMPLES: the
+//     same bytes are the MN-major B operand of a layer GEMM (contract features) and a K-major operand
+//     of a weight-gradient GEMM (contract samples);
+//   * a thread owns one feature row and 32 of the tile's samples, so biases, the sdf-head weight,
+//     bias-gradient sums and the softplus derivatives are per-thread registers, and every global
+//     read/write is a warp reading/writing 32 consecutive floats of one sample row (coalesced);
+//   * weight gradients accumulate across ALL of a CTA's tiles in TMEM (224 fp32 columns) and are
+//     flushed once, with one atomic per element per CTA;
+//   * pre-activations z1, z2 stay in TMEM for the whole tile, so softplus' / softplus'' are recomputed
+//     from fp32 values and no activation ever goes to HBM.
+// fp32-class accuracy: every GEMM is the 3-product fp16 split of tc.cuh accumulated in fp32.
+// Dynamic range (fp16 operands, cotangents ~1/S ~ 1e-7): the backward is linear in the cotangents, so
+// each SAMPLE's cotangent pair (d/d out, d/d g0) is multiplied by its own power of two 2^k_s before the
+// split and every per-sample result is multiplied back in fp32 -- per-sample outputs keep full relative
+// precision however small that sample's gradient is.  Weight-gradient GEMMs contract over samples, so
+// their activation-side operand carries the complementary factor 2^(K - k_s) <= 1 (K from the launch-wide
+// cotangent maximum, rsdf_absmax2): the accumulators hold 2^K * dW, precise relative to the samples
+// that dominate the sum.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace {
+
+constexpr int NS = 64;                    // samples per tile (UMMA N)
+constexpr int THREADS = 512;
+constexpr int HID = 128;
+constexpr int KP = 48;                    // padded width of the input and output sides
+constexpr uint32_t IMG_S_PLANE = KP * 128;       // [48 feature rows x 64 samples] fp16 plane
+constexpr uint32_t IMG_B_PLANE = HID * 128;      // [128 x 64]
+constexpr uint32_t IMG_S_BYTES = 2 * IMG_S_PLANE, IMG_B_BYTES = 2 * IMG_B_PLANE;
+constexpr uint32_t W1_PLANE = HID * KP * 2, W2_PLANE = HID * HID * 2, W3_PLANE = KP * HID * 2;
+constexpr uint32_t W1_OFF = 0, W2_OFF = W1_OFF + 2 * W1_PLANE, W3_OFF = W2_OFF + 2 * W2_PLANE;
+constexpr uint32_t W_END = W3_OFF + 2 * W3_PLANE;                                   // 114688
+
+struct Net {
+    const uint8_t *w1, *w2, *w3;          // blobs: [128 x 48], [128 x 128], [48 x 128] (rows x cols, padded)
+    const float *b1, *b2, *b3, *w3r0;     // fp32 biases and row 0 of W3 (the sdf head)
+    int n_in, n_out;
+};
+struct Inputs {
+    const float *in0, *in1;               // h0 = cat(in0 * sc0 + sh0, in1)
+    int w0, w1;
+    float sc0, sh0;
+    int S;
+};
+struct Ctrl {
+    uint64_t bar_w, bar_mma;
+    uint32_t tmem_slot, pad;
+};
+
+// 16 warps: warp w owns TMEM lane quadrant w%4 (feature rows 32*(w%4)..+31) and the 16 sample
+// columns [16*(w/4), +16) of the tile
+struct Tid {
+    int tid, warp, lane, q, cq, f, col0;
+    uint32_t tl;                          // TMEM address of this warp's lane quadrant, column 0
+};
+
+__device__ __forceinline__ void ld16(const Tid &t, int col, float *v) {
+    tc::tmem_ld16(t.tl + (uint32_t)(col + t.col0), v);
+    tc::tmem_ld_wait();
+}
+// this thread's 16 samples of feature row f -> two 16-byte chunks per plane of a [128 x 64] image
+__device__ __forceinline__ void st16(uint8_t *img, const Tid &t, const float *v) {
+    const int c = t.col0 >> 3;
+    tc::store_chunk(img, IMG_B_PLANE, HID, t.f, c, v);
+    tc::store_chunk(img, IMG_B_PLANE, HID, t.f, c + 1, v + 8);
+}
+
+// 3-product split GEMM, fully unrolled; descriptors advance by adding to the 14-bit address field
+template <int KSTEPS>
+__device__ __forceinline__ void gemm3(uint32_t d, const tc::Operand &A, const tc::Operand &B, uint32_t idesc,
+                                      bool accumulate) {
+    const uint64_t a_hi = tc::smem_desc(A.addr, A.lbo, A.sbo), a_lo = tc::smem_desc(A.addr + A.plane, A.lbo, A.sbo);
+    const uint64_t b_hi = tc::smem_desc(B.addr, B.lbo, B.sbo), b_lo = tc::smem_desc(B.addr + B.plane, B.lbo, B.sbo);
+    const uint64_t ak = A.kstep >> 4, bk = B.kstep >> 4;
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_lo + k * ak, b_hi + k * bk, idesc, accumulate || k > 0);
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_hi + k * ak, b_lo + k * bk, idesc, true);
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_hi + k * ak, b_hi + k * bk, idesc, true);
+}
+
+// softplus(beta=100, threshold=20) and its first two derivatives, torch semantics (aten softplus /
+// softplus_backward / its double-backward formula).  With e = exp(-|t|) in (0,1]:
+//   softplus = max(z,0) + log(1+e)/beta,  sigmoid(t) = 1/(1+e) or e/(1+e),  sigmoid' = beta e/(1+e)^2.
+// The fast intrinsics are safe here: their absolute error (~2^-22) is divided by beta = 100 in the
+// activation and enters the derivatives at <= 3e-7.
+__device__ __forceinline__ void sp_all(float z, float &a, float &s, float &ds) {
+    const float t = 100.0f * z;
+    if (t > 20.0f) { a = z; s = 1.0f; ds = 0.0f; return; }
+    const float e = __expf(-fabsf(t));
+    const float r = __fdividef(1.0f, 1.0f + e);
+    a = fmaf(0.01f, __logf(1.0f + e), fmaxf(z, 0.0f));
+    s = t >= 0.0f ? r : e * r;
+    ds = 100.0f * e * r * r;
+}
+__device__ __forceinline__ float sp_act(float z) {
+    const float t = 100.0f * z;
+    if (t > 20.0f) return z;
+    return fmaf(0.01f, __logf(1.0f + __expf(-fabsf(t))), fmaxf(z, 0.0f));
+}
+__device__ __forceinline__ float sp_sig(float z) {
+    const float t = 100.0f * z;
+    if (t > 20.0f) return 1.0f;
+    const float e = __expf(-fabsf(t));
+    const float r = __fdividef(1.0f, 1.0f + e);
+    return t >= 0.0f ? r : e * r;
+}
+
+// One 8-sample chunk (samples s0 + 8c .. +7) of feature row f, straight from row-major global memory:
+// a warp reads 32 consecutive floats of one sample row per load (coalesced).  Thread -> (f = tid % 64,
+// c = tid / 64); rows f >= KP do not exist.
+template <typename G>
+__device__ __forceinline__ void load_chunk8(const Tid &t, int s0, int S, int n_feat, G get, float *v) {
+    const int f = t.tid & 63, c = t.tid >> 6;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int s = s0 + 8 * c + j;
+        v[j] = (f < n_feat && s < S) ? get(s, f) : 0.0f;
+    }
+}
+__device__ __forceinline__ void store_chunk8(uint8_t *img, const Tid &t, const float *v) {
+    const int f = t.tid & 63, c = t.tid >> 6;
+    if (f < KP) tc::store_chunk(img, IMG_S_PLANE, KP, f, c, v);
+}
+
+// TMEM [feature lanes < w][64 samples] -> row-major out[S, w]:  out[s, f] = (acc + bias_f) * mul[s]
+__device__ __forceinline__ void store_rows(float *__restrict__ out, int w, int s0, int S, const Tid &t, int col,
+                                           float bias, const float *mul) {
+    if (t.q * 32 >= w) return;            // warp-uniform
+    float v[16];
+    ld16(t, col, v);
+    if (t.f < w) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int s = s0 + t.col0 + j;
+            if (s < S) out[(size_t)s * w + t.f] = (v[j] + bias) * (mul ? mul[t.col0 + j] : 1.0f);
+        }
+    }
+}
+
+__device__ __forceinline__ Tid make_tid() {
+    Tid t;
+    t.tid = threadIdx.x; t.warp = t.tid >> 5; t.lane = t.tid & 31;
+    t.q = t.warp & 3; t.cq = t.warp >> 2;
+    t.f = t.q * 32 + t.lane; t.col0 = 16 * t.cq;
+    t.tl = 0;
+    return t;
+}
+
+__device__ __forceinline__ void load_weights(uint8_t *smem, const Net &net, Ctrl *ct, int tid) {
+    if (tid == 0) {
+        tc::mbar_expect_tx(&ct->bar_w, W_END);
+        tc::bulk_g2s(smem + W1_OFF, net.w1, 2 * W1_PLANE, &ct->bar_w);
+        tc::bulk_g2s(smem + W2_OFF, net.w2, 2 * W2_PLANE, &ct->bar_w);
+        tc::bulk_g2s(smem + W3_OFF, net.w3, 2 * W3_PLANE, &ct->bar_w);
+    }
+}
+
+// publish this thread's smem image writes / TMEM reads, then let thread 0 issue the next MMA group
+#define PHASE_BEGIN()            \
+    tc::fence_async_smem();      \
+    tc::tc_fence_before();       \
+    __syncthreads();             \
+    if (t.tid == 0) {            \
+        tc::tc_fence_after();
+#define PHASE_END()                          \
+        tc::mma_commit(&ct->bar_mma);        \
+    }                                        \
+    tc::mbar_wait(&ct->bar_mma, mma_phase);  \
+    mma_phase ^= 1;                          \
+    tc::tc_fence_after();
+
+#define H0_GETTER                                                                               \
+    [&](int s, int f) {                                                                         \
+        return f < in.w0 ? fmaf(__ldg(in.in0 + (size_t)s * in.w0 + f), in.sc0, in.sh0)          \
+                         : __ldg(in.in1 + (size_t)s * in.w1 + (f - in.w0));                     \
+    }
+
+// ------------------------------------------------------------------------------------------------
+// forward: out[S, n_out] and (WITH_GRAD) g0[S, n_in] = d out[:,0] / d h0
+// TMEM columns: Z1 0, Z2 64, T0 128, T1 192
+constexpr uint32_t F_H0 = W_END, F_BIGA = F_H0 + IMG_S_BYTES, F_BIGB = F_BIGA + IMG_B_BYTES,
+                   F_CTRL = F_BIGB + IMG_B_BYTES, F_SMEM = F_CTRL + 64;
+
+template <bool WITH_GRAD>
+__global__ void __launch_bounds__(THREADS, 1)
+sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *__restrict__ g0) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Ctrl *ct = reinterpret_cast<Ctrl *>(smem + F_CTRL);
+    uint8_t *h0_img = smem + F_H0, *big_a = smem + F_BIGA, *big_b = smem + F_BIGB;
+    Tid t = make_tid();
+    if (t.tid == 0) {
+        tc::mbar_init(&ct->bar_w, 1);
+        tc::mbar_init(&ct->bar_mma, 1);
+        tc::mbar_fence_init();
+    }
+    if (t.warp == 0) tc::tmem_alloc(&ct->tmem_slot, 256);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = ct->tmem_slot;
+    t.tl = tmem + ((uint32_t)(t.q * 32) << 16);
+    load_weights(smem, net, ct, t.tid);
+    const float b1f = net.b1[t.f], b2f = net.b2[t.f], w30f = net.w3r0[t.f];
+    const float b3f = t.f < net.n_out ? net.b3[t.f] : 0.0f;
+    tc::mbar_wait(&ct->bar_w, 0);
+
+    const uint32_t sW1 = tc::smem_u32(smem + W1_OFF), sW2 = tc::smem_u32(smem + W2_OFF),
+                   sW3 = tc::smem_u32(smem + W3_OFF), sH0 = tc::smem_u32(h0_img), sA = tc::smem_u32(big_a),
+                   sB = tc::smem_u32(big_b);
+    const uint32_t id_kn = tc::instr_desc(128, NS, false, true);    // A K-major (W),   B MN-major (image)
+    const uint32_t id_tn = tc::instr_desc(128, NS, true, true);     // A MN-major (W^T), B MN-major
+    constexpr uint32_t Z1 = 0, Z2 = 64, T0 = 128, T1 = 192;
+    uint32_t mma_phase = 0;
+    const int n_tiles = (in.S + NS - 1) / NS;
+    float hv[8];
+    if ((int)blockIdx.x < n_tiles) load_chunk8(t, blockIdx.x * NS, in.S, net.n_in, H0_GETTER, hv);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int s0 = tile * NS;
+        store_chunk8(h0_img, t, hv);
+        // P1: Z1 = W1 h0
+        PHASE_BEGIN()
+            gemm3<KP / 16>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
+        PHASE_END()
+        // prefetch the next tile's inputs; they land while this tile computes
+        if (tile + (int)gridDim.x < n_tiles) load_chunk8(t, (tile + gridDim.x) * NS, in.S, net.n_in, H0_GETTER, hv);
+        {
+            float v[16];
+            ld16(t, Z1, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
+            st16(big_a, t, v);
+        }
+        // P2: Z2 = W2 a1
+        PHASE_BEGIN()
+            gemm3<HID / 16>(tmem + Z2, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+        PHASE_END()
+        {
+            float v[16], u[16];
+            ld16(t, Z2, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a, sg, ds;
+                sp_all(v[j] + b2f, a, sg, ds);
+                v[j] = a;
+                u[j] = sg * w30f;
+            }
+            st16(big_a, t, v);                            // a2 (a1's MMA has drained)
+            if (WITH_GRAD) st16(big_b, t, u);             // u2 = s2 . W3[0,:]
+        }
+        // P3: out = W3 a2 (lanes >= 48 are don't-care);  v1 = W2^T u2
+        PHASE_BEGIN()
+            gemm3<HID / 16>(tmem + T0, tc::op_kmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+            if (WITH_GRAD)
+                gemm3<HID / 16>(tmem + T1, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
+        PHASE_END()
+        store_rows(out, net.n_out, s0, in.S, t, T0, b3f, nullptr);
+        if (WITH_GRAD) {
+            float v[16], z[16];
+            ld16(t, T1, v);
+            ld16(t, Z1, z);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= sp_sig(z[j] + b1f);
+            st16(big_a, t, v);                            // u1 = s1 . v1
+            // P4: g0 = W1^T u1 (lanes >= 48 don't-care)
+            PHASE_BEGIN()
+                gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
+            PHASE_END()
+            store_rows(g0, net.n_in, s0, in.S, t, T0, 0.0f, nullptr);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (t.warp == 0) tc::tmem_free(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward.  TMEM columns: ACC_W2 0 (128), ACC_W1 128 (48), ACC_W3T 176 (48), Z1 224, Z2 288, T0 352, T1 416
+constexpr uint32_t B_H0 = W_END, B_H0W = B_H0 + IMG_S_BYTES, B_GO = B_H0W + IMG_S_BYTES, B_GG = B_GO + IMG_S_BYTES,
+                   B_BIGA = B_GG + IMG_S_BYTES, B_BIGB = B_BIGA + IMG_B_BYTES, B_CTRL = B_BIGB + IMG_B_BYTES,
+                   B_SMEM = B_CTRL + 64 + 4 * NS * 4;
+
+struct Grads {
+    const float *g_out, *g_g0;            // [S, n_out], [S, n_in] (g_g0 may be NULL)
+    const uint32_t *amax;                 // device: bits of max(|g_out|, |g_g0|) over the launch
+    float *g_in;                          // [S, n_in]  d/d h0 (may be NULL)
+    float *gW1, *gb1, *gW2, *gb2, *gW3, *gb3;   // atomically accumulated; caller zeroes
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    Ctrl *ct = reinterpret_cast<Ctrl *>(smem + B_CTRL);
+    uint32_t *smax = reinterpret_cast<uint32_t *>(smem + B_CTRL + 64);   // [64] per-sample |cotangent| max (bits)
+    float *ssc = reinterpret_cast<float *>(smax + NS);                    // [64] 2^k_s
+    float *sinv = ssc + NS;                                               // [64] 2^-k_s
+    float *swsc = sinv + NS;                                              // [64] 2^(K - k_s)
+    uint8_t *h0_img = smem + B_H0, *h0w_img = smem + B_H0W, *go_img = smem + B_GO, *gg_img = smem + B_GG,
+            *big_a = smem + B_BIGA, *big_b = smem + B_BIGB;
+    Tid t = make_tid();
+    if (t.tid == 0) {
+        tc::mbar_init(&ct->bar_w, 1);
+        tc::mbar_init(&ct->bar_mma, 1);
+        tc::mbar_fence_init();
+    }
+    if (t.tid < NS) smax[t.tid] = 0u;
+    if (t.warp == 0) tc::tmem_alloc(&ct->tmem_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = ct->tmem_slot;
+    t.tl = tmem + ((uint32_t)(t.q * 32) << 16);
+    load_weights(smem, net, ct, t.tid);
+    const float b1f = net.b1[t.f], b2f = net.b2[t.f], w30f = net.w3r0[t.f];
+    // launch-wide exponent: 2^K * gmax in [1, 2)
+    const int exp_g = (int)((__ldg(g.amax) >> 23) & 0xFFu);
+    tc::mbar_wait(&ct->bar_w, 0);
+
+    const uint32_t sW1 = tc::smem_u32(smem + W1_OFF), sW2 = tc::smem_u32(smem + W2_OFF),
+                   sW3 = tc::smem_u32(smem + W3_OFF), sH0 = tc::smem_u32(h0_img), sH0W = tc::smem_u32(h0w_img),
+                   sGO = tc::smem_u32(go_img), sGG = tc::smem_u32(gg_img), sA = tc::smem_u32(big_a),
+                   sB = tc::smem_u32(big_b);
+    const uint32_t id_kn = tc::instr_desc(128, NS, false, true);
+    const uint32_t id_tn = tc::instr_desc(128, NS, true, true);
+    const uint32_t id_g48 = tc::instr_desc(128, KP, false, false);    // weight-gradient products (contract samples)
+    const uint32_t id_g128 = tc::instr_desc(128, HID, false, false);
+    constexpr uint32_t AW2 = 0, AW1 = 128, AW3 = 176, Z1 = 224, Z2 = 288, T0 = 352, T1 = 416;
+    constexpr int KS = NS / 16;           // k-steps of a sample contraction
+    uint32_t mma_phase = 0;
+    float b1acc = 0.0f, b2acc = 0.0f, b3acc = 0.0f, w3acc = 0.0f;
+    const int n_tiles = (in.S + NS - 1) / NS;
+    const int cs = t.tid >> 6;            // the 8-sample chunk this thread stages
+    auto GO_GETTER = [&](int s, int f) { return __ldg(g.g_out + (size_t)s * net.n_out + f); };
+    auto GG_GETTER = [&](int s, int f) { return __ldg(g.g_g0 + (size_t)s * net.n_in + f); };
+    float hv[8], gov[8], ggv[8];
+    if ((int)blockIdx.x < n_tiles) {
+        load_chunk8(t, blockIdx.x * NS, in.S, net.n_in, H0_GETTER, hv);
+        load_chunk8(t, blockIdx.x * NS, in.S, net.n_out, GO_GETTER, gov);
+        load_chunk8(t, blockIdx.x * NS, in.S, g.g_g0 ? net.n_in : 0, GG_GETTER, ggv);
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s0 = tile * NS;
+        const bool acc = it > 0;
+        // ---- per-sample cotangent scale -----------------------------------------------------------
+        {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                b3acc += gov[j];
+                const float m = fmaxf(fabsf(gov[j]), fabsf(ggv[j]));
+                if (m > 0.0f) atomicMax(&smax[8 * cs + j], __float_as_uint(m));
+            }
+            __syncthreads();
+            if (t.tid < NS) {
+                const int e = (int)((smax[t.tid] >> 23) & 0xFFu);      // biased exponent of the sample's max
+                float sc = 1.0f, inv = 1.0f, wsc = 0.0f;
+                if (e > 0 && e < 254) {
+                    sc = __uint_as_float((uint32_t)(254 - e) << 23);   // 2^(127 - e): max -> [1, 2)
+                    inv = __uint_as_float((uint32_t)e << 23);
+                    const int d = e - exp_g;                           // <= 0
+                    wsc = d < -126 ? 0.0f : __uint_as_float((uint32_t)(127 + min(d, 0)) << 23);
+                }
+                ssc[t.tid] = sc; sinv[t.tid] = inv; swsc[t.tid] = wsc;
+                smax[t.tid] = 0u;
+            }
+            __syncthreads();
+            float hw[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float sc = ssc[8 * cs + j];
+                gov[j] *= sc; ggv[j] *= sc;
+                hw[j] = hv[j] * swsc[8 * cs + j];
+            }
+            store_chunk8(h0_img, t, hv);
+            store_chunk8(h0w_img, t, hw);
+            store_chunk8(go_img, t, gov);
+            store_chunk8(gg_img, t, ggv);
+        }
+        // P1: Z1 = W1 h0
+        PHASE_BEGIN()
+            gemm3<KP / 16>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
+        PHASE_END()
+        if (tile + (int)gridDim.x < n_tiles) {            // prefetch the next tile's rows
+            const int sn = (tile + gridDim.x) * NS;
+            load_chunk8(t, sn, in.S, net.n_in, H0_GETTER, hv);
+            load_chunk8(t, sn, in.S, net.n_out, GO_GETTER, gov);
+            load_chunk8(t, sn, in.S, g.g_g0 ? net.n_in : 0, GG_GETTER, ggv);
+        }
+        float wsc[16], inv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { wsc[j] = swsc[t.col0 + j]; inv[j] = sinv[t.col0 + j]; }
+        {
+            float v[16];
+            ld16(t, Z1, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
+            st16(big_a, t, v);                            // a1
+        }
+        // P2: Z2 = W2 a1
+        PHASE_BEGIN()
+            gemm3<HID / 16>(tmem + Z2, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+        PHASE_END()
+        {
+            float v[16], u[16];
+            ld16(t, Z2, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a, sg, ds;
+                sp_all(v[j] + b2f, a, sg, ds);
+                v[j] = a * wsc[j];
+                u[j] = sg * w30f;
+            }
+            st16(big_a, t, v);                            // a2 * 2^(K-k_s)  (weight-gradient operand only)
+            st16(big_b, t, u);                            // u2
+        }
+        // P3: gW3^T += a2 g_out^T ; v1 = W2^T u2 ; ub1 = W1 g_g0
+        PHASE_BEGIN()
+            gemm3<KS>(tmem + AW3, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGO, IMG_S_PLANE, KP), id_g48, acc);
+            gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
+            gemm3<KP / 16>(tmem + T1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sGG, IMG_S_PLANE, KP), id_kn, false);
+        PHASE_END()
+        float zp[16], vb[16];                             // z1-bar (chain part) and v1-bar, kept in registers
+        {
+            float v[16], ub[16], z[16];
+            ld16(t, T0, v);
+            ld16(t, T1, ub);
+            ld16(t, Z1, z);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a, sg, ds;
+                sp_all(z[j] + b1f, a, sg, ds);
+                vb[j] = sg * ub[j];
+                zp[j] = v[j] * ub[j] * ds;
+                v[j] *= sg * wsc[j];
+            }
+            st16(big_a, t, v);                            // u1 * 2^(K-k_s) = s1 . v1  (weight-gradient operand)
+            ld16(t, Z2, z);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = sp_sig(z[j] + b2f) * w30f * wsc[j];
+            st16(big_b, t, z);                            // u2 * 2^(K-k_s)  (v1's MMA has drained)
+        }
+        // P4: gW1 += u1 g_g0^T
+        PHASE_BEGIN()
+            gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGG, IMG_S_PLANE, KP), id_g48, acc);
+        PHASE_END()
+        st16(big_a, t, vb);                               // v1-bar
+        // P5: gW2 += u2 vb1^T ; ub2 = W2 vb1 ; ab2 = W3^T g_out
+        PHASE_BEGIN()
+            gemm3<KS>(tmem + AW2, tc::op_kmajor(sB, IMG_B_PLANE, HID), tc::op_kmajor(sA, IMG_B_PLANE, HID), id_g128, acc);
+            gemm3<HID / 16>(tmem + T0, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+            gemm3<KP / 16>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
+        PHASE_END()
+        {
+            float ub[16], ab[16], z[16];
+            ld16(t, T0, ub);
+            ld16(t, T1, ab);
+            ld16(t, Z2, z);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a, sg, ds;
+                sp_all(z[j] + b2f, a, sg, ds);
+                w3acc = fmaf(sg * ub[j], inv[j], w3acc);
+                const float zb = fmaf(ub[j] * w30f, ds, ab[j] * sg);
+                b2acc = fmaf(zb, inv[j], b2acc);
+                z[j] = zb;
+            }
+            st16(big_a, t, z);                            // z2-bar
+            ld16(t, Z1, z);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) z[j] = sp_act(z[j] + b1f) * wsc[j];
+            st16(big_b, t, z);                            // a1 * 2^(K-k_s)
+        }
+        // P6: gW2 += zb2 a1^T ; ab1 = W2^T zb2
+        PHASE_BEGIN()
+            gemm3<KS>(tmem + AW2, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sB, IMG_B_PLANE, HID), id_g128, true);
+            gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
+        PHASE_END()
+        {
+            float ab[16], z[16];
+            ld16(t, T0, ab);
+            ld16(t, Z1, z);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float zb = fmaf(ab[j], sp_sig(z[j] + b1f), zp[j]);
+                b1acc = fmaf(zb, inv[j], b1acc);
+                z[j] = zb;
+            }
+            st16(big_a, t, z);                            // z1-bar
+        }
+        // P7: gW1 += zb1 h0^T ; d/d h0 = W1^T zb1
+        PHASE_BEGIN()
+            gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sH0W, IMG_S_PLANE, KP), id_g48, true);
+            gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
+        PHASE_END()
+        if (g.g_in) store_rows(g.g_in, net.n_in, s0, in.S, t, T0, 0.0f, sinv);
+        __syncthreads();                                  // sinv/swsc are rewritten by the next tile
+    }
+    // ---- flush the weight-gradient accumulators (x 2^-K; one atomic per element per CTA) ------------
+    if (it > 0) {
+        const float ginv = (exp_g > 0 && exp_g < 255) ? __uint_as_float((uint32_t)exp_g << 23) : 0.0f;
+        float v[32];
+        {                                                 // gW2[f][32*cq + j]
+            const int cb = 32 * t.cq;
+            tc::tmem_ld32(t.tl + AW2 + (uint32_t)cb, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(g.gW2 + (size_t)t.f * HID + cb + j, v[j] * ginv);
+        }
+        if (t.cq < 3) {                                   // 48 columns: 16 per column-quarter 0..2
+            float u[16];
+            tc::tmem_ld16(t.tl + AW1 + (uint32_t)(16 * t.cq), u);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int col = 16 * t.cq + j;
+                if (col < net.n_in) atomicAdd(g.gW1 + (size_t)t.f * net.n_in + col, u[j] * ginv);
+            }
+            tc::tmem_ld16(t.tl + AW3 + (uint32_t)(16 * t.cq), u);     // gW3[o][f] from ACC_W3T[f][o]
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int col = 16 * t.cq + j;
+                if (col < net.n_out) atomicAdd(g.gW3 + (size_t)col * HID + t.f, u[j] * ginv);
+            }
+        }
+        atomicAdd(g.gW3 + t.f, w3acc);                    // the sdf head also feeds the gradient chain
+        atomicAdd(g.gb1 + t.f, b1acc);
+        atomicAdd(g.gb2 + t.f, b2acc);
+        const int fo = t.tid & 63;
+        if (fo < net.n_out) atomicAdd(g.gb3 + fo, b3acc);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (t.warp == 0) tc::tmem_free(tmem, 512);
+}
+
+// max |x| over two arrays -> *out (float bits; non-negative floats order like unsigned ints)
+__global__ void absmax2_kernel(const float *__restrict__ a, size_t na, const float *__restrict__ b, size_t nb,
+                               uint32_t *__restrict__ out) {
+    float m = 0.0f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = i0; i < na / 4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(a) + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (size_t i = (na / 4) * 4 + i0; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
+    for (size_t i = i0; i < nb / 4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(b) + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (size_t i = (nb / 4) * 4 + i0; i < nb; i += stride) m = fmaxf(m, fabsf(b[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f && m <= 3.4e38f) atomicMax(out, __float_as_uint(m));
+}
+
+bool check_net(const rsdf_sdf_mlp *n) {
+    return n && n->w1_blob && n->w2_blob && n->w3_blob && n->b1 && n->b2 && n->b3 && n->w3_row0 && n->n_in >= 1 &&
+           n->n_in <= KP && n->n_out >= 1 && n->n_out <= KP;
+}
+Net to_net(const rsdf_sdf_mlp *n) {
+    return Net{(const uint8_t *)n->w1_blob, (const uint8_t *)n->w2_blob, (const uint8_t *)n->w3_blob,
+               n->b1, n->b2, n->b3, n->w3_row0, n->n_in, n->n_out};
+}
+
+}  // namespace
+
+extern "C" {
+
+int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uint32_t *out_bits, void *stream) {
+    if (!out_bits || (na > 0 && !a) || (nb > 0 && !b) || na < 0 || nb < 0) return RSDF_EBADARG;
+    if ((((uintptr_t)a) & 15) || (((uintptr_t)b) & 15)) return RSDF_EBADARG;
+    cudaError_t e = cudaMemsetAsync(out_bits, 0, sizeof(uint32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    if (na + nb == 0) return 0;
+    absmax2_kernel<<<RSDF_NUM_SMS * 8, 256, 0, (cudaStream_t)stream>>>(a, (size_t)na, b, (size_t)nb, out_bits);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
+                     const float *in1, int w1, int n_samples, float *out, float *g0, void *stream) {
+    if (n_samples == 0) return 0;
+    if (!check_net(net) || !in0 || !out || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) || w0 + w1 != net->n_in)
+        return RSDF_EBADARG;
+    const Inputs in{in0, in1, w0, w1, scale0, shift0, n_samples};
+    const int n_tiles = (n_samples + NS - 1) / NS;
+    const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
+    cudaError_t e;
+    if (g0) {
+        e = cudaFuncSetAttribute(sdf_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        sdf_fwd_kernel<true><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, g0);
+    } else {
+        e = cudaFuncSetAttribute(sdf_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        sdf_fwd_kernel<false><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, nullptr);
+    }
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
+                     const float *in1, int w1, int n_samples, const float *g_out, const float *g_g0,
+                     const uint32_t *amax_bits, float *g_in, float *gW1, float *gb1, float *gW2, float *gb2,
+                     float *gW3, float *gb3, void *stream) {
+    if (n_samples == 0) return 0;
+    if (!check_net(net) || !in0 || !g_out || !amax_bits || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) ||
+        w0 + w1 != net->n_in || !gW1 || !gb1 || !gW2 || !gb2 || !gW3 || !gb3)
+        return RSDF_EBADARG;
+    const Inputs in{in0, in1, w0, w1, scale0, shift0, n_samples};
+    const Grads g{g_out, g_g0, amax_bits, g_in, gW1, gb1, gW2, gb2, gW3, gb3};
+    const int n_tiles = (n_samples + NS - 1) / NS;
+    const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
+    cudaError_t e = cudaFuncSetAttribute(sdf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    sdf_bwd_kernel<<<grid, THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -30,12 +30,14 @@ def pad16(n):
     return (n + 15) // 16 * 16
 
 
-def pack_weight(W):
-    """fp32 [N,K] (CUDA) -> uint8 blob of 4*N_pad*K_pad bytes."""
+def pack_weight(W, n_pad=None, k_pad=None):
+    """fp32 [N,K] (CUDA) -> uint8 blob of 4*N_pad*K_pad bytes (pads default to the next multiple of 16)."""
     W = W.detach().contiguous().float()
     N, K = W.shape
-    blob = torch.empty(4 * pad16(N) * pad16(K), dtype=torch.uint8, device=W.device)
-    L.call("rsdf_mlp_pack_weight", L.ptr(W), N, K, pad16(N), pad16(K), L.ptr(blob), L.stream())
+    n_pad, k_pad = n_pad or pad16(N), k_pad or pad16(K)
+    assert n_pad >= N and k_pad >= K and n_pad % 16 == 0 and k_pad % 16 == 0
+    blob = torch.empty(4 * n_pad * k_pad, dtype=torch.uint8, device=W.device)
+    L.call("rsdf_mlp_pack_weight", L.ptr(W), N, K, n_pad, k_pad, L.ptr(blob), L.stream())
     return blob
 
 

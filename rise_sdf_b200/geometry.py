@@ -39,8 +39,49 @@ class VolumeSDF(nn.Module):
         self._finite_difference_eps = None
         self.finite_difference_eps = config.get("finite_difference_eps", 1e-3)
 
+    fused_analytic = True       # class-wide switch (tests compare the fused and the op-by-op paths)
+
+    def _fused_parts(self):
+        """(hash-grid Encoding, level mask or None) when the analytic-normal path can run on the fused
+        SDF-field kernels (csrc/sdf_train.cu): include_xyz composite over a HashGrid, SDF-shaped MLP."""
+        from . import sdf_field, tinycudann as tcnn
+        from .network_utils import CompositeEncoding, ProgressiveBandHashGrid, VanillaMLP
+        comp = self.encoding
+        if not (VolumeSDF.fused_analytic and isinstance(comp, CompositeEncoding) and comp.include_xyz
+                and isinstance(self.network, VanillaMLP) and sdf_field.supports(self.network, comp.n_output_dims)):
+            return None
+        inner, mask = comp.encoding, None
+        if isinstance(inner, ProgressiveBandHashGrid):
+            inner, mask = inner.encoding, inner.mask
+        if not (isinstance(inner, tcnn.Encoding) and inner.kind == "hashgrid"):
+            return None
+        return inner, mask
+
+    def _forward_fused_analytic(self, points, parts):
+        """sdf, d sdf/d points, feature with ONE fused MLP node (models/geometry.py:206-228 semantics:
+        grad == autograd.grad(sdf, points, create_graph=True))."""
+        from . import sdf_field, tinycudann as tcnn
+        inner, mask = parts
+        comp = self.encoding
+        shape = points.shape[:-1]
+        x01 = contract_to_unisphere(points.reshape(-1, 3), self.radius, self.contraction_type)
+        y, dy_dx = tcnn.hashgrid_with_jacobian(inner, x01)
+        enc = y if mask is None else y * mask
+        out, g0 = sdf_field.fused_sdf(self.network, x01, comp.xyz_scale, comp.xyz_offset, enc)
+        g_enc = g0[:, 3:] if mask is None else g0[:, 3:] * mask
+        grad_x01 = tcnn.hashgrid_input_grad(inner, g_enc, x01, dy_dx) + g0[:, :3] * comp.xyz_scale
+        grad = grad_x01 / (2.0 * self.radius)          # d x01 / d points (scale_anything)
+        out = out.view(*shape, self.n_output_dims)
+        return out[..., 0], grad.view(*shape, 3), out
+
     def forward(self, points, with_grad=True, with_feature=True, with_laplace=False):
         analytic = with_grad and self.grad_type == "analytic"
+        parts = self._fused_parts() if (analytic and points.is_cuda and not with_laplace) else None
+        if parts is not None:
+            with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
+                sdf, grad, feature = self._forward_fused_analytic(points, parts)
+            rv = [sdf, grad] + ([feature] if with_feature else [])
+            return [v if self.training else v.detach() for v in rv]
         # The reference enables grad whenever self.training (models/geometry.py:208), even when the
         # caller sits under no_grad (occupancy update, sampling's alpha_fn) and the graph is thrown
         # away (SURVEY.md Appendix F).  Same numbers, no wasted graph: only build it if it can be used.

@@ -181,6 +181,13 @@ class VanillaMLP(nn.Module):
                 from .fused_mlp import PackedMLP
                 self._packed = PackedMLP(self)
             return self.output_activation(self._packed(x))
+        if x.is_cuda and x.dim() == 2 and VanillaMLP.tc_training and VanillaMLP.fused_training:
+            from . import sdf_field
+            if sdf_field.supports(self):
+                # SDF-shaped net (finite-difference evaluations of the split-sum config): one fused
+                # forward node / one fused backward kernel (csrc/sdf_train.cu)
+                out, _ = sdf_field.fused_sdf(self, x, want_g0=False)
+                return self.output_activation(out)
         if x.is_cuda and x.dim() == 2 and VanillaMLP.tc_training:
             # training: every GEMM of forward / backward / double-backward runs on tcgen05
             # (csrc/gemm_stream.cu) through differentiable primitives; activations stay in torch
@@ -198,6 +205,7 @@ class VanillaMLP(nn.Module):
     _packed = None
     fused_inference = True      # class-wide switches (tests compare the kernel and the torch paths)
     tc_training = True
+    fused_training = True
 
     def make_linear(self, dim_in, dim_out, is_first, is_last):
         layer = nn.Linear(dim_in, dim_out, bias=True)

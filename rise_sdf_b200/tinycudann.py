@@ -107,6 +107,42 @@ class _HashGridForward(torch.autograd.Function):
         return gx, gt, None
 
 
+class _HashGridForwardJ(torch.autograd.Function):
+    """(x, table) -> (y, dy_dx) with the Jacobian as an explicit, non-differentiable output: the fused
+    SDF-field path (rise_sdf_b200/sdf_field.py) contracts it with d sdf/d enc itself instead of
+    going through torch.autograd.grad."""
+
+    @staticmethod
+    def forward(ctx, x, table, meta):
+        S = x.shape[0]
+        y = torch.empty(S, meta.n_output_dims, device=x.device, dtype=torch.float32)
+        dy_dx = torch.empty(S, meta.n_output_dims, 3, device=x.device, dtype=torch.float32)
+        L.call("rsdf_hashgrid_fwd", L.ptr(x), L.ptr(table), meta.ref, S, L.ptr(y), L.ptr(dy_dx), L.stream())
+        ctx.save_for_backward(x, table, dy_dx)
+        ctx.meta = meta
+        ctx.mark_non_differentiable(dy_dx)
+        return y, dy_dx
+
+    @staticmethod
+    def backward(ctx, gy, _g_dy_dx):
+        x, table, dy_dx = ctx.saved_tensors
+        gx, gt = _HashGridBackward.apply(gy.contiguous(), x, table, dy_dx, ctx.meta, ctx.needs_input_grad[0],
+                                         ctx.needs_input_grad[1])
+        return gx, gt, None
+
+
+def hashgrid_with_jacobian(enc, x):
+    """enc: a HashGrid `Encoding`; x [S,3] in [0,1] -> (y [S,n_out], dy_dx [S,n_out,3])."""
+    L.require_cuda(x)
+    return _HashGridForwardJ.apply(x.contiguous().float(), enc.params, enc.meta)
+
+
+def hashgrid_input_grad(enc, gy, x, dy_dx):
+    """dy_dx^T gy -> [S,3]; differentiable w.r.t. gy, x and the table (second-order pass)."""
+    gx, _ = _HashGridBackward.apply(gy.contiguous(), x.contiguous().float(), enc.params, dy_dx, enc.meta, True, False)
+    return gx
+
+
 class _SHForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, degree):
