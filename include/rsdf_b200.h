@@ -225,6 +225,48 @@ int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
  * The fp16-split kernels derive their power-of-two cotangent scaling from it. */
 int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uint32_t *out_bits, void *stream);
 
+/* Training path of the ReLU VanillaMLPs (radiance / albedo / roughness / metallic / env / secondary
+ * networks: models/texture.py:15-41,234-434 over models/network_utils.py:109-157), one persistent tcgen05
+ * launch per layer.  What crosses a layer boundary is an "image stream": [n_tiles = ceil(S/64)] tiles, each
+ * the fp16 hi plane | lo plane of a [rows x 64 samples] operand in the UMMA canonical no-swizzle layout
+ * (2*rows*128 bytes per tile), moved by bulk async copies (csrc/relu_mlp.cu).
+ *   forward : rows mode (in[0] != NULL): input = cat(in[g]*in_scale[g]+in_shift[g]), optionally kept as an
+ *             image stream (a0_save);  image mode: a_in.  Output: a_out = relu(W a + b) images (r_pad == 128)
+ *             or rows_out[S, r_real] = W a + b (head; r_pad == 16).
+ *   backward: cotangent of this layer's pre-activation as an image stream zb_in (x 2^K, K from *amax) or,
+ *             for the head, row-major g_rows[S, r_real] (scaled in-kernel);  a_in = the layer's input
+ *             activation stream saved by the forward.  Produces gW[r_real, k_real] (atomic +=), and either
+ *             zb_out = (W^T zb) . [a_in > 0] for the layer below (+ its bias gradient gb_prev) or, for the
+ *             first layer, rows_out[S, k_real] = W^T zb (unscaled).  gb_self: head bias gradient. */
+typedef struct rsdf_relu_layer_fwd_args {
+    const void *w;
+    const float *bias;
+    int32_t r_pad, r_real, k_pad, n_samples;
+    const float *in[3];
+    int32_t in_w[3];
+    float in_scale[3], in_shift[3];
+    int32_t n_in;
+    const void *a_in;
+    void *a0_save;
+    void *a_out;
+    float *rows_out;
+} rsdf_relu_layer_fwd_args;
+typedef struct rsdf_relu_layer_bwd_args {
+    const void *w;
+    int32_t r_pad, r_real, k_pad, k_real, n_samples;
+    const void *zb_in;
+    const float *g_rows;
+    const uint32_t *amax;
+    const void *a_in;
+    void *zb_out;
+    float *rows_out;
+    float *gW;
+    float *gb_prev;
+    float *gb_self;
+} rsdf_relu_layer_bwd_args;
+int rsdf_relu_layer_fwd(const rsdf_relu_layer_fwd_args *args_host, void *stream);
+int rsdf_relu_layer_bwd(const rsdf_relu_layer_bwd_args *args_host, void *stream);
+
 /* self-test of the tcgen05 operand roles (see csrc/mlp_tc.cu); mode 0: C=A*W^T, 1: C=A*W,
  * 2: C+=A^T*Y */
 int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *Y, float *C, int S,

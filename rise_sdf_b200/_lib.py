@@ -28,6 +28,20 @@ class SdfMlpC(ctypes.Structure):
                 ("w3_row0", c_p), ("n_in", ctypes.c_int32), ("n_out", ctypes.c_int32)]
 
 
+class ReluFwdC(ctypes.Structure):
+    _fields_ = [("w", c_p), ("bias", c_p), ("r_pad", ctypes.c_int32), ("r_real", ctypes.c_int32),
+                ("k_pad", ctypes.c_int32), ("n_samples", ctypes.c_int32), ("inp", c_p * 3), ("in_w", ctypes.c_int32 * 3),
+                ("in_scale", ctypes.c_float * 3), ("in_shift", ctypes.c_float * 3), ("n_in", ctypes.c_int32),
+                ("a_in", c_p), ("a0_save", c_p), ("a_out", c_p), ("rows_out", c_p)]
+
+
+class ReluBwdC(ctypes.Structure):
+    _fields_ = [("w", c_p), ("r_pad", ctypes.c_int32), ("r_real", ctypes.c_int32), ("k_pad", ctypes.c_int32),
+                ("k_real", ctypes.c_int32), ("n_samples", ctypes.c_int32), ("zb_in", c_p), ("g_rows", c_p),
+                ("amax", c_p), ("a_in", c_p), ("zb_out", c_p), ("rows_out", c_p), ("gW", c_p), ("gb_prev", c_p),
+                ("gb_self", c_p)]
+
+
 # name -> argtypes (restype is int for all but the two string getters)
 _SIGS = {
     "rsdf_ray_aabb_intersect": [c_p, c_p, c_p, c_i, c_p, c_p, c_p],
@@ -64,6 +78,8 @@ _SIGS = {
     "rsdf_sdf_mlp_fwd": [c_p, c_p, c_i, c_f, c_f, c_p, c_i, c_i, c_p, c_p, c_p],
     "rsdf_sdf_mlp_bwd": [c_p, c_p, c_i, c_f, c_f, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rsdf_absmax2": [c_p, ctypes.c_longlong, c_p, ctypes.c_longlong, c_p, c_p],
+    "rsdf_relu_layer_fwd": [c_p, c_p],
+    "rsdf_relu_layer_bwd": [c_p, c_p],
     "rsdf_tc_gemm_test": [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 

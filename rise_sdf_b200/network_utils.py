@@ -188,6 +188,11 @@ class VanillaMLP(nn.Module):
                 # forward node / one fused backward kernel (csrc/sdf_train.cu)
                 out, _ = sdf_field.fused_sdf(self, x, want_g0=False)
                 return self.output_activation(out)
+            from . import relu_mlp
+            if relu_mlp.supports(self):
+                # ReLU texture networks: one tcgen05 launch per layer, fp16 hi/lo operand-image streams
+                # between layers (csrc/relu_mlp.cu)
+                return self.output_activation(relu_mlp.relu_mlp(self, x))
         if x.is_cuda and x.dim() == 2 and VanillaMLP.tc_training:
             # training: every GEMM of forward / backward / double-backward runs on tcgen05
             # (csrc/gemm_stream.cu) through differentiable primitives; activations stay in torch
