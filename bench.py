@@ -28,17 +28,55 @@ sys.path.insert(0, ROOT)
 
 N_RAYS = 8192
 METRIC = "train_rays_per_s"
-# algorithmic bytes per sample of the dominant hand-written kernel:
-# hash-grid forward with fused dy/dx: 12 (x) + 16*8*2*4 (corner reads) + 16*2*4 (y) + 3*16*2*4 (dy_dx)
-HASHGRID_FWD_BYTES = 12 + 1024 + 128 + 384
+# ALGORITHMIC work per sample and per launch of every hand-written kernel on the step.
+#   hbm kernels: bytes/sample;  tensor kernels: fp32-equivalent flops/sample (2*in*out per product; the
+#   3-product fp16 split that delivers fp32-class accuracy is NOT counted three times).
+_GEO = (35, 128, 128, 48)
+_F_FWD = 2 * (35 * 128 + 128 * 128 + 128 * 48)
+_F_CHAIN = 2 * (128 * 128 + 128 * 35)                      # g0 = W1^T (s1 . (W2^T (s2 . w3)))
+_F_BWD = (2 * (35 * 128 + 128 * 128) + _F_CHAIN            # recomputed forward + chain
+          + 2 * (35 * 128 + 128 * 128 + 48 * 128 + 128 * 128 + 128 * 35)     # data gradients
+          + 2 * (2 * 35 * 128 + 2 * 128 * 128 + 48 * 128))                   # weight gradients
+KERNEL_WORK = {
+    # hash-grid forward with fused dy/dx: 12 (x) + 16*8*2*4 (corner reads) + 16*2*4 (y) + 3*16*2*4 (dy_dx)
+    "rsdf_hashgrid_fwd": ("hbm", 12 + 1024 + 128 + 384, "hashgrid_fwd_kernel<true>"),
+    "rsdf_hashgrid_bwd_table": ("hbm", 12 + 128 + 2048, "hashgrid_bwd_table_kernel"),
+    "rsdf_hashgrid_bwd_bwd": ("hbm", 12 + 12 + 128 + 2048 + 1024 + 128, "hashgrid_bwd_bwd_kernel<table,dLdy>"),
+    "rsdf_hashgrid_bwd_input": ("hbm", 384 + 128 + 12, "hashgrid_bwd_input_kernel"),
+    "rsdf_sdf_mlp_fwd": ("tensor", _F_FWD + _F_CHAIN, "sdf_fwd_kernel<true>"),
+    "rsdf_sdf_mlp_bwd": ("tensor", _F_BWD, "sdf_bwd_kernel"),
+    # radiance MLP 67 -> 128 x4 -> 3, five launches: image streams in/out (csrc/relu_mlp.cu), per-launch average
+    "rsdf_relu_layer_fwd": ("hbm", (268 + 320 + 512 + 3 * 1024 + 512 + 12) / 5.0, "relu_layer_fwd_kernel"),
+    "rsdf_relu_layer_bwd": ("hbm", (12 + 512 + 512 + 3 * 1536 + 512 + 320 + 268) / 5.0, "relu_layer_bwd_kernel"),
+    "rsdf_neus_render_fwd": ("hbm", 64, "neus_render_fwd_kernel"),
+    "rsdf_neus_render_bwd": ("hbm", 64 + 32, "neus_render_bwd_kernel"),
+}
+# DRAM bytes per launch from the committed `ncu --set full` captures (profiles/), per sample
+NCU_TRAFFIC_PER_SAMPLE = {}
 
 
 def peaks():
+    """(hbm GB/s, dense bf16 TFLOP/s sustained, source).  The step is long, so the sustained tensor figure applies."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1500.0))), "measured"
+    return 6650.0, 1500.0, "fallback"
+
+
+def roofline_of(name, calls, total_ms, n_samples, hbm_peak, tc_peak, peak_src):
+    bound, work, kernel = KERNEL_WORK[name]
+    avg_ms = total_ms / max(calls, 1)
+    if avg_ms <= 0:
+        return None
+    if bound == "hbm":
+        achieved, peak, unit = work * n_samples / (avg_ms / 1e3) / 1e9, hbm_peak, "GB/s"
+    else:
+        achieved, peak, unit = work * n_samples / (avg_ms / 1e3) / 1e12, tc_peak, "TFLOP/s"
+    tr = NCU_TRAFFIC_PER_SAMPLE.get(name)
+    return {"bound": bound, "kernel": kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src,
+            "unit": unit, "frac": achieved / peak, "traffic": tr * n_samples if tr else None,
+            "work_per_sample": work, "avg_launch_ms": avg_ms, "launches_per_step": None}
 
 
 class ClockSampler:
@@ -239,7 +277,8 @@ def run_ours(args):
     barrier()
     # ---- timed: resident inputs -----------------------------------------------------------
     timed = ["rsdf_hashgrid_fwd", "rsdf_hashgrid_bwd_table", "rsdf_hashgrid_bwd_input", "rsdf_hashgrid_bwd_bwd",
-             "rsdf_march_count", "rsdf_march_fill", "rsdf_neus_render_fwd", "rsdf_neus_render_bwd"]
+             "rsdf_march_count", "rsdf_march_fill", "rsdf_neus_render_fwd", "rsdf_neus_render_bwd",
+             "rsdf_sdf_mlp_fwd", "rsdf_sdf_mlp_bwd", "rsdf_relu_layer_fwd", "rsdf_relu_layer_bwd", "rsdf_absmax2"]
     L.stats_reset(True, timed)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -290,10 +329,16 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * N_RAYS / (ms_step / 1e3)
     e2e_v = world * N_RAYS / (ms_e2e / args.steps / 1e3)
-    peak, peak_src = peaks()
-    hg_calls, hg_ms = ktimes.get("rsdf_hashgrid_fwd", (0, 0.0))
-    hg_avg_ms = hg_ms / max(hg_calls, 1)
-    achieved = HASHGRID_FWD_BYTES * n_samples / (hg_avg_ms / 1e3) / 1e9 if hg_avg_ms > 0 else 0.0
+    hbm_peak, tc_peak, peak_src = peaks()
+    rooflines = {}
+    for name, (calls, tot) in ktimes.items():
+        if name in KERNEL_WORK and calls:
+            r = roofline_of(name, calls, tot, n_samples, hbm_peak, tc_peak, peak_src)
+            if r:
+                r["launches_per_step"] = calls / args.steps
+                r["ms_per_step"] = tot / args.steps
+                rooflines[name] = r
+    dominant = max(rooflines, key=lambda k: rooflines[k]["ms_per_step"]) if rooflines else None
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -313,12 +358,15 @@ def run_ours(args):
                    "rays_per_gpu": N_RAYS, "samples_per_step": n_samples, "occupied_fraction": round(occ_frac, 4),
                    "cache": "4 rotating ray batches; per-step working set (hash table 50 MB + ~2 GB activations) "
                             "exceeds the 126 MB L2, no explicit flush",
-                   "parallelism": f"dp{world}", "mlp": "torch nn.Linear fp32 (cuBLAS) -- fused kernel pending"},
+                   "parallelism": f"dp{world}",
+                   "mlp": "tcgen05 kernels, fp16 hi/lo 3-product split with fp32 TMEM accumulation (fp32-class): "
+                          "fused SDF field fwd/bwd incl. 2nd order (csrc/sdf_train.cu), per-layer ReLU MLP with "
+                          "operand-image streams (csrc/relu_mlp.cu)"},
         "e2e": {"value": e2e_v, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "hashgrid_fwd_kernel<true>", "achieved": achieved, "peak": peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "bytes_per_sample": HASHGRID_FWD_BYTES, "avg_launch_ms": hg_avg_ms},
+        # the kernel with the largest share of the step; every other hand-written kernel in `rooflines`
+        "roofline": rooflines.get(dominant),
+        "rooflines": rooflines,
         "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(ktimes.items())},
         "clocks": clocks,
     }

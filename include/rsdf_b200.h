@@ -205,25 +205,31 @@ int rsdf_mm_tn(const float *A, const float *B, float *G, int S, int Fa, int Fb, 
  *   blobs: rsdf_mlp_pack_weight(W1[128,n_in], N_pad=128, K_pad=48), (W2[128,128], 128, 128),
  *          (W3[n_out,128], N_pad=48, K_pad=128);  w3_row0 = W3[0,:] in fp32.
  *   inputs: h0 = cat(in0[S,w0] * scale0 + shift0, in1[S,w1]),  w0 + w1 == n_in.
- *   fwd: out[S,n_out], g0[S,n_in] (g0 may be NULL: plain forward).
- *   bwd: cotangents g_out[S,n_out], g_g0[S,n_in] (may be NULL) -> g_in[S,n_in] = d/d h0 (may be NULL) and
- *        gW1[128,n_in], gb1[128], gW2[128,128], gb2[128], gW3[n_out,128], gb3[n_out], accumulated
- *        atomically (caller zeroes).  The forward is recomputed; nothing but h0 is kept between passes.
- *        Cotangents are rescaled per sample by powers of two inside the kernel (fp16 operand range). */
+ *   fwd: out[S,n_out]; optionally sdf[S] = out[:,0] once more as its own array; g0 split at w0 into
+ *        g0a[S,w0] = d out0/d h0[:, :w0] and g0b[S,w1] (g0a == NULL: plain forward).
+ *   bwd: cotangents g_out[S,n_out], g_sdf[S] (added to g_out[:,0]; may be NULL), g_g0a[S,w0] / g_g0b[S,w1]
+ *        (either may be NULL) -> g_in0[S,w0] = d/d in0 (scale0 applied), g_in1[S,w1] = d/d in1 (either may
+ *        be NULL) and gW1[128,n_in], gb1[128], gW2[128,128], gb2[128], gW3[n_out,128], gb3[n_out], accumulated
+ *        atomically (caller zeroes).  The forward is recomputed; nothing but the inputs is kept between passes.
+ *        Cotangents are rescaled per sample by powers of two inside the kernel (fp16 operand range);
+ *        amax_bits = rsdf_absmax2 over all cotangent arrays. */
 typedef struct rsdf_sdf_mlp {
     const void *w1_blob, *w2_blob, *w3_blob;
     const float *b1, *b2, *b3, *w3_row0;
     int32_t n_in, n_out;
 } rsdf_sdf_mlp;
 int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
-                     const float *in1, int w1, int n_samples, float *out, float *g0, void *stream);
+                     const float *in1, int w1, int n_samples, float *out, float *sdf, float *g0a, float *g0b,
+                     void *stream);
 int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
-                     const float *in1, int w1, int n_samples, const float *g_out, const float *g_g0,
-                     const uint32_t *amax_bits /* rsdf_absmax2(g_out, g_g0) */, float *g_in, float *gW1,
-                     float *gb1, float *gW2, float *gb2, float *gW3, float *gb3, void *stream);
-/* *out_bits = float bits of max(|a|, |b|) (device scalar; either array may be empty; 16-byte aligned).
- * The fp16-split kernels derive their power-of-two cotangent scaling from it. */
-int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uint32_t *out_bits, void *stream);
+                     const float *in1, int w1, int n_samples, const float *g_out, const float *g_sdf,
+                     const float *g_g0a, const float *g_g0b, const uint32_t *amax_bits, float *g_in0, float *g_in1,
+                     float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3, void *stream);
+/* *out_bits = float bits of max(|a|, |b|) (device scalar; either array may be empty; 16-byte aligned);
+ * accumulate != 0 keeps the value already in *out_bits as a third candidate.  The fp16-split kernels derive
+ * their power-of-two cotangent scaling from it. */
+int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uint32_t *out_bits, int accumulate,
+                 void *stream);
 
 /* Training path of the ReLU VanillaMLPs (radiance / albedo / roughness / metallic / env / secondary
  * networks: models/texture.py:15-41,234-434 over models/network_utils.py:109-157), one persistent tcgen05

@@ -70,7 +70,7 @@ __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.
     tc::fence_async_smem();      \
     tc::tc_fence_before();       \
     __syncthreads();             \
-    if (t.tid == 0) {            \
+    if (t.warp == 0 && tc::elect_one()) { \
         tc::tc_fence_after();
 #define PHASE_END()                          \
         tc::mma_commit(&ct->bar_mma);        \
@@ -129,14 +129,23 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
     tc::mbar_wait(&ct->bar_w, 0);
     const uint32_t sW = tc::smem_u32(smem + F_W);
     const uint32_t idesc = tc::instr_desc(128, NS, false, true);
-    const int w0 = p.in_w[0], w01 = w0 + p.in_w[1];
-    auto get = [&](int s, int f) {
-        if (f < w0) return fmaf(__ldg(p.in[0] + (size_t)s * w0 + f), p.in_scale[0], p.in_shift[0]);
-        if (f < w01) return fmaf(__ldg(p.in[1] + (size_t)s * p.in_w[1] + (f - w0)), p.in_scale[1], p.in_shift[1]);
-        return fmaf(__ldg(p.in[2] + (size_t)s * p.in_w[2] + (f - w01)), p.in_scale[2], p.in_shift[2]);
-    };
-    // rows mode staging map: feature row fr = tid % 128, chunks cr, cr + 4
+    // rows mode staging map: feature row fr = tid % 128, chunks cr, cr + 4.  A thread's feature -- hence its
+    // segment, base pointer, row stride and affine -- is fixed, so the 16 loads of a tile are branch-free
+    // and issue back to back (a per-load segment branch serialises them: 16 exposed HBM latencies per tile).
     const int fr = t.tid & 127, cr = t.tid >> 7;
+    const float *rbase = p.in[0];
+    int rstride = 0;
+    float rsc = 0.0f, rsh = 0.0f;
+    if (rows_in && fr < p.n_in) {
+        const int w0 = p.in_w[0], w01 = w0 + p.in_w[1];
+        const int g = fr < w0 ? 0 : (fr < w01 ? 1 : 2);
+        const int f0 = g == 0 ? 0 : (g == 1 ? w0 : w01);
+        rbase = p.in[g] + (fr - f0);
+        rstride = p.in_w[g];
+        rsc = p.in_scale[g];
+        rsh = p.in_shift[g];
+    }
+    const bool rvalid = rows_in && fr < p.n_in;
     float rv[2][8];
     auto load_rows = [&](int s0) {
 #pragma unroll
@@ -144,7 +153,8 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int s = s0 + 8 * (cr + 4 * k) + j;
-                rv[k][j] = (fr < p.n_in && s < p.S) ? get(s, fr) : 0.0f;
+                const float x = __ldg(rbase + (size_t)min(s, p.S - 1) * rstride);
+                rv[k][j] = (rvalid && s < p.S) ? fmaf(x, rsc, rsh) : 0.0f;
             }
     };
     if (rows_in && (int)blockIdx.x < n_tiles) load_rows(blockIdx.x * NS);
@@ -273,7 +283,8 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int s = s0 + 8 * cr + j;
-            gv[j] = (t.tid < 128 && fr < p.r_real && s < p.S) ? __ldg(p.g_rows + (size_t)s * p.r_real + fr) : 0.0f;
+            const float x = __ldg(p.g_rows + (size_t)min(s, p.S - 1) * p.r_real + min(fr, p.r_real - 1));
+            gv[j] = (t.tid < 128 && fr < p.r_real && s < p.S) ? x : 0.0f;
         }
     };
     if (rows_in && (int)blockIdx.x < n_tiles) load_g(blockIdx.x * NS);

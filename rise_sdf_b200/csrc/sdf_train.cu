@@ -96,43 +96,69 @@ __device__ __forceinline__ void gemm3(uint32_t d, const tc::Operand &A, const tc
     for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_hi + k * ak, b_hi + k * bk, idesc, true);
 }
 
+__device__ __forceinline__ float exp2f_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // softplus(beta=100, threshold=20) and its first two derivatives, torch semantics (aten softplus /
 // softplus_backward / its double-backward formula).  With e = exp(-|t|) in (0,1]:
 //   softplus = max(z,0) + log(1+e)/beta,  sigmoid(t) = 1/(1+e) or e/(1+e),  sigmoid' = beta e/(1+e)^2.
 // The fast intrinsics are safe here: their absolute error (~2^-22) is divided by beta = 100 in the
 // activation and enters the derivatives at <= 3e-7.
-__device__ __forceinline__ void sp_all(float z, float &a, float &s, float &ds) {
-    const float t = 100.0f * z;
-    if (t > 20.0f) { a = z; s = 1.0f; ds = 0.0f; return; }
-    const float e = __expf(-fabsf(t));
+// Branch-free: for t > 20, e < 2.1e-9 so 1 + e == 1 in fp32 and the activation / sigmoid reduce to z / 1
+// exactly as torch's threshold branch does; only sigmoid' needs the explicit select.
+constexpr float SP_K = 100.0f * 1.4426950408889634f;          // beta * log2(e)
+constexpr float SP_L = 0.01f * 0.6931471805599453f;           // ln(2) / beta
+__device__ __forceinline__ void sp_sig_dsig(float z, float &s, float &ds) {
+    const float e = exp2f_fast(-fabsf(z) * SP_K);
     const float r = __fdividef(1.0f, 1.0f + e);
-    a = fmaf(0.01f, __logf(1.0f + e), fmaxf(z, 0.0f));
-    s = t >= 0.0f ? r : e * r;
-    ds = 100.0f * e * r * r;
+    const float er = e * r;
+    s = z >= 0.0f ? r : er;
+    ds = z > 0.2f ? 0.0f : 100.0f * er * r;
+}
+__device__ __forceinline__ void sp_all(float z, float &a, float &s, float &ds) {
+    const float e = exp2f_fast(-fabsf(z) * SP_K);
+    const float r = __fdividef(1.0f, 1.0f + e);
+    const float er = e * r;
+    a = fmaf(SP_L, __log2f(1.0f + e), fmaxf(z, 0.0f));
+    s = z >= 0.0f ? r : er;
+    ds = z > 0.2f ? 0.0f : 100.0f * er * r;
 }
 __device__ __forceinline__ float sp_act(float z) {
-    const float t = 100.0f * z;
-    if (t > 20.0f) return z;
-    return fmaf(0.01f, __logf(1.0f + __expf(-fabsf(t))), fmaxf(z, 0.0f));
+    return fmaf(SP_L, __log2f(1.0f + exp2f_fast(-fabsf(z) * SP_K)), fmaxf(z, 0.0f));
 }
 __device__ __forceinline__ float sp_sig(float z) {
-    const float t = 100.0f * z;
-    if (t > 20.0f) return 1.0f;
-    const float e = __expf(-fabsf(t));
+    const float e = exp2f_fast(-fabsf(z) * SP_K);
     const float r = __fdividef(1.0f, 1.0f + e);
-    return t >= 0.0f ? r : e * r;
+    return z >= 0.0f ? r : e * r;
 }
 
-// One 8-sample chunk (samples s0 + 8c .. +7) of feature row f, straight from row-major global memory:
-// a warp reads 32 consecutive floats of one sample row per load (coalesced).  Thread -> (f = tid % 64,
-// c = tid / 64); rows f >= KP do not exist.
-template <typename G>
-__device__ __forceinline__ void load_chunk8(const Tid &t, int s0, int S, int n_feat, G get, float *v) {
-    const int f = t.tid & 63, c = t.tid >> 6;
+// Row-major global -> registers: thread (f = tid % 64, c = tid / 64) fetches the 8-sample chunk
+// (samples s0 + 8c .. +7) of feature row f; a warp reads 32 consecutive floats of one sample row per
+// load (coalesced).  The thread's feature -- hence its source array, column and affine -- is fixed for
+// the whole kernel, so the loads are branch-free and issue back to back.
+struct RowSrc {
+    const float *base;                    // &array[0][column of this thread's feature]
+    int stride;                           // floats per row
+    float sc, sh;
+    bool valid;
+};
+__device__ __forceinline__ RowSrc row_src(const float *a, int wa, float sca, float sha, const float *b, int wb, int f) {
+    RowSrc r{a, 0, 0.0f, 0.0f, false};
+    if (f < wa) { if (a) r = RowSrc{a + f, wa, sca, sha, true}; }
+    else if (f < wa + wb) { if (b) r = RowSrc{b + (f - wa), wb, 1.0f, 0.0f, true}; }
+    if (!r.valid) r.base = a ? a : b;
+    return r;
+}
+template <bool AFFINE = true>
+__device__ __forceinline__ void load_chunk8(const RowSrc &r, int tid, int s0, int S, float *v) {
+    const int c = tid >> 6;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int s = s0 + 8 * c + j;
-        v[j] = (f < n_feat && s < S) ? get(s, f) : 0.0f;
+        const float x = r.base ? __ldg(r.base + (size_t)min(s, S - 1) * r.stride) : 0.0f;
+        v[j] = (r.valid && s < S) ? (AFFINE ? fmaf(x, r.sc, r.sh) : x) : 0.0f;
     }
 }
 __device__ __forceinline__ void store_chunk8(uint8_t *img, const Tid &t, const float *v) {
@@ -140,17 +166,26 @@ __device__ __forceinline__ void store_chunk8(uint8_t *img, const Tid &t, const f
     if (f < KP) tc::store_chunk(img, IMG_S_PLANE, KP, f, c, v);
 }
 
-// TMEM [feature lanes < w][64 samples] -> row-major out[S, w]:  out[s, f] = (acc + bias_f) * mul[s]
-__device__ __forceinline__ void store_rows(float *__restrict__ out, int w, int s0, int S, const Tid &t, int col,
-                                           float bias, const float *mul) {
+// TMEM [feature lanes < wa + wb][64 samples] -> two row-major arrays split at feature wa:
+//   f < wa : outa[s, f] = (acc + bias_f) * mul[s] * sca          f >= wa : outb[s, f - wa] = (acc + bias_f) * mul[s]
+// (either array may be NULL; outb == NULL with wb == 0 is the single-array case)
+__device__ __forceinline__ void store_rows(float *__restrict__ outa, int wa, float sca, float *__restrict__ outb,
+                                           int wb, int s0, int S, const Tid &t, int col, float bias,
+                                           const float *mul) {
+    const int w = wa + wb;
     if (t.q * 32 >= w) return;            // warp-uniform
     float v[16];
     ld16(t, col, v);
     if (t.f < w) {
+        const bool a = t.f < wa;
+        float *dst = a ? outa : outb;
+        if (!dst) return;
+        const int wd = a ? wa : wb, fd = a ? t.f : t.f - wa;
+        const float sc = a ? sca : 1.0f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int s = s0 + t.col0 + j;
-            if (s < S) out[(size_t)s * w + t.f] = (v[j] + bias) * (mul ? mul[t.col0 + j] : 1.0f);
+            if (s < S) dst[(size_t)s * wd + fd] = (v[j] + bias) * (mul ? mul[t.col0 + j] : 1.0f) * sc;
         }
     }
 }
@@ -174,24 +209,34 @@ __device__ __forceinline__ void load_weights(uint8_t *smem, const Net &net, Ctrl
 }
 
 // publish this thread's smem image writes / TMEM reads, then let thread 0 issue the next MMA group
+#ifdef RSDF_PROFILE_PHASES
+// developer instrumentation (scripts/prof_phases.py): thread 0 of CTA 0 accumulates clock64 deltas
+//   [0] epilogue (previous PHASE_END -> PHASE_BEGIN)  [1] fences + __syncthreads  [2] MMA issue  [3] MMA wait
+__device__ unsigned long long g_prof[8];
+#define PROF_DECL() long long pt_ = clock64(); unsigned long long pa_[4] = {0, 0, 0, 0};
+#define PROF_MARK(i) { const long long n_ = clock64(); pa_[i] += (unsigned long long)(n_ - pt_); pt_ = n_; }
+#define PROF_FLUSH() if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < 4; ++i_) g_prof[i_] = pa_[i_]; }
+#else
+#define PROF_DECL()
+#define PROF_MARK(i)
+#define PROF_FLUSH()
+#endif
 #define PHASE_BEGIN()            \
+    PROF_MARK(0)                 \
     tc::fence_async_smem();      \
     tc::tc_fence_before();       \
     __syncthreads();             \
-    if (t.tid == 0) {            \
+    PROF_MARK(1)                 \
+    if (t.warp == 0 && tc::elect_one()) { \
         tc::tc_fence_after();
 #define PHASE_END()                          \
         tc::mma_commit(&ct->bar_mma);        \
     }                                        \
+    PROF_MARK(2)                             \
     tc::mbar_wait(&ct->bar_mma, mma_phase);  \
     mma_phase ^= 1;                          \
-    tc::tc_fence_after();
-
-#define H0_GETTER                                                                               \
-    [&](int s, int f) {                                                                         \
-        return f < in.w0 ? fmaf(__ldg(in.in0 + (size_t)s * in.w0 + f), in.sc0, in.sh0)          \
-                         : __ldg(in.in1 + (size_t)s * in.w1 + (f - in.w0));                     \
-    }
+    tc::tc_fence_after();                    \
+    PROF_MARK(3)
 
 // ------------------------------------------------------------------------------------------------
 // forward: out[S, n_out] and (WITH_GRAD) g0[S, n_in] = d out[:,0] / d h0
@@ -201,7 +246,8 @@ constexpr uint32_t F_H0 = W_END, F_BIGA = F_H0 + IMG_S_BYTES, F_BIGB = F_BIGA + 
 
 template <bool WITH_GRAD>
 __global__ void __launch_bounds__(THREADS, 1)
-sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *__restrict__ g0) {
+sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *__restrict__ sdf,
+               float *__restrict__ g0a, float *__restrict__ g0b) {
     extern __shared__ __align__(1024) uint8_t smem[];
     Ctrl *ct = reinterpret_cast<Ctrl *>(smem + F_CTRL);
     uint8_t *h0_img = smem + F_H0, *big_a = smem + F_BIGA, *big_b = smem + F_BIGB;
@@ -229,9 +275,11 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
     const uint32_t id_tn = tc::instr_desc(128, NS, true, true);     // A MN-major (W^T), B MN-major
     constexpr uint32_t Z1 = 0, Z2 = 64, T0 = 128, T1 = 192;
     uint32_t mma_phase = 0;
+    PROF_DECL()
     const int n_tiles = (in.S + NS - 1) / NS;
+    const RowSrc src_h = row_src(in.in0, in.w0, in.sc0, in.sh0, in.in1, in.w1, t.tid & 63);
     float hv[8];
-    if ((int)blockIdx.x < n_tiles) load_chunk8(t, blockIdx.x * NS, in.S, net.n_in, H0_GETTER, hv);
+    if ((int)blockIdx.x < n_tiles) load_chunk8(src_h, t.tid, blockIdx.x * NS, in.S, hv);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int s0 = tile * NS;
         store_chunk8(h0_img, t, hv);
@@ -240,7 +288,7 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
             gemm3<KP / 16>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
         PHASE_END()
         // prefetch the next tile's inputs; they land while this tile computes
-        if (tile + (int)gridDim.x < n_tiles) load_chunk8(t, (tile + gridDim.x) * NS, in.S, net.n_in, H0_GETTER, hv);
+        if (tile + (int)gridDim.x < n_tiles) load_chunk8(src_h, t.tid, (tile + gridDim.x) * NS, in.S, hv);
         {
             float v[16];
             ld16(t, Z1, v);
@@ -271,7 +319,16 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
             if (WITH_GRAD)
                 gemm3<HID / 16>(tmem + T1, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
         PHASE_END()
-        store_rows(out, net.n_out, s0, in.S, t, T0, b3f, nullptr);
+        store_rows(out, net.n_out, 1.0f, nullptr, 0, s0, in.S, t, T0, b3f, nullptr);
+        if (sdf && t.q == 0) {            // the sdf head (feature row 0) once more as its own [S] array
+            float v[16];
+            ld16(t, T0, v);
+            if (t.f == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (s0 + t.col0 + j < in.S) sdf[s0 + t.col0 + j] = v[j] + b3f;
+            }
+        }
         if (WITH_GRAD) {
             float v[16], z[16];
             ld16(t, T1, v);
@@ -283,9 +340,10 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
             PHASE_BEGIN()
                 gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
             PHASE_END()
-            store_rows(g0, net.n_in, s0, in.S, t, T0, 0.0f, nullptr);
+            store_rows(g0a, in.w0, 1.0f, g0b, in.w1, s0, in.S, t, T0, 0.0f, nullptr);
         }
     }
+    PROF_FLUSH()
     tc::tc_fence_before();
     __syncthreads();
     if (t.warp == 0) tc::tmem_free(tmem, 256);
@@ -298,9 +356,10 @@ constexpr uint32_t B_H0 = W_END, B_H0W = B_H0 + IMG_S_BYTES, B_GO = B_H0W + IMG_
                    B_SMEM = B_CTRL + 64 + 4 * NS * 4;
 
 struct Grads {
-    const float *g_out, *g_g0;            // [S, n_out], [S, n_in] (g_g0 may be NULL)
-    const uint32_t *amax;                 // device: bits of max(|g_out|, |g_g0|) over the launch
-    float *g_in;                          // [S, n_in]  d/d h0 (may be NULL)
+    const float *g_out, *g_sdf;           // [S, n_out], [S] (added to g_out[:, 0]; may be NULL)
+    const float *g_g0a, *g_g0b;           // cotangent of g0, split at w0: [S, w0], [S, w1] (either may be NULL)
+    const uint32_t *amax;                 // device: bits of the launch-wide cotangent maximum
+    float *g_in0, *g_in1;                 // d/d in0 [S, w0] (chain rule through scale0 applied), d/d in1 [S, w1]
     float *gW1, *gb1, *gW2, *gb2, *gW3, *gb3;   // atomically accumulated; caller zeroes
 };
 
@@ -344,17 +403,28 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
     constexpr uint32_t AW2 = 0, AW1 = 128, AW3 = 176, Z1 = 224, Z2 = 288, T0 = 352, T1 = 416;
     constexpr int KS = NS / 16;           // k-steps of a sample contraction
     uint32_t mma_phase = 0;
+    PROF_DECL()
     float b1acc = 0.0f, b2acc = 0.0f, b3acc = 0.0f, w3acc = 0.0f;
     const int n_tiles = (in.S + NS - 1) / NS;
     const int cs = t.tid >> 6;            // the 8-sample chunk this thread stages
-    auto GO_GETTER = [&](int s, int f) { return __ldg(g.g_out + (size_t)s * net.n_out + f); };
-    auto GG_GETTER = [&](int s, int f) { return __ldg(g.g_g0 + (size_t)s * net.n_in + f); };
+    const RowSrc src_h = row_src(in.in0, in.w0, in.sc0, in.sh0, in.in1, in.w1, t.tid & 63);
+    const RowSrc src_go = row_src(g.g_out, net.n_out, 1.0f, 0.0f, nullptr, 0, t.tid & 63);
+    const RowSrc src_gg = row_src(g.g_g0a, in.w0, 1.0f, 0.0f, g.g_g0b, in.w1, t.tid & 63);
+    const bool add_sdf = g.g_sdf != nullptr && (t.tid & 63) == 0;      // g_sdf joins feature row 0 of g_out
     float hv[8], gov[8], ggv[8];
-    if ((int)blockIdx.x < n_tiles) {
-        load_chunk8(t, blockIdx.x * NS, in.S, net.n_in, H0_GETTER, hv);
-        load_chunk8(t, blockIdx.x * NS, in.S, net.n_out, GO_GETTER, gov);
-        load_chunk8(t, blockIdx.x * NS, in.S, g.g_g0 ? net.n_in : 0, GG_GETTER, ggv);
-    }
+    auto load_tile = [&](int s0) {
+        load_chunk8(src_h, t.tid, s0, in.S, hv);
+        load_chunk8<false>(src_go, t.tid, s0, in.S, gov);
+        load_chunk8<false>(src_gg, t.tid, s0, in.S, ggv);
+        if (add_sdf) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int s = s0 + 8 * cs + j;
+                if (s < in.S) gov[j] += __ldg(g.g_sdf + s);
+            }
+        }
+    };
+    if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x * NS);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const int s0 = tile * NS;
@@ -374,8 +444,8 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
                 if (e > 0 && e < 254) {
                     sc = __uint_as_float((uint32_t)(254 - e) << 23);   // 2^(127 - e): max -> [1, 2)
                     inv = __uint_as_float((uint32_t)e << 23);
-                    const int d = e - exp_g;                           // <= 0
-                    wsc = d < -126 ? 0.0f : __uint_as_float((uint32_t)(127 + min(d, 0)) << 23);
+                    const int d = e - exp_g;                           // <= 0 (+1 when g_sdf adds onto g_out[:,0])
+                    wsc = d < -126 ? 0.0f : __uint_as_float((uint32_t)(127 + min(d, 8)) << 23);
                 }
                 ssc[t.tid] = sc; sinv[t.tid] = inv; swsc[t.tid] = wsc;
                 smax[t.tid] = 0u;
@@ -397,15 +467,8 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
         PHASE_BEGIN()
             gemm3<KP / 16>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
         PHASE_END()
-        if (tile + (int)gridDim.x < n_tiles) {            // prefetch the next tile's rows
-            const int sn = (tile + gridDim.x) * NS;
-            load_chunk8(t, sn, in.S, net.n_in, H0_GETTER, hv);
-            load_chunk8(t, sn, in.S, net.n_out, GO_GETTER, gov);
-            load_chunk8(t, sn, in.S, g.g_g0 ? net.n_in : 0, GG_GETTER, ggv);
-        }
-        float wsc[16], inv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { wsc[j] = swsc[t.col0 + j]; inv[j] = sinv[t.col0 + j]; }
+        if (tile + (int)gridDim.x < n_tiles) load_tile((tile + gridDim.x) * NS);      // prefetch the next tile's rows
+        const float *wsc = swsc + t.col0, *inv = sinv + t.col0;    // per-sample factors (smem broadcasts)
         {
             float v[16];
             ld16(t, Z1, v);
@@ -444,8 +507,8 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
             ld16(t, Z1, z);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float a, sg, ds;
-                sp_all(z[j] + b1f, a, sg, ds);
+                float sg, ds;
+                sp_sig_dsig(z[j] + b1f, sg, ds);
                 vb[j] = sg * ub[j];
                 zp[j] = v[j] * ub[j] * ds;
                 v[j] *= sg * wsc[j];
@@ -474,8 +537,8 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
             ld16(t, Z2, z);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float a, sg, ds;
-                sp_all(z[j] + b2f, a, sg, ds);
+                float sg, ds;
+                sp_sig_dsig(z[j] + b2f, sg, ds);
                 w3acc = fmaf(sg * ub[j], inv[j], w3acc);
                 const float zb = fmaf(ub[j] * w30f, ds, ab[j] * sg);
                 b2acc = fmaf(zb, inv[j], b2acc);
@@ -509,7 +572,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
             gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sH0W, IMG_S_PLANE, KP), id_g48, true);
             gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
         PHASE_END()
-        if (g.g_in) store_rows(g.g_in, net.n_in, s0, in.S, t, T0, 0.0f, sinv);
+        if (g.g_in0 || g.g_in1) store_rows(g.g_in0, in.w0, in.sc0, g.g_in1, in.w1, s0, in.S, t, T0, 0.0f, sinv);
         __syncthreads();                                  // sinv/swsc are rewritten by the next tile
     }
     // ---- flush the weight-gradient accumulators (x 2^-K; one atomic per element per CTA) ------------
@@ -546,6 +609,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
         const int fo = t.tid & 63;
         if (fo < net.n_out) atomicAdd(g.gb3 + fo, b3acc);
     }
+    PROF_FLUSH()
     tc::tc_fence_before();
     __syncthreads();
     if (t.warp == 0) tc::tmem_free(tmem, 512);
@@ -584,11 +648,20 @@ Net to_net(const rsdf_sdf_mlp *n) {
 
 extern "C" {
 
-int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uint32_t *out_bits, void *stream) {
+#ifdef RSDF_PROFILE_PHASES
+int rsdf_debug_read_prof(unsigned long long *host8) {
+    return (int)cudaMemcpyFromSymbol(host8, g_prof, sizeof(unsigned long long) * 8);
+}
+#endif
+
+int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uint32_t *out_bits, int accumulate,
+                 void *stream) {
     if (!out_bits || (na > 0 && !a) || (nb > 0 && !b) || na < 0 || nb < 0) return RSDF_EBADARG;
     if ((((uintptr_t)a) & 15) || (((uintptr_t)b) & 15)) return RSDF_EBADARG;
-    cudaError_t e = cudaMemsetAsync(out_bits, 0, sizeof(uint32_t), (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(out_bits, 0, sizeof(uint32_t), (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     if (na + nb == 0) return 0;
     absmax2_kernel<<<RSDF_NUM_SMS * 8, 256, 0, (cudaStream_t)stream>>>(a, (size_t)na, b, (size_t)nb, out_bits);
     RSDF_LAUNCH_CHECK();
@@ -596,37 +669,39 @@ int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uin
 }
 
 int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
-                     const float *in1, int w1, int n_samples, float *out, float *g0, void *stream) {
+                     const float *in1, int w1, int n_samples, float *out, float *sdf, float *g0a, float *g0b,
+                     void *stream) {
     if (n_samples == 0) return 0;
-    if (!check_net(net) || !in0 || !out || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) || w0 + w1 != net->n_in)
+    if (!check_net(net) || !in0 || !out || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) || w0 + w1 != net->n_in ||
+        (g0a && w1 > 0 && !g0b))
         return RSDF_EBADARG;
     const Inputs in{in0, in1, w0, w1, scale0, shift0, n_samples};
     const int n_tiles = (n_samples + NS - 1) / NS;
     const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
     cudaError_t e;
-    if (g0) {
+    if (g0a) {
         e = cudaFuncSetAttribute(sdf_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
         if (e != cudaSuccess) return (int)e;
-        sdf_fwd_kernel<true><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, g0);
+        sdf_fwd_kernel<true><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, g0a, g0b);
     } else {
         e = cudaFuncSetAttribute(sdf_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
         if (e != cudaSuccess) return (int)e;
-        sdf_fwd_kernel<false><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, nullptr);
+        sdf_fwd_kernel<false><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, nullptr, nullptr);
     }
     RSDF_LAUNCH_CHECK();
     return 0;
 }
 
 int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
-                     const float *in1, int w1, int n_samples, const float *g_out, const float *g_g0,
-                     const uint32_t *amax_bits, float *g_in, float *gW1, float *gb1, float *gW2, float *gb2,
-                     float *gW3, float *gb3, void *stream) {
+                     const float *in1, int w1, int n_samples, const float *g_out, const float *g_sdf,
+                     const float *g_g0a, const float *g_g0b, const uint32_t *amax_bits, float *g_in0, float *g_in1,
+                     float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3, void *stream) {
     if (n_samples == 0) return 0;
     if (!check_net(net) || !in0 || !g_out || !amax_bits || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) ||
         w0 + w1 != net->n_in || !gW1 || !gb1 || !gW2 || !gb2 || !gW3 || !gb3)
         return RSDF_EBADARG;
     const Inputs in{in0, in1, w0, w1, scale0, shift0, n_samples};
-    const Grads g{g_out, g_g0, amax_bits, g_in, gW1, gb1, gW2, gb2, gW3, gb3};
+    const Grads g{g_out, g_sdf, g_g0a, g_g0b, amax_bits, g_in0, g_in1, gW1, gb1, gW2, gb2, gW3, gb3};
     const int n_tiles = (n_samples + NS - 1) / NS;
     const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
     cudaError_t e = cudaFuncSetAttribute(sdf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM);

@@ -21,6 +21,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// one lane of a fully active warp (warp-uniform call site): lets the compiler issue tcgen05.mma
+// straight-line instead of wrapping every instruction in an ELECT / BRA.U.ANY loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -154,17 +167,16 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // x = hi + lo with hi = fp16(x), lo = fp16(x - hi): two 11-bit significands -> the three kept
 // products (hi*hi + hi*lo + lo*hi) carry ~2^-22 relative error per term, i.e. fp32-class GEMMs.
 // (A bf16 split would stop at 2^-17, which finite-difference SDF normals amplify ~1400x.)
-// fp16's narrow exponent is harmless here: |x| is clamped to the fp16 range (MLP activations and
+// fp16's narrow exponent is harmless here: |x| saturates at the fp16 range (MLP activations and
 // weights are O(1)), and a lo part that drops into the subnormal range still has an ABSOLUTE
 // error <= 2^-25, far below the fp32 accumulation error of an O(1) pre-activation.
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-    x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
-    x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
-    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-    const __half l0 = __float2half_rn(x0 - __half2float(h0));
-    const __half l1 = __float2half_rn(x1 - __half2float(h1));
-    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    // 6 instructions per PAIR: one saturating packed conversion (F2FP.SATFINITE.F16.F32.PACK_AB) per
+    // plane, two widening moves and two fp32 subtractions
+    float f0, f1;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    asm("{ .reg .b16 a, b; mov.b32 {a, b}, %2; cvt.f32.f16 %0, a; cvt.f32.f16 %1, b; }" : "=f"(f0), "=f"(f1) : "r"(hi));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - f1), "f"(x0 - f0));
 }
 // write 8 consecutive columns [c*8, c*8+8) of row r into a tile image (hi plane at img,
 // lo plane at img + plane_bytes); rows = tile height (128)

@@ -67,12 +67,11 @@ class VolumeSDF(nn.Module):
         x01 = contract_to_unisphere(points.reshape(-1, 3), self.radius, self.contraction_type)
         y, dy_dx = tcnn.hashgrid_with_jacobian(inner, x01)
         enc = y if mask is None else y * mask
-        out, g0 = sdf_field.fused_sdf(self.network, x01, comp.xyz_scale, comp.xyz_offset, enc)
-        g_enc = g0[:, 3:] if mask is None else g0[:, 3:] * mask
-        grad_x01 = tcnn.hashgrid_input_grad(inner, g_enc, x01, dy_dx) + g0[:, :3] * comp.xyz_scale
+        out, sdf, g0_xyz, g0_enc = sdf_field.fused_sdf_parts(self.network, x01, comp.xyz_scale, comp.xyz_offset, enc)
+        g_enc = g0_enc if mask is None else g0_enc * mask
+        grad_x01 = tcnn.hashgrid_input_grad(inner, g_enc, x01, dy_dx) + g0_xyz * comp.xyz_scale
         grad = grad_x01 / (2.0 * self.radius)          # d x01 / d points (scale_anything)
-        out = out.view(*shape, self.n_output_dims)
-        return out[..., 0], grad.view(*shape, 3), out
+        return sdf.view(*shape), grad.view(*shape, 3), out.view(*shape, self.n_output_dims)
 
     def forward(self, points, with_grad=True, with_feature=True, with_laplace=False):
         analytic = with_grad and self.grad_type == "analytic"

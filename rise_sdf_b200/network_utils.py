@@ -178,8 +178,11 @@ class VanillaMLP(nn.Module):
         if x.is_cuda and not torch.is_grad_enabled() and x.dim() == 2 and VanillaMLP.fused_inference:
             # inference: the whole chain runs in one fused tcgen05 kernel (csrc/mlp_tc.cu)
             if self._packed is None:
+                from . import sdf_field
                 from .fused_mlp import PackedMLP
-                self._packed = PackedMLP(self)
+                # SDF-shaped nets run on the features-on-lanes kernel (csrc/sdf_train.cu, ~2x the rows/s of
+                # the generic chain kernel); everything else on csrc/mlp_fwd.cu
+                self._packed = sdf_field.PackedSDF(self) if sdf_field.supports(self) else PackedMLP(self)
             return self.output_activation(self._packed(x))
         if x.is_cuda and x.dim() == 2 and VanillaMLP.tc_training and VanillaMLP.fused_training:
             from . import sdf_field
@@ -206,6 +209,23 @@ class VanillaMLP(nn.Module):
             return self.output_activation(h)
         x = self.layers(x.float())
         return self.output_activation(x)
+
+    def forward_segments(self, segs):
+        """forward(cat(segs, -1)) without materialising the concatenation when a fused kernel takes the
+        segments directly (models/texture.py builds its network inputs with torch.cat)."""
+        segs = [s.reshape(-1, s.shape[-1]) for s in segs]
+        x0 = segs[0]
+        if x0.is_cuda and len(segs) <= 3 and not self.sphere_init:
+            if not torch.is_grad_enabled() and VanillaMLP.fused_inference:
+                if self._packed is None:
+                    from .fused_mlp import PackedMLP
+                    self._packed = PackedMLP(self)
+                return self.output_activation(self._packed(segs))
+            if torch.is_grad_enabled() and VanillaMLP.tc_training and VanillaMLP.fused_training:
+                from . import relu_mlp
+                if relu_mlp.supports(self):
+                    return self.output_activation(relu_mlp.relu_mlp(self, segs))
+        return self.forward(torch.cat(segs, dim=-1))
 
     _packed = None
     fused_inference = True      # class-wide switches (tests compare the kernel and the torch paths)

@@ -87,7 +87,7 @@ class _ReluMLP(torch.autograd.Function):
             g_out = g_out.contiguous().float()
             n_tiles = (S + NS - 1) // NS
             amax = torch.empty(1, device=dev, dtype=torch.int32)
-            L.call("rsdf_absmax2", L.ptr(g_out), g_out.numel(), None, 0, L.ptr(amax), L.stream())
+            L.call("rsdf_absmax2", L.ptr(g_out), g_out.numel(), None, 0, L.ptr(amax), 0, L.stream())
             zb = None
             for i in range(len(Ws) - 1, -1, -1):
                 p = L.ReluBwdC()
@@ -113,7 +113,11 @@ class _ReluMLP(torch.autograd.Function):
         g_segs, off = [], 0
         for g in range(ctx.n_seg):
             w = ctx.seg_w[g]
-            g_segs.append(g_in[:, off:off + w] * ctx.scales[g] if ctx.needs_input_grad[3 + g] else None)
+            if not ctx.needs_input_grad[3 + g]:
+                g_segs.append(None)
+            else:
+                gs = g_in[:, off:off + w]
+                g_segs.append(gs if ctx.scales[g] == 1.0 else gs * ctx.scales[g])
             off += w
         g_params = []
         for gW, gb in zip(gWs, gbs):

@@ -37,7 +37,23 @@ def _net_struct(W1, b1, W2, b2, W3, b3):
     return c, keep
 
 
+def _absmax(tensors, dev):
+    """Device scalar (int32 bits of a float) = max |x| over the given tensors (None entries skipped)."""
+    amax = torch.empty(1, device=dev, dtype=torch.int32)
+    ts = [t for t in tensors if t is not None]
+    for i in range(0, max(len(ts), 1), 2):
+        a = ts[i] if i < len(ts) else None
+        b = ts[i + 1] if i + 1 < len(ts) else None
+        L.call("rsdf_absmax2", L.ptr(a), 0 if a is None else a.numel(), L.ptr(b), 0 if b is None else b.numel(),
+               L.ptr(amax), 1 if i else 0, L.stream())
+    return amax
+
+
 class _FusedSDF(torch.autograd.Function):
+    """(in0, in1, W1..b3) -> (out [S,n_out], sdf [S] = out[:,0], g0a [S,w0], g0b [S,w1]).  sdf and the two
+    halves of g0 are separate outputs so that no slice/select backward (zero-fill + copy + add over
+    [S,48] / [S,35]) appears in the graph: the backward kernel takes the four cotangents directly."""
+
     @staticmethod
     def forward(ctx, in0, in1, W1, b1, W2, b2, W3, b3, scale0, shift0, want_g0):
         L.require_cuda(in0, in1, W1)
@@ -45,52 +61,91 @@ class _FusedSDF(torch.autograd.Function):
         in1 = None if in1 is None else in1.contiguous().float()
         S, w0 = in0.shape
         w1 = 0 if in1 is None else in1.shape[1]
+        dev = in0.device
         net, keep = _net_struct(W1, b1, W2, b2, W3, b3)
-        out = torch.empty(S, W3.shape[0], device=in0.device, dtype=torch.float32)
-        g0 = torch.empty(S, w0 + w1, device=in0.device, dtype=torch.float32) if want_g0 else None
+        out = torch.empty(S, W3.shape[0], device=dev, dtype=torch.float32)
+        sdf = torch.empty(S, device=dev, dtype=torch.float32)
+        g0a = torch.empty(S, w0, device=dev, dtype=torch.float32) if want_g0 else None
+        g0b = torch.empty(S, w1, device=dev, dtype=torch.float32) if (want_g0 and w1) else None
         if S:
             L.call("rsdf_sdf_mlp_fwd", ctypes.byref(net), L.ptr(in0), w0, float(scale0), float(shift0), L.ptr(in1), w1,
-                   S, L.ptr(out), L.ptr(g0), L.stream())
+                   S, L.ptr(out), L.ptr(sdf), L.ptr(g0a), L.ptr(g0b), L.stream())
         ctx.save_for_backward(in0, in1, W1, b1, W2, b2, W3, b3)
         ctx.net, ctx.keep, ctx.scale0, ctx.shift0 = net, keep, float(scale0), float(shift0)
-        if not want_g0:
-            g0 = in0.new_zeros(0)
-            ctx.mark_non_differentiable(g0)
-        return out, g0
+        empty = []
+        if g0a is None:
+            g0a = in0.new_zeros(0); empty.append(g0a)
+        if g0b is None:
+            g0b = in0.new_zeros(0); empty.append(g0b)
+        if empty:
+            ctx.mark_non_differentiable(*empty)
+        return out, sdf, g0a, g0b
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, g_out, g_g0):
+    def backward(ctx, g_out, g_sdf, g_g0a, g_g0b):
         in0, in1, W1, b1, W2, b2, W3, b3 = ctx.saved_tensors
         S, w0 = in0.shape
         w1 = 0 if in1 is None else in1.shape[1]
         dev = in0.device
-        g_out = g_out.contiguous().float()
-        g_g0 = None if (g_g0 is None or g_g0.numel() == 0) else g_g0.contiguous().float()
-        need_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        g_in = torch.empty(S, w0 + w1, device=dev, dtype=torch.float32) if need_in else None
+        prep = lambda g: None if (g is None or g.numel() == 0) else g.contiguous().float()
+        g_out, g_sdf, g_g0a, g_g0b = prep(g_out), prep(g_sdf), prep(g_g0a), prep(g_g0b)
+        if g_out is None:
+            g_out = torch.zeros(S, W3.shape[0], device=dev, dtype=torch.float32)
+        g_in0 = torch.empty(S, w0, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        g_in1 = torch.empty(S, w1, device=dev, dtype=torch.float32) if (ctx.needs_input_grad[1] and w1) else None
         gW1, gb1, gW2, gb2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2)
         gW3, gb3 = torch.zeros_like(W3), torch.zeros_like(b3)
         if S:
-            amax = torch.empty(1, device=dev, dtype=torch.int32)
-            L.call("rsdf_absmax2", L.ptr(g_out), g_out.numel(), L.ptr(g_g0), 0 if g_g0 is None else g_g0.numel(),
-                   L.ptr(amax), L.stream())
+            amax = _absmax([g_out, g_sdf, g_g0a, g_g0b], dev)
             L.call("rsdf_sdf_mlp_bwd", ctypes.byref(ctx.net), L.ptr(in0), w0, ctx.scale0, ctx.shift0, L.ptr(in1), w1, S,
-                   L.ptr(g_out), L.ptr(g_g0), L.ptr(amax), L.ptr(g_in), L.ptr(gW1), L.ptr(gb1), L.ptr(gW2),
-                   L.ptr(gb2), L.ptr(gW3), L.ptr(gb3), L.stream())
-        elif need_in:
-            g_in.zero_()
-        g_in0 = g_in1 = None
-        if ctx.needs_input_grad[0]:
-            g_in0 = g_in[:, :w0] * ctx.scale0
-        if ctx.needs_input_grad[1] and in1 is not None:
-            g_in1 = g_in[:, w0:]
+                   L.ptr(g_out), L.ptr(g_sdf), L.ptr(g_g0a), L.ptr(g_g0b), L.ptr(amax), L.ptr(g_in0), L.ptr(g_in1),
+                   L.ptr(gW1), L.ptr(gb1), L.ptr(gW2), L.ptr(gb2), L.ptr(gW3), L.ptr(gb3), L.stream())
         return g_in0, g_in1, gW1, gb1, gW2, gb2, gW3, gb3, None, None, None
+
+
+def fused_sdf_parts(mlp, in0, scale0=1.0, shift0=0.0, in1=None, want_g0=True):
+    """-> (out [S, dim_out], sdf [S], g0a [S, w0] | None, g0b [S, w1] | None)."""
+    (W1, b1), (W2, b2), (W3, b3) = mlp.effective_weights()
+    out, sdf, g0a, g0b = _FusedSDF.apply(in0, in1, W1.float(), b1.float(), W2.float(), b2.float(), W3.float(),
+                                         b3.float(), scale0, shift0, want_g0)
+    if not want_g0:
+        return out, sdf, None, None
+    return out, sdf, g0a, (g0b if in1 is not None else None)
 
 
 def fused_sdf(mlp, in0, scale0=1.0, shift0=0.0, in1=None, want_g0=True):
     """-> (out [S, dim_out], g0 [S, dim_in] or None).  `mlp`: a VanillaMLP for which supports() holds."""
-    (W1, b1), (W2, b2), (W3, b3) = mlp.effective_weights()
-    out, g0 = _FusedSDF.apply(in0, in1, W1.float(), b1.float(), W2.float(), b2.float(), W3.float(), b3.float(),
-                              scale0, shift0, want_g0)
-    return out, (g0 if want_g0 else None)
+    out, _, g0a, g0b = fused_sdf_parts(mlp, in0, scale0, shift0, in1, want_g0)
+    if not want_g0:
+        return out, None
+    return out, (g0a if g0b is None else torch.cat([g0a, g0b], -1))
+
+
+class PackedSDF:
+    """Inference-side cache of the packed weight images of an SDF-shaped VanillaMLP (re-packed when a
+    parameter changes); runs the forward kernel without autograd.  Used by the eval / relighting render,
+    the occupancy update and the finite-difference evaluations (7 per sample in the split-sum config)."""
+
+    def __init__(self, mlp):
+        self.mlp, self._key, self._net, self._keep = mlp, None, None, None
+
+    def _struct(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.mlp.parameters())
+        if key != self._key:
+            with torch.no_grad():
+                (W1, b1), (W2, b2), (W3, b3) = self.mlp.effective_weights()
+                self._net, self._keep = _net_struct(W1.float(), b1.float(), W2.float(), b2.float(), W3.float(), b3.float())
+            self._key = key
+        return self._net
+
+    @torch.no_grad()
+    def __call__(self, x):
+        L.require_cuda(x)
+        x = x.contiguous().float()
+        S = x.shape[0]
+        out = torch.empty(S, self.mlp.dim_out, device=x.device, dtype=torch.float32)
+        if S:
+            L.call("rsdf_sdf_mlp_fwd", ctypes.byref(self._struct()), L.ptr(x), x.shape[1], 1.0, 0.0, None, 0, S,
+                   L.ptr(out), None, None, None, L.stream())
+        return out

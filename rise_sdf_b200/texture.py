@@ -21,9 +21,12 @@ class VolumeRadiance(nn.Module):
     def forward(self, features, dirs, *args):
         dirs = (dirs + 1.0) / 2.0
         dirs_embd = self.encoding(dirs.view(-1, self.n_dir_dims))
-        network_inp = torch.cat([features.view(-1, features.shape[-1]), dirs_embd]
-                                + [arg.view(-1, arg.shape[-1]) for arg in args], dim=-1)
-        color = self.network(network_inp).view(*features.shape[:-1], self.n_output_dims).float()
+        segs = [features.view(-1, features.shape[-1]), dirs_embd] + [arg.view(-1, arg.shape[-1]) for arg in args]
+        if hasattr(self.network, "forward_segments"):
+            color = self.network.forward_segments(segs)
+        else:
+            color = self.network(torch.cat(segs, dim=-1))
+        color = color.view(*features.shape[:-1], self.n_output_dims).float()
         if "color_activation" in self.config:
             color = get_activation(self.config.color_activation)(color)
         return color
@@ -82,14 +85,14 @@ class VolumeMixedMipSplitOcc(nn.Module):
         wo = torch.sum(wi * normals, -1, keepdim=True) * normals * 2 - wi
         NoV = torch.sum(normals * wi, -1, keepdim=True)
         xyz_embd = self.xyz_encoding(positions.view(-1, self.n_pos_dims))
-        network_inp = torch.cat([features.view(-1, features.shape[-1]), xyz_embd], dim=-1)
-        albedo = self.albedo_network(network_inp).view(*features.shape[:-1], 6).float()
+        network_inp = [features.view(-1, features.shape[-1]), xyz_embd]
+        albedo = self.albedo_network.forward_segments(network_inp).view(*features.shape[:-1], 6).float()
         diff_rgb, albedo = albedo[..., :3], albedo[..., 3:]
-        roughness = self.roughness_network(network_inp).view(*features.shape[:-1], 1).float()
-        metallic = self.metallic_network(network_inp).view(*features.shape[:-1], 2).float()
+        roughness = self.roughness_network.forward_segments(network_inp).view(*features.shape[:-1], 1).float()
+        metallic = self.metallic_network.forward_segments(network_inp).view(*features.shape[:-1], 2).float()
         blend, metallic = metallic[..., :1], metallic[..., 1:]
         wo_enc = self.dir_encoding(((wo + 1.0) / 2.0).view(-1, self.n_dir_dims))
-        spec_rgb = self.env_network(torch.cat([features, wo_enc], dim=-1)).view(*features.shape[:-1], 3).float()
+        spec_rgb = self.env_network.forward_segments([features, wo_enc]).view(*features.shape[:-1], 3).float()
         albedo, diff_rgb, blend = self._act(albedo), self._act(diff_rgb), self._act(blend)
         metallic, roughness, spec_rgb = self._act(metallic), self._act(roughness), self._act(spec_rgb)
         spec_rgb = blend * spec_rgb
