@@ -43,6 +43,9 @@ KERNEL_WORK = {
     "rsdf_hashgrid_bwd_table": ("hbm", 12 + 128 + 2048, "hashgrid_bwd_table_kernel"),
     "rsdf_hashgrid_bwd_bwd": ("hbm", 12 + 12 + 128 + 2048 + 1024 + 128, "hashgrid_bwd_bwd_kernel<table,dLdy>"),
     "rsdf_hashgrid_bwd_input": ("hbm", 384 + 128 + 12, "hashgrid_bwd_input_kernel"),
+    # first + second order table scatter in one pass: x, v, dL_dy, g2, one atomic RMW per corner
+    "rsdf_hashgrid_bwd_table2": ("hbm", 12 + 12 + 128 + 128 + 2048, "hashgrid_bwd_table2_kernel"),
+    "rsdf_hashgrid_jvp": ("hbm", 384 + 12 + 128, "hashgrid_jvp_kernel"),
     "rsdf_sdf_mlp_fwd": ("tensor", _F_FWD + _F_CHAIN, "sdf_fwd_kernel<true>"),
     "rsdf_sdf_mlp_bwd": ("tensor", _F_BWD, "sdf_bwd_kernel"),
     # radiance MLP 67 -> 128 x4 -> 3, five launches: image streams in/out (csrc/relu_mlp.cu), per-launch average
@@ -278,7 +281,8 @@ def run_ours(args):
     # ---- timed: resident inputs -----------------------------------------------------------
     timed = ["rsdf_hashgrid_fwd", "rsdf_hashgrid_bwd_table", "rsdf_hashgrid_bwd_input", "rsdf_hashgrid_bwd_bwd",
              "rsdf_march_count", "rsdf_march_fill", "rsdf_neus_render_fwd", "rsdf_neus_render_bwd",
-             "rsdf_sdf_mlp_fwd", "rsdf_sdf_mlp_bwd", "rsdf_relu_layer_fwd", "rsdf_relu_layer_bwd", "rsdf_absmax2"]
+             "rsdf_sdf_mlp_fwd", "rsdf_sdf_mlp_bwd", "rsdf_relu_layer_fwd", "rsdf_relu_layer_bwd", "rsdf_absmax2",
+             "rsdf_hashgrid_bwd_table2", "rsdf_hashgrid_jvp", "rsdf_sh_fwd", "rsdf_sh_bwd"]
     L.stats_reset(True, timed)
     sampler = ClockSampler(local)
     if rank == 0:

@@ -128,6 +128,14 @@ int rsdf_hashgrid_bwd_bwd(const float *x, const float *table, const float *v, co
                           const rsdf_hashgrid_meta *meta, int n_samples, float *grad_table,
                           float *grad_dL_dy, float *grad_x, void *stream);
 
+/* First- and second-order table gradients of the SAME samples in one scatter pass:
+ * grad_table += (d y/d table)^T dL_dy + d/d table <v, dy_dx^T g2>  (== rsdf_hashgrid_bwd_table followed by
+ * rsdf_hashgrid_bwd_bwd with grad_table only; one atomic per corner instead of two). */
+int rsdf_hashgrid_bwd_table2(const float *x, const float *dL_dy, const float *v, const float *g2,
+                             const rsdf_hashgrid_meta *meta, int n_samples, float *grad_table, void *stream);
+/* g[S,n_out] = dy_dx[S,n_out,3] . v[S,3]: the d(dL_dy) output of the second-order pass from the stored Jacobian */
+int rsdf_hashgrid_jvp(const float *dy_dx, const float *v, int n_samples, int n_out, float *g, void *stream);
+
 /* tinycudann.Encoding(3, SphericalHarmonics): u[S,3] in [0,1] -> out[S,degree^2] */
 int rsdf_sh_fwd(const float *u, int n_samples, int degree, float *out, void *stream);
 /* grad wrt u */

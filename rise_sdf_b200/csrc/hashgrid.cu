@@ -307,6 +307,57 @@ hashgrid_bwd_bwd_kernel(const float *__restrict__ x, const float *__restrict__ t
     }
 }
 
+// First- and second-order table gradients in ONE scatter pass (one atomic per corner instead of two):
+//   grad_table[c][f] += w(c) * dL_dy[f]  +  (sum_d v_d sgn_d(c) prod_{d'!=d} w_d'(c)) * scale * g2[f]
+// i.e. hashgrid_bwd_table_kernel + hashgrid_bwd_bwd_kernel<TO_TABLE> of the same samples, where
+// g2 = d sdf / d enc (the cotangent the analytic normal pulls through the encoding) and v = d loss / d normal.
+__global__ void __launch_bounds__(THREADS)
+hashgrid_bwd_table2_kernel(const float *__restrict__ x, const float *__restrict__ dL_dy, const float *__restrict__ v,
+                           const float *__restrict__ g2, const Meta m, int n_samples, float *__restrict__ grad_table) {
+    const int n_out = m.n_levels * NFEAT;
+    const int ls = threadIdx.x / TILE_S;
+    const int t = threadIdx.x % TILE_S;
+    const int s = blockIdx.x * TILE_S + t;
+    const bool ok = s < n_samples;
+    float px = 0.f, py = 0.f, pz = 0.f, vv[3] = {0.f, 0.f, 0.f};
+    if (ok) {
+        px = x[3 * s]; py = x[3 * s + 1]; pz = x[3 * s + 2];
+        vv[0] = v[3 * s]; vv[1] = v[3 * s + 1]; vv[2] = v[3 * s + 2];
+    }
+    for (int l = ls; l < m.n_levels; l += THREADS / TILE_S) {
+        const float scale = m.scale[l];
+        const uint32_t res = m.res[l], off = m.offset[l], size = m.offset[l + 1] - off;
+        float2 gy = make_float2(0.f, 0.f), gq = make_float2(0.f, 0.f);
+        if (ok) {
+            gy = __ldg(reinterpret_cast<const float2 *>(dL_dy + (size_t)s * n_out) + l);
+            gq = __ldg(reinterpret_cast<const float2 *>(g2 + (size_t)s * n_out) + l);
+        }
+        const Cell c = locate(px, py, pz, scale);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float wd[3] = {(k & 1) ? c.w[0] : 1.0f - c.w[0], (k & 2) ? c.w[1] : 1.0f - c.w[1],
+                                 (k & 4) ? c.w[2] : 1.0f - c.w[2]};
+            const float sg[3] = {(k & 1) ? scale : -scale, (k & 2) ? scale : -scale, (k & 4) ? scale : -scale};
+            const float wt = wd[0] * wd[1] * wd[2];
+            const float coef = vv[0] * sg[0] * wd[1] * wd[2] + vv[1] * sg[1] * wd[0] * wd[2] +
+                               vv[2] * sg[2] * wd[0] * wd[1];
+            const uint32_t idx = grid_index(c.c[0] + (k & 1), c.c[1] + ((k >> 1) & 1), c.c[2] + (k >> 2), res, size);
+            scatter_add2(grad_table, off + idx, fmaf(coef, gq.x, wt * gy.x), fmaf(coef, gq.y, wt * gy.y), ok);
+        }
+    }
+}
+
+// g[s][f] = sum_d dy_dx[s][f][d] * v[s][d]   (the d(dL_dy) leg of the second-order pass, from the
+// Jacobian the forward already wrote: no table gathers)
+__global__ void hashgrid_jvp_kernel(const float *__restrict__ dy_dx, const float *__restrict__ v, long long n,
+                                    int n_out, float *__restrict__ g) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (sample, feature)
+    if (i >= n) return;
+    const long long s = i / n_out;
+    const float *q = dy_dx + i * 3, *vs = v + s * 3;
+    g[i] = fmaf(q[2], vs[2], fmaf(q[1], vs[1], q[0] * vs[0]));
+}
+
 bool load_meta(const rsdf_hashgrid_meta *h, Meta &m) {
     if (!h || h->n_levels < 1 || h->n_levels > RSDF_MAX_LEVELS || h->n_features != NFEAT) return false;
     m.n_levels = h->n_levels;
@@ -481,6 +532,26 @@ int rsdf_hashgrid_bwd_bwd(const float *x, const float *table, const float *v, co
         default: return 0;
     }
 #undef RSDF_BB
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_hashgrid_bwd_table2(const float *x, const float *dL_dy, const float *v, const float *g2,
+                             const rsdf_hashgrid_meta *meta, int n_samples, float *grad_table, void *stream) {
+    if (n_samples == 0) return 0;
+    Meta m;
+    if (!x || !dL_dy || !v || !g2 || !grad_table || !load_meta(meta, m)) return RSDF_EBADARG;
+    hashgrid_bwd_table2_kernel<<<rsdf_div_up(n_samples, TILE_S), THREADS, 0, (cudaStream_t)stream>>>(
+        x, dL_dy, v, g2, m, n_samples, grad_table);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_hashgrid_jvp(const float *dy_dx, const float *v, int n_samples, int n_out, float *g, void *stream) {
+    if (n_samples == 0) return 0;
+    if (!dy_dx || !v || !g || n_out < 1) return RSDF_EBADARG;
+    const long long n = (long long)n_samples * n_out;
+    hashgrid_jvp_kernel<<<rsdf_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(dy_dx, v, n, n_out, g);
     RSDF_LAUNCH_CHECK();
     return 0;
 }

@@ -431,11 +431,15 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
         const bool acc = it > 0;
         // ---- per-sample cotangent scale -----------------------------------------------------------
         {
+            // per-sample max over the feature rows: a warp holds 32 rows of the same 8 samples, so one
+            // redux.sync per sample and a single shared atomic per warp (48 same-address atomics per
+            // sample serialise into ~3000 bank-conflict wavefronts per tile otherwise)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 b3acc += gov[j];
                 const float m = fmaxf(fabsf(gov[j]), fabsf(ggv[j]));
-                if (m > 0.0f) atomicMax(&smax[8 * cs + j], __float_as_uint(m));
+                const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                if (t.lane == 0 && wm != 0u) atomicMax(&smax[8 * cs + j], wm);
             }
             __syncthreads();
             if (t.tid < NS) {

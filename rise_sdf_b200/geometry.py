@@ -65,17 +65,20 @@ class VolumeSDF(nn.Module):
         comp = self.encoding
         shape = points.shape[:-1]
         x01 = contract_to_unisphere(points.reshape(-1, 3), self.radius, self.contraction_type)
-        y, dy_dx = tcnn.hashgrid_with_jacobian(inner, x01)
+        y, dy_dx, link = tcnn.hashgrid_with_jacobian(inner, x01)
         enc = y if mask is None else y * mask
         out, sdf, g0_xyz, g0_enc = sdf_field.fused_sdf_parts(self.network, x01, comp.xyz_scale, comp.xyz_offset, enc)
         g_enc = g0_enc if mask is None else g0_enc * mask
-        grad_x01 = tcnn.hashgrid_input_grad(inner, g_enc, x01, dy_dx) + g0_xyz * comp.xyz_scale
+        grad_x01 = tcnn.hashgrid_input_grad(inner, g_enc, x01, dy_dx, link) + g0_xyz * comp.xyz_scale
         grad = grad_x01 / (2.0 * self.radius)          # d x01 / d points (scale_anything)
         return sdf.view(*shape), grad.view(*shape, 3), out.view(*shape, self.n_output_dims)
 
     def forward(self, points, with_grad=True, with_feature=True, with_laplace=False):
         analytic = with_grad and self.grad_type == "analytic"
-        parts = self._fused_parts() if (analytic and points.is_cuda and not with_laplace) else None
+        # (sample positions are data on the render path; a caller that differentiates w.r.t. the points
+        # themselves takes the op-by-op autograd path below)
+        parts = self._fused_parts() if (analytic and points.is_cuda and not with_laplace
+                                        and not points.requires_grad) else None
         if parts is not None:
             with torch.set_grad_enabled(self.training and torch.is_grad_enabled()):
                 sdf, grad, feature = self._forward_fused_analytic(points, parts)

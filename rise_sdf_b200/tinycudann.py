@@ -107,40 +107,95 @@ class _HashGridForward(torch.autograd.Function):
         return gx, gt, None
 
 
+class _Link:
+    """Shared by the two autograd nodes of the fused analytic-normal path.  The second-order node runs
+    first in the backward sweep (its output feeds the MLP node) and, instead of scattering its table
+    gradient right away, parks (v, g2) here; the first-order node then adds both contributions to the
+    table with ONE scatter pass (rsdf_hashgrid_bwd_table2)."""
+    __slots__ = ("v", "g2")
+
+    def __init__(self):
+        self.v = self.g2 = None
+
+
 class _HashGridForwardJ(torch.autograd.Function):
     """(x, table) -> (y, dy_dx) with the Jacobian as an explicit, non-differentiable output: the fused
     SDF-field path (rise_sdf_b200/sdf_field.py) contracts it with d sdf/d enc itself instead of
     going through torch.autograd.grad."""
 
     @staticmethod
-    def forward(ctx, x, table, meta):
+    def forward(ctx, x, table, meta, link):
         S = x.shape[0]
         y = torch.empty(S, meta.n_output_dims, device=x.device, dtype=torch.float32)
         dy_dx = torch.empty(S, meta.n_output_dims, 3, device=x.device, dtype=torch.float32)
         L.call("rsdf_hashgrid_fwd", L.ptr(x), L.ptr(table), meta.ref, S, L.ptr(y), L.ptr(dy_dx), L.stream())
         ctx.save_for_backward(x, table, dy_dx)
-        ctx.meta = meta
+        ctx.meta, ctx.link = meta, link
         ctx.mark_non_differentiable(dy_dx)
         return y, dy_dx
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gy, _g_dy_dx):
         x, table, dy_dx = ctx.saved_tensors
-        gx, gt = _HashGridBackward.apply(gy.contiguous(), x, table, dy_dx, ctx.meta, ctx.needs_input_grad[0],
-                                         ctx.needs_input_grad[1])
-        return gx, gt, None
+        S, n_out = gy.shape
+        gy = gy.contiguous()
+        link, gx, gt = ctx.link, None, None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty(S, 3, device=gy.device, dtype=torch.float32)
+            L.call("rsdf_hashgrid_bwd_input", L.ptr(dy_dx), L.ptr(gy), S, n_out, L.ptr(gx), L.stream())
+        if ctx.needs_input_grad[1]:
+            gt = torch.zeros_like(table)
+            if link is not None and link.v is not None:
+                L.call("rsdf_hashgrid_bwd_table2", L.ptr(x), L.ptr(gy), L.ptr(link.v), L.ptr(link.g2), ctx.meta.ref, S,
+                       L.ptr(gt), L.stream())
+                link.v = link.g2 = None
+            else:
+                L.call("rsdf_hashgrid_bwd_table", L.ptr(x), L.ptr(gy), ctx.meta.ref, S, L.ptr(gt), L.stream())
+        return gx, gt, None, None
+
+
+class _HashGridInputGrad(torch.autograd.Function):
+    """(g2, dy_dx; x, table) -> dy_dx^T g2 [S,3] for the fused path.  Backward (the second-order pass):
+    d/d g2 = dy_dx . v from the stored Jacobian; the table leg is deferred to the linked first-order
+    node (see _Link).  x is not differentiated on this path (sample positions are data)."""
+
+    @staticmethod
+    def forward(ctx, g2, dy_dx, x, table, meta, link):
+        S, n_out = g2.shape
+        g2 = g2.contiguous()
+        gx = torch.empty(S, 3, device=g2.device, dtype=torch.float32)
+        L.call("rsdf_hashgrid_bwd_input", L.ptr(dy_dx), L.ptr(g2), S, n_out, L.ptr(gx), L.stream())
+        ctx.save_for_backward(g2, dy_dx, x, table)
+        ctx.meta, ctx.link = meta, link
+        return gx
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, v):
+        g2, dy_dx, x, table = ctx.saved_tensors
+        S, n_out = g2.shape
+        v = v.contiguous()
+        g_g2 = None
+        if ctx.needs_input_grad[0]:
+            g_g2 = torch.empty_like(g2)
+            L.call("rsdf_hashgrid_jvp", L.ptr(dy_dx), L.ptr(v), S, n_out, L.ptr(g_g2), L.stream())
+        if table.requires_grad:
+            ctx.link.v, ctx.link.g2 = v, g2
+        return g_g2, None, None, None, None, None
 
 
 def hashgrid_with_jacobian(enc, x):
-    """enc: a HashGrid `Encoding`; x [S,3] in [0,1] -> (y [S,n_out], dy_dx [S,n_out,3])."""
+    """enc: a HashGrid `Encoding`; x [S,3] in [0,1] -> (y [S,n_out], dy_dx [S,n_out,3], link)."""
     L.require_cuda(x)
-    return _HashGridForwardJ.apply(x.contiguous().float(), enc.params, enc.meta)
+    link = _Link()
+    y, dy_dx = _HashGridForwardJ.apply(x.contiguous().float(), enc.params, enc.meta, link)
+    return y, dy_dx, link
 
 
-def hashgrid_input_grad(enc, gy, x, dy_dx):
-    """dy_dx^T gy -> [S,3]; differentiable w.r.t. gy, x and the table (second-order pass)."""
-    gx, _ = _HashGridBackward.apply(gy.contiguous(), x.contiguous().float(), enc.params, dy_dx, enc.meta, True, False)
-    return gx
+def hashgrid_input_grad(enc, g2, x, dy_dx, link):
+    """dy_dx^T g2 -> [S,3]; differentiable w.r.t. g2 and (through the linked forward node) the table."""
+    return _HashGridInputGrad.apply(g2, dy_dx, x.contiguous().float(), enc.params, enc.meta, link)
 
 
 class _SHForward(torch.autograd.Function):
