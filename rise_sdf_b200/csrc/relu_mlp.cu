@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
                 const float x = __ldg(rbase + (size_t)min(s, p.S - 1) * rstride);
                 rv[k][j] = (rvalid && s < p.S) ? fmaf(x, rsc, rsh) : 0.0f;
             }
+        (void)0;
     };
     if (rows_in && (int)blockIdx.x < n_tiles) load_rows(blockIdx.x * NS);
     uint32_t mma_phase = 0;
@@ -193,11 +194,16 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
         } else if (t.q * 32 < p.r_real) {
             float v[16];
             ld16(t, 0, v);
-            if (t.f < p.r_real) {
+            const int sb = s0 + t.col0;
+            if (t.f < p.r_real && sb < p.S) {
+                float *o = p.rows_out + (size_t)sb * p.r_real + t.f;
+                if (sb + 16 <= p.S) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int s = s0 + t.col0 + j;
-                    if (s < p.S) p.rows_out[(size_t)s * p.r_real + t.f] = v[j] + bf;
+                    for (int j = 0; j < 16; ++j) o[j * p.r_real] = v[j] + bf;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (sb + j < p.S) o[j * p.r_real] = v[j] + bf;
                 }
             }
         }
@@ -323,11 +329,16 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
         } else if (t.q * 32 < p.k_real) {
             float v[16];
             ld16(t, T0, v);
-            if (t.f < p.k_real) {
+            const int sb = s0 + t.col0;
+            if (t.f < p.k_real && sb < p.S) {
+                float *o = p.rows_out + (size_t)sb * p.k_real + t.f;
+                if (sb + 16 <= p.S) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int s = s0 + t.col0 + j;
-                    if (s < p.S) p.rows_out[(size_t)s * p.k_real + t.f] = v[j] * ginv;
+                    for (int j = 0; j < 16; ++j) o[j * p.k_real] = v[j] * ginv;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (sb + j < p.S) o[j * p.k_real] = v[j] * ginv;
                 }
             }
         }

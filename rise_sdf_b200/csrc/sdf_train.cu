@@ -153,12 +153,24 @@ __device__ __forceinline__ RowSrc row_src(const float *a, int wa, float sca, flo
 }
 template <bool AFFINE = true>
 __device__ __forceinline__ void load_chunk8(const RowSrc &r, int tid, int s0, int S, float *v) {
-    const int c = tid >> 6;
+    const int sb = s0 + 8 * (tid >> 6);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int s = s0 + 8 * c + j;
-        const float x = r.base ? __ldg(r.base + (size_t)min(s, S - 1) * r.stride) : 0.0f;
-        v[j] = (r.valid && s < S) ? (AFFINE ? fmaf(x, r.sc, r.sh) : x) : 0.0f;
+    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    if (!r.valid || sb >= S) return;
+    const float *p = r.base + (size_t)sb * r.stride;
+    if (sb + 8 <= S) {                    // full chunk: 8 independent loads, constant stride
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x = __ldg(p + j * r.stride);
+            v[j] = AFFINE ? fmaf(x, r.sc, r.sh) : x;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (sb + j < S) {
+                const float x = __ldg(p + j * r.stride);
+                v[j] = AFFINE ? fmaf(x, r.sc, r.sh) : x;
+            }
     }
 }
 __device__ __forceinline__ void store_chunk8(uint8_t *img, const Tid &t, const float *v) {
@@ -176,17 +188,27 @@ __device__ __forceinline__ void store_rows(float *__restrict__ outa, int wa, flo
     if (t.q * 32 >= w) return;            // warp-uniform
     float v[16];
     ld16(t, col, v);
-    if (t.f < w) {
-        const bool a = t.f < wa;
-        float *dst = a ? outa : outb;
-        if (!dst) return;
-        const int wd = a ? wa : wb, fd = a ? t.f : t.f - wa;
-        const float sc = a ? sca : 1.0f;
+    if (t.f >= w) return;
+    const bool a = t.f < wa;
+    float *dst = a ? outa : outb;
+    const int sb = s0 + t.col0;
+    if (!dst || sb >= S) return;
+    const int wd = a ? wa : wb, fd = a ? t.f : t.f - wa;
+    const float sc = a ? sca : 1.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int s = s0 + t.col0 + j;
-            if (s < S) dst[(size_t)s * wd + fd] = (v[j] + bias) * (mul ? mul[t.col0 + j] : 1.0f) * sc;
-        }
+    for (int j = 0; j < 16; ++j) v[j] = (v[j] + bias) * sc;
+    if (mul) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= mul[t.col0 + j];
+    }
+    float *p = dst + (size_t)sb * wd + fd;
+    if (sb + 16 <= S) {                   // full column block: 16 stores, constant stride, no predicates
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p[j * wd] = v[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (sb + j < S) p[j * wd] = v[j];
     }
 }
 
@@ -324,9 +346,17 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
             float v[16];
             ld16(t, T0, v);
             if (t.f == 0) {
+                const int sb = s0 + t.col0;
+                if (sb + 16 <= in.S) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (s0 + t.col0 + j < in.S) sdf[s0 + t.col0 + j] = v[j] + b3f;
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4 *>(sdf + sb + j) =
+                            make_float4(v[j] + b3f, v[j + 1] + b3f, v[j + 2] + b3f, v[j + 3] + b3f);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (sb + j < in.S) sdf[sb + j] = v[j] + b3f;
+                }
             }
         }
         if (WITH_GRAD) {
@@ -417,11 +447,10 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
         load_chunk8<false>(src_go, t.tid, s0, in.S, gov);
         load_chunk8<false>(src_gg, t.tid, s0, in.S, ggv);
         if (add_sdf) {
+            const int sb = s0 + 8 * cs;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int s = s0 + 8 * cs + j;
-                if (s < in.S) gov[j] += __ldg(g.g_sdf + s);
-            }
+            for (int j = 0; j < 8; ++j)
+                if (sb + j < in.S) gov[j] += __ldg(g.g_sdf + sb + j);
         }
     };
     if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x * NS);

@@ -73,6 +73,38 @@ class VolumeSDF(nn.Module):
         grad = grad_x01 / (2.0 * self.radius)          # d x01 / d points (scale_anything)
         return sdf.view(*shape), grad.view(*shape, 3), out.view(*shape, self.n_output_dims)
 
+    def _field(self, x01):
+        """network(encoding(x01)) for x01 [S,3] in the unit cube.  On the fused kernels the MLP reads the two
+        segments (x01 with the xyz affine, hash features) directly: no [S,35] concatenation, and under
+        no_grad (eval / relighting / occupancy update / the 7 finite-difference evaluations per sample of
+        the split-sum config) no autograd bookkeeping either."""
+        from . import sdf_field
+        from .network_utils import VanillaMLP
+        parts = self._fused_parts() if (x01.is_cuda and not x01.requires_grad and x01.shape[0] > 0) else None
+        if parts is not None:
+            inner, mask = parts
+            comp = self.encoding
+            if torch.is_grad_enabled():
+                if VanillaMLP.tc_training and VanillaMLP.fused_training:
+                    y = inner(x01)
+                    out, _ = sdf_field.fused_sdf(self.network, x01, comp.xyz_scale, comp.xyz_offset,
+                                                 y if mask is None else y * mask, want_g0=False)
+                    return self.network.output_activation(out)
+            elif VanillaMLP.fused_inference:
+                y = inner(x01)
+                if mask is not None:
+                    if self._mask_ones is None:            # one host sync; update_step refreshes the cache
+                        self._mask_ones = bool((mask == 1).all())
+                    if not self._mask_ones:
+                        y = y * mask
+                if self._packed_sdf is None:
+                    self._packed_sdf = sdf_field.PackedSDF(self.network)
+                return self.network.output_activation(self._packed_sdf(x01, comp.xyz_scale, comp.xyz_offset, y))
+        return self.network(self.encoding(x01))
+
+    _packed_sdf = None
+    _mask_ones = None           # cached "progressive level mask is all ones" (refreshed in update_step)
+
     def forward(self, points, with_grad=True, with_feature=True, with_laplace=False):
         analytic = with_grad and self.grad_type == "analytic"
         # (sample positions are data on the render path; a caller that differentiates w.r.t. the points
@@ -94,7 +126,7 @@ class VolumeSDF(nn.Module):
                 points.requires_grad_(True)
             points_ = points
             points = contract_to_unisphere(points, self.radius, self.contraction_type)
-            out = self.network(self.encoding(points.view(-1, 3))).view(*points.shape[:-1], self.n_output_dims).float()
+            out = self._field(points.view(-1, 3)).view(*points.shape[:-1], self.n_output_dims).float()
             sdf, feature = out[..., 0], out
             if with_grad:
                 if self.grad_type == "analytic":
@@ -106,8 +138,7 @@ class VolumeSDF(nn.Module):
                                                [0.0, -eps, 0.0], [0.0, 0.0, eps], [0.0, 0.0, -eps]]).to(points_)
                     points_d_ = (points_[..., None, :] + offsets).clamp(-self.radius, self.radius)
                     points_d = scale_anything(points_d_, (-self.radius, self.radius), (0, 1))
-                    points_d_sdf = self.network(self.encoding(points_d.view(-1, 3)))[..., 0] \
-                        .view(*points.shape[:-1], 6).float()
+                    points_d_sdf = self._field(points_d.view(-1, 3))[..., 0].view(*points.shape[:-1], 6).float()
                     grad = 0.5 * (points_d_sdf[..., 0::2] - points_d_sdf[..., 1::2]) / eps
                     if with_laplace:
                         # curvature probe (models/geometry.py:246-282)
@@ -139,6 +170,8 @@ class VolumeSDF(nn.Module):
     def update_step(self, epoch, global_step):
         update_module_step(self.encoding, epoch, global_step)
         update_module_step(self.network, epoch, global_step)
+        parts = self._fused_parts()
+        self._mask_ones = None if (parts is None or parts[1] is None) else bool((parts[1] == 1).all())
         if self.grad_type == "finite_difference":
             if isinstance(self.finite_difference_eps, float):
                 self._finite_difference_eps = self.finite_difference_eps
