@@ -648,6 +648,156 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
     if (t.warp == 0) tc::tmem_free(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// inference forward (out and/or sdf only): eval / relighting render, occupancy update, and the 7 evaluations per
+// sample behind the finite-difference normals of the split-sum config -- by far the most-called kernel of a relit
+// frame.  Without the gradient chain only ONE [128 x 64] activation image is live per tile, so two tiles fit next
+// to the 112 KB of weights, and the kernel runs as TWO INDEPENDENT HALF-CTAs: epilogue group g (8 warps, named
+// barrier 1 + g) works through its own stream of 64-sample tiles with its own images and TMEM columns, and MMA-
+// issuer warp 16 + g serves it (tcgen05.mma issue blocks the issuing warp while the tensor pipe's queue is full,
+// so issuing is that warp's only job).  Group g announces "operands of the next GEMM are in place" on mbarrier
+// ready[g]; the issuer issues it (full-size N = 64 instructions) and commits to done[g]; the group waits on
+// done[g].  Nothing else couples the groups: while one waits (MMA, TMEM load, barrier) the other's epilogue runs.
+constexpr int EV_GRP = 256, EV_THREADS = 2 * EV_GRP + 64;
+constexpr uint32_t EV_H0 = W_END, EV_A = EV_H0 + 2 * IMG_S_BYTES, EV_CTRL = EV_A + 2 * IMG_B_BYTES,
+                   EV_SMEM = EV_CTRL + 64;
+struct EvCtrl {
+    uint64_t bar_w, done[2], ready[2];
+    uint32_t tmem_slot, pad;
+};
+__device__ __forceinline__ void ev_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(EV_GRP) : "memory");
+}
+__device__ __forceinline__ void ev_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+#define EV_ISSUE(...)                                          \
+    {                                                          \
+        tc::mbar_wait(&ct->ready[g], rpar);                    \
+        rpar ^= 1u;                                            \
+        tc::tc_fence_after();                                  \
+        if (tc::elect_one()) {                                 \
+            __VA_ARGS__                                        \
+            tc::mma_commit(&ct->done[g]);                      \
+        }                                                      \
+        __syncwarp();                                          \
+    }
+#define EV_DONE() { tc::fence_async_smem(); tc::tc_fence_before(); ev_sync(g); if (tg == 0) ev_arrive(&ct->ready[g]); }
+#define EV_WAIT() { tc::mbar_wait(&ct->done[g], dpar); dpar ^= 1u; tc::tc_fence_after(); }
+
+__global__ void __launch_bounds__(EV_THREADS, 1)
+sdf_eval_kernel(const Net net, const Inputs in, float *__restrict__ out, float *__restrict__ sdf) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    EvCtrl *ct = reinterpret_cast<EvCtrl *>(smem + EV_CTRL);
+    Tid t = make_tid();
+    if (t.tid == 0) {
+        tc::mbar_init(&ct->bar_w, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&ct->done[i], 1); tc::mbar_init(&ct->ready[i], 1); }
+        tc::mbar_fence_init();
+    }
+    if (t.warp == 0) tc::tmem_alloc(&ct->tmem_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = ct->tmem_slot;
+    if (t.tid == 0) {
+        tc::mbar_expect_tx(&ct->bar_w, W_END);
+        tc::bulk_g2s(smem + W1_OFF, net.w1, 2 * W1_PLANE, &ct->bar_w);
+        tc::bulk_g2s(smem + W2_OFF, net.w2, 2 * W2_PLANE, &ct->bar_w);
+        tc::bulk_g2s(smem + W3_OFF, net.w3, 2 * W3_PLANE, &ct->bar_w);
+    }
+    tc::mbar_wait(&ct->bar_w, 0);
+    const int n_tiles = (in.S + NS - 1) / NS;
+    const uint32_t sW1 = tc::smem_u32(smem + W1_OFF), sW2 = tc::smem_u32(smem + W2_OFF), sW3 = tc::smem_u32(smem + W3_OFF);
+    const uint32_t id_kn = tc::instr_desc(128, NS, false, true);
+    if (t.warp >= 2 * EV_GRP / 32) {
+        // ---- MMA issuer warp of group g ----------------------------------------------------------
+        const int g = t.warp - 2 * EV_GRP / 32;
+        const uint32_t sH0 = tc::smem_u32(smem + EV_H0 + g * IMG_S_BYTES), sA = tc::smem_u32(smem + EV_A + g * IMG_B_BYTES);
+        const uint32_t tm = tmem + (uint32_t)(192 * g);
+        uint32_t rpar = 0u;
+        for (int tile = 2 * blockIdx.x + g; tile < n_tiles; tile += 2 * gridDim.x) {
+            EV_ISSUE(gemm3<KP / 16>(tm + 0, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);)
+            EV_ISSUE(gemm3<HID / 16>(tm + 64, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);)
+            EV_ISSUE(gemm3<HID / 16>(tm + 128, tc::op_kmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);)
+        }
+    } else {
+        // ---- epilogue group g: thread = feature row f x the 32 sample columns [32*cg, +32) -----------
+        const int g = t.warp >> 3, tg = t.tid & (EV_GRP - 1);
+        const int cg = (t.warp >> 2) & 1;
+        t.tl = tmem + ((uint32_t)(t.q * 32) << 16) + (uint32_t)(192 * g);
+        uint8_t *h0_img = smem + EV_H0 + g * IMG_S_BYTES, *a_img = smem + EV_A + g * IMG_B_BYTES;
+        const float b1f = net.b1[t.f], b2f = net.b2[t.f];
+        const float b3f = t.f < net.n_out ? net.b3[t.f] : 0.0f;
+        // staging: feature row fs = tg % 64 (< 48), chunks cs and cs + 4 of the tile
+        const int fs = tg & 63, cs = tg >> 6;
+        const RowSrc src_h = row_src(in.in0, in.w0, in.sc0, in.sh0, in.in1, in.w1, fs);
+        uint32_t dpar = 0u;
+        float hv[2][8];
+        int tile = 2 * blockIdx.x + g;
+        if (tile < n_tiles) {
+            load_chunk8(src_h, cs << 6, tile * NS, in.S, hv[0]);
+            load_chunk8(src_h, (cs + 4) << 6, tile * NS, in.S, hv[1]);
+        }
+        for (; tile < n_tiles; tile += 2 * gridDim.x) {
+            const int s0 = tile * NS;
+            if (fs < KP) {
+                tc::store_chunk(h0_img, IMG_S_PLANE, KP, fs, cs, hv[0]);
+                tc::store_chunk(h0_img, IMG_S_PLANE, KP, fs, cs + 4, hv[1]);
+            }
+            EV_DONE()
+            const int tn = tile + 2 * gridDim.x;          // prefetch this group's next tile
+            if (tn < n_tiles) {
+                load_chunk8(src_h, cs << 6, tn * NS, in.S, hv[0]);
+                load_chunk8(src_h, (cs + 4) << 6, tn * NS, in.S, hv[1]);
+            }
+            EV_WAIT()
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {              // a1 = softplus(Z1 + b1)
+                t.col0 = 32 * cg + 16 * cc;
+                float v[16];
+                ld16(t, 0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
+                st16(a_img, t, v);
+            }
+            EV_DONE()
+            EV_WAIT()
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {              // a2 = softplus(Z2 + b2)  (a1's GEMM has drained)
+                t.col0 = 32 * cg + 16 * cc;
+                float v[16];
+                ld16(t, 64, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b2f);
+                st16(a_img, t, v);
+            }
+            EV_DONE()
+            EV_WAIT()
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {              // out = W3 a2 + b3 (lanes >= n_out don't-care)
+                t.col0 = 32 * cg + 16 * cc;
+                if (out) store_rows(out, net.n_out, 1.0f, nullptr, 0, s0, in.S, t, 128, b3f, nullptr);
+                if (sdf && t.q == 0) {
+                    float v[16];
+                    ld16(t, 128, v);
+                    const int sb = s0 + t.col0;
+                    if (t.f == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (sb + j < in.S) sdf[sb + j] = v[j] + b3f;
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            ev_sync(g);                                   // this group's images / TMEM columns are reused next tile
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (t.warp == 0) tc::tmem_free(tmem, 512);
+}
+
 // max |x| over two arrays -> *out (float bits; non-negative floats order like unsigned ints)
 __global__ void absmax2_kernel(const float *__restrict__ a, size_t na, const float *__restrict__ b, size_t nb,
                                uint32_t *__restrict__ out) {
@@ -705,8 +855,8 @@ int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
                      const float *in1, int w1, int n_samples, float *out, float *sdf, float *g0a, float *g0b,
                      void *stream) {
     if (n_samples == 0) return 0;
-    if (!check_net(net) || !in0 || !out || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) || w0 + w1 != net->n_in ||
-        (g0a && w1 > 0 && !g0b))
+    if (!check_net(net) || !in0 || (!out && !sdf) || (g0a && !out) || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) ||
+        w0 + w1 != net->n_in || (g0a && w1 > 0 && !g0b))
         return RSDF_EBADARG;
     const Inputs in{in0, in1, w0, w1, scale0, shift0, n_samples};
     const int n_tiles = (n_samples + NS - 1) / NS;
@@ -717,9 +867,11 @@ int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
         if (e != cudaSuccess) return (int)e;
         sdf_fwd_kernel<true><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, g0a, g0b);
     } else {
-        e = cudaFuncSetAttribute(sdf_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
+        e = cudaFuncSetAttribute(sdf_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV_SMEM);
         if (e != cudaSuccess) return (int)e;
-        sdf_fwd_kernel<false><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, nullptr, nullptr);
+        const int pairs = (n_tiles + 1) / 2;
+        sdf_eval_kernel<<<pairs < RSDF_NUM_SMS ? pairs : RSDF_NUM_SMS, EV_THREADS, EV_SMEM, (cudaStream_t)stream>>>(
+            to_net(net), in, out, sdf);
     }
     RSDF_LAUNCH_CHECK();
     return 0;

@@ -73,8 +73,8 @@ class VolumeSDF(nn.Module):
         grad = grad_x01 / (2.0 * self.radius)          # d x01 / d points (scale_anything)
         return sdf.view(*shape), grad.view(*shape, 3), out.view(*shape, self.n_output_dims)
 
-    def _field(self, x01):
-        """network(encoding(x01)) for x01 [S,3] in the unit cube.  On the fused kernels the MLP reads the two
+    def _field(self, x01, sdf_only=False):
+        """network(encoding(x01)) for x01 [S,3] in the unit cube (sdf_only: just channel 0, [S]).  On the fused kernels the MLP reads the two
         segments (x01 with the xyz affine, hash features) directly: no [S,35] concatenation, and under
         no_grad (eval / relighting / occupancy update / the 7 finite-difference evaluations per sample of
         the split-sum config) no autograd bookkeeping either."""
@@ -89,7 +89,8 @@ class VolumeSDF(nn.Module):
                     y = inner(x01)
                     out, _ = sdf_field.fused_sdf(self.network, x01, comp.xyz_scale, comp.xyz_offset,
                                                  y if mask is None else y * mask, want_g0=False)
-                    return self.network.output_activation(out)
+                    out = self.network.output_activation(out)
+                    return out[..., 0] if sdf_only else out
             elif VanillaMLP.fused_inference:
                 y = inner(x01)
                 if mask is not None:
@@ -99,8 +100,13 @@ class VolumeSDF(nn.Module):
                         y = y * mask
                 if self._packed_sdf is None:
                     self._packed_sdf = sdf_field.PackedSDF(self.network)
-                return self.network.output_activation(self._packed_sdf(x01, comp.xyz_scale, comp.xyz_offset, y))
-        return self.network(self.encoding(x01))
+                identity = self.network.config_output_activation_is_identity
+                if sdf_only and identity:                 # only the sdf head is written: 4 B instead of 192 B per point
+                    return self._packed_sdf(x01, comp.xyz_scale, comp.xyz_offset, y, sdf_only=True)
+                out = self.network.output_activation(self._packed_sdf(x01, comp.xyz_scale, comp.xyz_offset, y))
+                return out[..., 0] if sdf_only else out
+        out = self.network(self.encoding(x01))
+        return out[..., 0] if sdf_only else out
 
     _packed_sdf = None
     _mask_ones = None           # cached "progressive level mask is all ones" (refreshed in update_step)
@@ -138,7 +144,7 @@ class VolumeSDF(nn.Module):
                                                [0.0, -eps, 0.0], [0.0, 0.0, eps], [0.0, 0.0, -eps]]).to(points_)
                     points_d_ = (points_[..., None, :] + offsets).clamp(-self.radius, self.radius)
                     points_d = scale_anything(points_d_, (-self.radius, self.radius), (0, 1))
-                    points_d_sdf = self._field(points_d.view(-1, 3))[..., 0].view(*points.shape[:-1], 6).float()
+                    points_d_sdf = self._field(points_d.view(-1, 3), sdf_only=True).view(*points.shape[:-1], 6).float()
                     grad = 0.5 * (points_d_sdf[..., 0::2] - points_d_sdf[..., 1::2]) / eps
                     if with_laplace:
                         # curvature probe (models/geometry.py:246-282)

@@ -153,6 +153,8 @@ class VanillaMLP(nn.Module):
         layers += [self.make_linear(self.n_neurons, dim_out, False, True)]
         self.layers = nn.Sequential(*layers)
         self.output_activation = get_activation(config.get("output_activation", None))
+        oa = config.get("output_activation", None)
+        self.config_output_activation_is_identity = oa is None or str(oa).lower() == "none"
 
     @property
     def activation_name(self):

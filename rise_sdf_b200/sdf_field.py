@@ -140,15 +140,16 @@ class PackedSDF:
         return self._net
 
     @torch.no_grad()
-    def __call__(self, in0, scale0=1.0, shift0=0.0, in1=None):
-        """out [S, dim_out] for h0 = cat(in0 * scale0 + shift0, in1)."""
+    def __call__(self, in0, scale0=1.0, shift0=0.0, in1=None, sdf_only=False):
+        """out [S, dim_out] (or just sdf [S] = out[:, 0] with sdf_only) for h0 = cat(in0 * scale0 + shift0, in1)."""
         L.require_cuda(in0, in1)
         in0 = in0.contiguous().float()
         in1 = None if in1 is None else in1.contiguous().float()
         S = in0.shape[0]
-        out = torch.empty(S, self.mlp.dim_out, device=in0.device, dtype=torch.float32)
+        out = None if sdf_only else torch.empty(S, self.mlp.dim_out, device=in0.device, dtype=torch.float32)
+        sdf = torch.empty(S, device=in0.device, dtype=torch.float32) if sdf_only else None
         if S:
             L.call("rsdf_sdf_mlp_fwd", ctypes.byref(self._struct()), L.ptr(in0), in0.shape[1], float(scale0),
-                   float(shift0), L.ptr(in1), 0 if in1 is None else in1.shape[1], S, L.ptr(out), None, None, None,
+                   float(shift0), L.ptr(in1), 0 if in1 is None else in1.shape[1], S, L.ptr(out), L.ptr(sdf), None, None,
                    L.stream())
-        return out
+        return sdf if sdf_only else out
