@@ -178,7 +178,7 @@ def run_relight(args, dev, world, rank, n_frames=2):
     import torch
     import torch.distributed as dist
     from rise_sdf_b200 import synthetic as syn
-    from rise_sdf_b200.relight import EnvSet, render_frame_shard, synthetic_envs
+    from rise_sdf_b200.relight import EnvSet, balanced_tile, render_frame_shard, synthetic_envs
     from rise_sdf_b200.split_mixed_occ import SplitMixedOCCModel, split_mixed_occ_config
 
     torch.manual_seed(42)
@@ -216,7 +216,8 @@ def run_relight(args, dev, world, rank, n_frames=2):
     return {"metric": "relit_800x800_frames_per_s", "value": n_relit / (ms / 1e3), "unit": "frames/s",
             "ms_per_frame": ms / n_relit, "frames": n_relit, "env_maps": len(envs.maps), "n_gpus": world,
             "scaling": "strong", "occupied_fraction": round(float(model.occupancy_grid.binaries.float().mean()), 4),
-            "sharding": "32768-ray tiles round-robin over ranks, no collective",
+            "sharding": f"{balanced_tile(640000, world)}-ray tiles round-robin over ranks (equal tile count per rank), "
+                        "no collective",
             "mean_rgb": float(out[0]["comp_rgb_phys_full"].mean()) if out[0]["comp_rgb_phys_full"].numel() else None}
 
 

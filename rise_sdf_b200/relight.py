@@ -32,10 +32,22 @@ def my_tiles(n_rays, tile, rank, world):
     return [(s, min(s + tile, n_rays)) for k, s in enumerate(range(0, n_rays, tile)) if k % world == rank]
 
 
+def balanced_tile(n_rays, world, max_tile=32768, per_rank=4):
+    """Tile size such that every rank gets the same NUMBER of tiles (>= per_rank of them when the frame is
+    large enough): 640 000 rays -> 32 000 for 1/2/4 ranks (20 tiles), 20 032 for 8 ranks (32 tiles, 4 each)."""
+    t = min(max_tile, -(-n_rays // (world * per_rank)))
+    t = -(-t // 64) * 64
+    n = -(-n_rays // t)
+    n = -(-n // world) * world                # round the tile count up to a multiple of the ranks
+    return -(-(-(-n_rays // n)) // 64) * 64
+
+
 @torch.no_grad()
-def render_frame_shard(model, rays, envs, rank=0, world=1, tile=32768, keys=("comp_rgb_phys_full",)):
+def render_frame_shard(model, rays, envs, rank=0, world=1, tile=None, keys=("comp_rgb_phys_full",)):
     """Render this rank's tiles of one frame under every env map.  rays: [H*W, 6] on the device.
     Returns {env_index: {key: [n_my_rays, C]}} plus the tile list."""
+    if tile is None:
+        tile = balanced_tile(rays.shape[0], world)
     tiles = my_tiles(rays.shape[0], tile, rank, world)
     out = {}
     for e in range(len(envs.maps)):

@@ -15,7 +15,7 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from rise_sdf_b200.relight import my_tiles
+    from rise_sdf_b200.relight import balanced_tile, my_tiles
     from rise_sdf_b200.train import FlatGradBucket
     torch.manual_seed(0)                                   # identical "weights" on every rank
     params = [torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.tensor(0.3))]
@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
     assert params[0].grad.data_ptr() == bucket.flat.data_ptr()      # grads really live in the flat buffer
     local = bucket.flat.clone()
     bucket.all_reduce_mean()
-    tiles = my_tiles(640000, 32768, rank, world)
+    tiles = my_tiles(640000, balanced_tile(640000, world), rank, world)
     q.put((rank, local, bucket.flat.clone(), tiles))
     dist.destroy_process_group()
 
@@ -48,4 +48,12 @@ def test_flat_bucket_allreduce_and_tile_sharding():
     covered = sorted(res[0][3] + res[1][3])
     assert covered[0][0] == 0 and covered[-1][1] == 640000
     assert all(a[1] == b[0] for a, b in zip(covered[:-1], covered[1:]))       # disjoint, complete cover
-    assert abs(len(res[0][3]) - len(res[1][3])) <= 1                          # balanced round-robin
+    assert len(res[0][3]) == len(res[1][3])                                   # same tile count on every rank
+
+
+def test_balanced_tile_counts():
+    from rise_sdf_b200.relight import balanced_tile, my_tiles
+    for world in (1, 2, 3, 4, 8):
+        t = balanced_tile(640000, world)
+        counts = [len(my_tiles(640000, t, r, world)) for r in range(world)]
+        assert t % 64 == 0 and t <= 32768 and len(set(counts)) == 1 and sum(counts) * t >= 640000
