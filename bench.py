@@ -221,6 +221,54 @@ def run_relight(args, dev, world, rank, n_frames=2):
             "mean_rgb": float(out[0]["comp_rgb_phys_full"].mean()) if out[0]["comp_rgb_phys_full"].numel() else None}
 
 
+def run_split_train(args, dev, world, rank, n_rays=4096):
+    """BASELINE configs[2]: split-mixed-occ training step -- split-sum PBR shading at stage 1, env-light mip
+    pyramid rebuilt every step, finite-difference normals + curvature probe, reflection bounce, all losses of
+    systems/split_occ.py, backward, (all-reduce), Adam.  4096 rays/GPU/step.  Returns a dict for the JSON line."""
+    import torch
+    import torch.distributed as dist
+    from rise_sdf_b200 import synthetic as syn
+    from rise_sdf_b200.split_mixed_occ import SplitMixedOCCModel, split_mixed_occ_config
+    from rise_sdf_b200.train import SplitTrainer
+
+    torch.manual_seed(42)
+    model = SplitMixedOCCModel(split_mixed_occ_config()).to(dev)
+    with torch.no_grad():
+        model.geometry.network.layers[0].weight_v[:, 3:].normal_(0.0, 0.05)
+    model.train()
+    model.update_step(0, 20000)                      # all hash levels on, stage 1 (split-sum shading active)
+    gj = torch.Generator().manual_seed(7)
+    model.occupancy_grid._update(0, model.occ_eval_fn, occ_thre=0.001, jitter=torch.rand(128 ** 3, 3, generator=gj))
+    trainer = SplitTrainer(model)
+    poses, dirs = syn.camera_poses(), syn.ray_directions()
+    batches = [tuple(t.to(dev) for t in syn.training_rays(n_rays, seed=7 + 1000 * b, rank=rank, poses=poses, directions=dirs))
+               for b in range(2)]
+    torch.cuda.manual_seed(4321 + rank)
+    for i in range(max(args.warmup, 3)):
+        trainer.step(*batches[i % 2])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = max(3, args.steps // 2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        _, out = trainer.step(*batches[i % 2])
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    return {"metric": "split_train_rays_per_s", "value": world * n_rays / (ms / 1e3), "unit": "rays/s",
+            "ms_per_step": ms, "steps": steps, "rays_per_gpu": n_rays, "n_gpus": world, "scaling": "weak",
+            "primary_samples_per_step": int(out["num_samples"].sum()),
+            "workload": "split-mixed-occ-tensoir training step (configs[2]): stage 1 split-sum shading, "
+                        "build_mips per step, FD normals + curvature, reflection bounce, fwd+loss+bwd+Adam"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -317,9 +365,11 @@ def run_ours(args):
     ms_e2e = t0.elapsed_time(t1)
 
     # ---- second headline: relit frames/s (all ranks take part; no collective on the data path)
-    relight = None
+    relight = split_train = None
     if not args.no_relight:
         del trainer, devb
+        torch.cuda.empty_cache()
+        split_train = run_split_train(args, dev, world, rank)
         torch.cuda.empty_cache()
         relight = run_relight(args, dev, world, rank)
 
@@ -377,6 +427,8 @@ def run_ours(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if split_train:
+        line["split_train"] = split_train
     if relight:
         line["relight"] = relight
     print(json.dumps(line), flush=True)
@@ -391,7 +443,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-relight", action="store_true", help="skip the relit-frames/s section")
+    ap.add_argument("--no-relight", action="store_true",
+                    help="skip the split-train rays/s and relit-frames/s sections (configs[2], configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -393,6 +393,9 @@ struct Grads {
     float *gW1, *gb1, *gW2, *gb2, *gW3, *gb3;   // atomically accumulated; caller zeroes
 };
 
+// CHAIN = false: no cotangent reaches g0 (plain first-order backward, e.g. the finite-difference evaluations
+// of the split-sum config): the gradient-chain GEMMs and three of the seven epilogue passes drop out.
+template <bool CHAIN>
 __global__ void __launch_bounds__(THREADS, 1)
 sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -524,16 +527,20 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
                 u[j] = sg * w30f;
             }
             st16(big_a, t, v);                            // a2 * 2^(K-k_s)  (weight-gradient operand only)
-            st16(big_b, t, u);                            // u2
+            if (CHAIN) st16(big_b, t, u);                 // u2
         }
-        // P3: gW3^T += a2 g_out^T ; v1 = W2^T u2 ; ub1 = W1 g_g0
+        // P3: gW3^T += a2 g_out^T ; v1 = W2^T u2 ; ub1 = W1 g_g0   (no chain: ab2 = W3^T g_out right away)
         PHASE_BEGIN()
             gemm3<KS>(tmem + AW3, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGO, IMG_S_PLANE, KP), id_g48, acc);
-            gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
-            gemm3<KP / 16>(tmem + T1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sGG, IMG_S_PLANE, KP), id_kn, false);
+            if (CHAIN) {
+                gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
+                gemm3<KP / 16>(tmem + T1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sGG, IMG_S_PLANE, KP), id_kn, false);
+            } else {
+                gemm3<KP / 16>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
+            }
         PHASE_END()
         float zp[16], vb[16];                             // z1-bar (chain part) and v1-bar, kept in registers
-        {
+        if (CHAIN) {
             float v[16], ub[16], z[16];
             ld16(t, T0, v);
             ld16(t, T1, ub);
@@ -552,20 +559,27 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
             for (int j = 0; j < 16; ++j) z[j] = sp_sig(z[j] + b2f) * w30f * wsc[j];
             st16(big_b, t, z);                            // u2 * 2^(K-k_s)  (v1's MMA has drained)
         }
-        // P4: gW1 += u1 g_g0^T
-        PHASE_BEGIN()
-            gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGG, IMG_S_PLANE, KP), id_g48, acc);
-        PHASE_END()
-        st16(big_a, t, vb);                               // v1-bar
-        // P5: gW2 += u2 vb1^T ; ub2 = W2 vb1 ; ab2 = W3^T g_out
-        PHASE_BEGIN()
-            gemm3<KS>(tmem + AW2, tc::op_kmajor(sB, IMG_B_PLANE, HID), tc::op_kmajor(sA, IMG_B_PLANE, HID), id_g128, acc);
-            gemm3<HID / 16>(tmem + T0, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
-            gemm3<KP / 16>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
-        PHASE_END()
+        if (CHAIN) {
+            // P4: gW1 += u1 g_g0^T
+            PHASE_BEGIN()
+                gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGG, IMG_S_PLANE, KP), id_g48, acc);
+            PHASE_END()
+            st16(big_a, t, vb);                           // v1-bar
+            // P5: gW2 += u2 vb1^T ; ub2 = W2 vb1 ; ab2 = W3^T g_out
+            PHASE_BEGIN()
+                gemm3<KS>(tmem + AW2, tc::op_kmajor(sB, IMG_B_PLANE, HID), tc::op_kmajor(sA, IMG_B_PLANE, HID), id_g128, acc);
+                gemm3<HID / 16>(tmem + T0, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+                gemm3<KP / 16>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
+            PHASE_END()
+        }
         {
             float ub[16], ab[16], z[16];
-            ld16(t, T0, ub);
+            if (CHAIN) {
+                ld16(t, T0, ub);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ub[j] = 0.0f;
+            }
             ld16(t, T1, ab);
             ld16(t, Z2, z);
 #pragma unroll
@@ -585,7 +599,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
         }
         // P6: gW2 += zb2 a1^T ; ab1 = W2^T zb2
         PHASE_BEGIN()
-            gemm3<KS>(tmem + AW2, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sB, IMG_B_PLANE, HID), id_g128, true);
+            gemm3<KS>(tmem + AW2, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sB, IMG_B_PLANE, HID), id_g128, CHAIN || acc);
             gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
         PHASE_END()
         {
@@ -594,7 +608,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
             ld16(t, Z1, z);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float zb = fmaf(ab[j], sp_sig(z[j] + b1f), zp[j]);
+                const float zb = fmaf(ab[j], sp_sig(z[j] + b1f), CHAIN ? zp[j] : 0.0f);
                 b1acc = fmaf(zb, inv[j], b1acc);
                 z[j] = zb;
             }
@@ -602,7 +616,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
         }
         // P7: gW1 += zb1 h0^T ; d/d h0 = W1^T zb1
         PHASE_BEGIN()
-            gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sH0W, IMG_S_PLANE, KP), id_g48, true);
+            gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sH0W, IMG_S_PLANE, KP), id_g48, CHAIN || acc);
             gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
         PHASE_END()
         if (g.g_in0 || g.g_in1) store_rows(g.g_in0, in.w0, in.sc0, g.g_in1, in.w1, s0, in.S, t, T0, 0.0f, sinv);
@@ -889,9 +903,16 @@ int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
     const Grads g{g_out, g_sdf, g_g0a, g_g0b, amax_bits, g_in0, g_in1, gW1, gb1, gW2, gb2, gW3, gb3};
     const int n_tiles = (n_samples + NS - 1) / NS;
     const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
-    cudaError_t e = cudaFuncSetAttribute(sdf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    sdf_bwd_kernel<<<grid, THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);
+    cudaError_t e;
+    if (g_g0a || g_g0b) {
+        e = cudaFuncSetAttribute(sdf_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        sdf_bwd_kernel<true><<<grid, THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);
+    } else {
+        e = cudaFuncSetAttribute(sdf_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        sdf_bwd_kernel<false><<<grid, THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);
+    }
     RSDF_LAUNCH_CHECK();
     return 0;
 }

@@ -27,6 +27,49 @@ def neus_loss(out, rgb, fg_mask, lambda_rgb_mse=10.0, lambda_mask=0.1, lambda_ei
     return loss, {"rgb_mse": loss_rgb, "eikonal": loss_eik, "mask": loss_mask, "sparsity": loss_sparse}
 
 
+SPLIT_LAMBDAS = dict(lambda_rgb_mse=10.0, lambda_rgb_l1=0.0, lambda_rgb_phys_mse=10.0, lambda_rgb_phys_l1=0.0,
+                     lambda_mask=0.1, lambda_eikonal=0.05, lambda_sparsity=0.01, lambda_curvature=1.0,
+                     lambda_opaque=0.0, lambda_normal_orientation=0.05, lambda_emitter_distillation=0.0,
+                     sparsity_scale=1.0)      # configs/split-mixed-occ-tensoir.yaml:139-152
+
+
+def split_loss(model, out, rgb, fg_mask, has_mask=True, **overrides):
+    """Loss block of systems/split_occ.py:163-225 (distortion terms excluded: their lambdas are 0 in the
+    config and the helper library is not part of the path)."""
+    lam = dict(SPLIT_LAMBDAS, **overrides)
+    valid = out["rays_valid_full"][..., 0]
+    parts = {}
+    parts["rgb_mse"] = F.mse_loss(out["comp_rgb_full"][valid], rgb[valid])
+    loss = parts["rgb_mse"] * lam["lambda_rgb_mse"]
+    if lam["lambda_rgb_l1"]:
+        loss = loss + F.l1_loss(out["comp_rgb_full"][valid], rgb[valid]) * lam["lambda_rgb_l1"]
+    if model.stage != 0:
+        parts["rgb_phys_mse"] = F.mse_loss(out["comp_rgb_phys_full"][valid], rgb[valid])
+        loss = loss + parts["rgb_phys_mse"] * lam["lambda_rgb_phys_mse"]
+        if lam["lambda_rgb_phys_l1"]:
+            loss = loss + F.l1_loss(out["comp_rgb_phys_full"][valid], rgb[valid]) * lam["lambda_rgb_phys_l1"]
+    parts["eikonal"] = ((torch.linalg.norm(out["sdf_grad_samples"], ord=2, dim=-1) - 1.0) ** 2).mean()
+    loss = loss + parts["eikonal"] * lam["lambda_eikonal"]
+    opacity = torch.clamp(out["opacity"].squeeze(-1), 1e-3, 1 - 1e-3)
+    parts["mask"] = binary_cross_entropy(opacity, fg_mask.float())
+    loss = loss + parts["mask"] * (lam["lambda_mask"] if has_mask else 0.0)
+    if lam["lambda_opaque"]:
+        loss = loss + binary_cross_entropy(opacity, opacity) * lam["lambda_opaque"]
+    parts["sparsity"] = torch.exp(-lam["sparsity_scale"] * out["sdf_samples"].abs()).mean()
+    loss = loss + parts["sparsity"] * lam["lambda_sparsity"]
+    if lam["lambda_curvature"] > 0:
+        assert "sdf_laplace_samples" in out, "Need geometry.grad_type='finite_difference' to get SDF Laplace samples"
+        parts["curvature"] = out["sdf_laplace_samples"].abs().mean()
+        loss = loss + parts["curvature"] * lam["lambda_curvature"]
+    if lam["lambda_emitter_distillation"] > 0 and model.stage != 0:
+        loss = loss + F.mse_loss(out["comp_spec_rgb_full"][valid], out["comp_spec_rgb_phys_full"][valid]) \
+            * lam["lambda_emitter_distillation"]
+    for name, value in model.geometry.regularizations(out).items():      # normal_orientation
+        parts[name] = value
+        loss = loss + value * lam[f"lambda_{name}"]
+    return loss, parts
+
+
 class FlatGradBucket:
     """All parameters' gradients as views into one contiguous fp32 buffer, so the data-parallel
     exchange is a single NCCL all-reduce instead of DDP's 25 MB buckets."""
@@ -67,6 +110,38 @@ class NeusTrainer:
         self.bucket.zero()
         out = m(rays)
         loss, parts = neus_loss(out, rgb, fg_mask)
+        loss.backward()
+        self.bucket.all_reduce_mean()
+        if optimize:
+            self.opt.step()
+        self.global_step += 1
+        return loss, out
+
+
+class SplitTrainer:
+    """One split-mixed-occ training step (systems/split_occ.py:150-237): rebuild the env-light mip pyramid
+    (`emitter.build_mips()`, the `base` cube map is learnable), render, loss, backward, gradient exchange,
+    Adam with the per-group learning rates of configs/split-mixed-occ-tensoir.yaml:153-166."""
+
+    def __init__(self, model, lr=0.005, lr_variance=0.001, lr_emitter=0.01):
+        self.model = model
+        groups = [
+            {"params": list(model.geometry.parameters()), "lr": lr},
+            {"params": [p for p in model.texture.parameters() if p.numel() > 0], "lr": lr},
+            {"params": list(model.variance.parameters()), "lr": lr_variance},
+            {"params": list(model.emitter.parameters()), "lr": lr_emitter},
+        ]
+        self.bucket = FlatGradBucket([p for g in groups for p in g["params"]])
+        self.opt = torch.optim.Adam(groups, lr=lr, betas=(0.9, 0.999), eps=1e-12)
+        self.global_step = 0
+
+    def step(self, rays, rgb, fg_mask, background, optimize=True):
+        m = self.model
+        m.background_color = background
+        self.bucket.zero()
+        m.emitter.build_mips()
+        out = m(rays)
+        loss, parts = split_loss(m, out, rgb, fg_mask)
         loss.backward()
         self.bucket.all_reduce_mean()
         if optimize:
