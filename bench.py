@@ -54,8 +54,14 @@ KERNEL_WORK = {
     "rsdf_neus_render_fwd": ("hbm", 64, "neus_render_fwd_kernel"),
     "rsdf_neus_render_bwd": ("hbm", 64 + 32, "neus_render_bwd_kernel"),
 }
-# DRAM bytes per launch from the committed `ncu --set full` captures (profiles/), per sample
-NCU_TRAFFIC_PER_SAMPLE = {}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/kernels_r01_full.txt, 3 339 366 samples), expressed per sample; per-launch averages for the
+# multi-launch entry points
+NCU_TRAFFIC_PER_SAMPLE = {
+    "rsdf_hashgrid_fwd": 694, "rsdf_hashgrid_bwd_input": 529, "rsdf_hashgrid_jvp": 520, "rsdf_hashgrid_bwd_table2": 324,
+    "rsdf_sdf_mlp_fwd": 466, "rsdf_sdf_mlp_bwd": 602,
+    "rsdf_relu_layer_fwd": (1085 + 3 * 1012 + 525) / 5.0, "rsdf_relu_layer_bwd": (1025 + 3 * 1530 + 1095) / 5.0,
+}
 
 
 def peaks():

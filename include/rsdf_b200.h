@@ -251,7 +251,8 @@ int rsdf_absmax2(const float *a, long long na, const float *b, long long nb, uin
  *             for the head, row-major g_rows[S, r_real] (scaled in-kernel);  a_in = the layer's input
  *             activation stream saved by the forward.  Produces gW[r_real, k_real] (atomic +=), and either
  *             zb_out = (W^T zb) . [a_in > 0] for the layer below (+ its bias gradient gb_prev) or, for the
- *             first layer, rows_out[S, k_real] = W^T zb (unscaled).  gb_self: head bias gradient. */
+ *             first layer (first_layer = 1), rows_out[g][S, seg_w[g]] = (W^T zb)[:, segment g] * seg_scale[g],
+ *             unscaled by 2^K, one array per input segment.  gb_self: head bias gradient. */
 typedef struct rsdf_relu_layer_fwd_args {
     const void *w;
     const float *bias;
@@ -273,7 +274,10 @@ typedef struct rsdf_relu_layer_bwd_args {
     const uint32_t *amax;
     const void *a_in;
     void *zb_out;
-    float *rows_out;
+    float *rows_out[3];      /* first layer: one gradient array per input segment (NULL = not needed) */
+    int32_t seg_w[3];
+    float seg_scale[3];      /* chain rule through the input affine of the forward */
+    int32_t first_layer;
     float *gW;
     float *gb_prev;
     float *gb_self;

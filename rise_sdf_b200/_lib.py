@@ -38,7 +38,8 @@ class ReluFwdC(ctypes.Structure):
 class ReluBwdC(ctypes.Structure):
     _fields_ = [("w", c_p), ("r_pad", ctypes.c_int32), ("r_real", ctypes.c_int32), ("k_pad", ctypes.c_int32),
                 ("k_real", ctypes.c_int32), ("n_samples", ctypes.c_int32), ("zb_in", c_p), ("g_rows", c_p),
-                ("amax", c_p), ("a_in", c_p), ("zb_out", c_p), ("rows_out", c_p), ("gW", c_p), ("gb_prev", c_p),
+                ("amax", c_p), ("a_in", c_p), ("zb_out", c_p), ("rows_out", c_p * 3), ("seg_w", ctypes.c_int32 * 3),
+                ("seg_scale", ctypes.c_float * 3), ("first_layer", ctypes.c_int32), ("gW", c_p), ("gb_prev", c_p),
                 ("gb_self", c_p)]
 
 

@@ -231,7 +231,10 @@ struct BwdArgs {
     const uint32_t *amax;            // float bits of the launch-wide cotangent maximum
     const uint8_t *a_in;             // stream of this layer's INPUT activation images [k_pad x 64]
     uint8_t *zb_out;                 // stream of [128 x 64] images: (W^T zb) . [a > 0]          -- or --
-    float *rows_out;                 // [S, k_real] = W^T zb, unscaled (first layer)
+    float *rows_out[3];              // first layer: d/d input segment g = (W^T zb)[:, seg g] * seg_scale[g], [S, seg_w[g]]
+    int seg_w[3];                    //   (NULL entries are skipped; the segments partition the k_real input columns)
+    float seg_scale[3];
+    int first_layer;                 // 1: rows_out mode (no zb_out)
     float *gW;                       // [r_real, k_real], atomically accumulated
     float *gb_prev;                  // [k_real] bias gradient of the previous layer (with zb_out)
     float *gb_self;                  // [r_real] bias gradient of this layer (with g_rows)
@@ -294,6 +297,22 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
         }
     };
     if (rows_in && (int)blockIdx.x < n_tiles) load_g(blockIdx.x * NS);
+    // first layer: this thread's feature row belongs to one input segment -> fixed destination array
+    float *seg_dst = nullptr;
+    int seg_wd = 0;
+    float seg_sc = 1.0f;
+    if (p.first_layer && t.f < p.k_real) {
+        int f0 = 0;
+#pragma unroll
+        for (int sgm = 0; sgm < 3; ++sgm) {
+            if (t.f >= f0 && t.f < f0 + p.seg_w[sgm] && p.rows_out[sgm]) {
+                seg_dst = p.rows_out[sgm] + (t.f - f0);
+                seg_wd = p.seg_w[sgm];
+                seg_sc = p.seg_scale[sgm];
+            }
+            f0 += p.seg_w[sgm];
+        }
+    }
     uint32_t mma_phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -330,15 +349,16 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
             float v[16];
             ld16(t, T0, v);
             const int sb = s0 + t.col0;
-            if (t.f < p.k_real && sb < p.S) {
-                float *o = p.rows_out + (size_t)sb * p.k_real + t.f;
+            if (seg_dst && sb < p.S) {
+                float *o = seg_dst + (size_t)sb * seg_wd;
+                const float sc = ginv * seg_sc;
                 if (sb + 16 <= p.S) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j * p.k_real] = v[j] * ginv;
+                    for (int j = 0; j < 16; ++j) o[j * seg_wd] = v[j] * sc;
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (sb + j < p.S) o[j * p.k_real] = v[j] * ginv;
+                        if (sb + j < p.S) o[j * seg_wd] = v[j] * sc;
                 }
             }
         }
@@ -418,7 +438,8 @@ int rsdf_relu_layer_bwd(const rsdf_relu_layer_bwd_args *a, void *stream) {
     if (p.S == 0) return 0;
     if (!p.w || !p.amax || !p.a_in || !p.gW || p.r_pad % 16 || p.k_pad % 16 || p.r_pad < 16 || p.r_pad > 128 ||
         p.k_pad < 16 || p.k_pad > 128 || p.r_real < 1 || p.r_real > p.r_pad || p.k_real < 1 || p.k_real > p.k_pad ||
-        (!p.zb_in && !p.g_rows) || (!p.zb_out && !p.rows_out) || (p.zb_out && p.k_pad != 128) ||
+        (!p.zb_in && !p.g_rows) || (!p.zb_out && !p.first_layer) || (p.zb_out && p.first_layer) ||
+        (p.first_layer && p.seg_w[0] + p.seg_w[1] + p.seg_w[2] != p.k_real) || (p.zb_out && p.k_pad != 128) ||
         (p.g_rows && p.r_pad != 16))
         return RSDF_EBADARG;
     cudaError_t e = cudaFuncSetAttribute(relu_layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM);

@@ -81,8 +81,8 @@ class _ReluMLP(torch.autograd.Function):
         n_out = Ws[-1].shape[0]
         gWs = [torch.zeros_like(W) for W in Ws]
         gbs = [torch.zeros_like(b) for b in bs]
-        need_in = any(ctx.needs_input_grad[3:3 + ctx.n_seg])
-        g_in = torch.zeros(S, ctx.n_in, device=dev, dtype=torch.float32)
+        g_segs = [torch.empty(S, w, device=dev, dtype=torch.float32) if ctx.needs_input_grad[3 + g] else None
+                  for g, w in enumerate(ctx.seg_w)]
         if S:
             g_out = g_out.contiguous().float()
             n_tiles = (S + NS - 1) // NS
@@ -101,7 +101,10 @@ class _ReluMLP(torch.autograd.Function):
                 else:
                     p.zb_in = zb.data_ptr()
                 if first:
-                    p.rows_out = g_in.data_ptr()
+                    p.first_layer = 1
+                    for g, w in enumerate(ctx.seg_w):
+                        p.seg_w[g], p.seg_scale[g] = w, ctx.scales[g]
+                        p.rows_out[g] = None if g_segs[g] is None else g_segs[g].data_ptr()
                 else:
                     zb_next = _stream(n_tiles, HID, dev)
                     p.zb_out, p.gb_prev = zb_next.data_ptr(), gbs[i - 1].data_ptr()
@@ -110,15 +113,6 @@ class _ReluMLP(torch.autograd.Function):
                 if not first:
                     zb = zb_next
         ctx.acts = None
-        g_segs, off = [], 0
-        for g in range(ctx.n_seg):
-            w = ctx.seg_w[g]
-            if not ctx.needs_input_grad[3 + g]:
-                g_segs.append(None)
-            else:
-                gs = g_in[:, off:off + w]
-                g_segs.append(gs if ctx.scales[g] == 1.0 else gs * ctx.scales[g])
-            off += w
         g_params = []
         for gW, gb in zip(gWs, gbs):
             g_params += [gW, gb]
