@@ -128,6 +128,14 @@ int rsdf_hashgrid_bwd_bwd(const float *x, const float *table, const float *v, co
                           const rsdf_hashgrid_meta *meta, int n_samples, float *grad_table,
                           float *grad_dL_dy, float *grad_x, void *stream);
 
+/* Encodings of the six finite-difference neighbours p +- eps e_d (k = +x,-x,+y,-y,+z,-z) of every sample, for
+ * VolumeSDF's `grad_type: finite_difference` branch (models/geometry.py:229-244): neighbours are formed exactly
+ * like the reference (fp32 add, clamp to +-radius, (p + r) * fl32(1/2r)); x01_out[6S,3] and y[6S,n_out] are
+ * row = 6 s + k, the order of `points_d.view(-1, 3)`.  Bit-identical to rsdf_hashgrid_fwd on x01_out, but
+ * corners are re-gathered only when a neighbour leaves the previous neighbour's cell. */
+int rsdf_hashgrid_fd6(const float *points, const float *table, const rsdf_hashgrid_meta *meta, int n_samples,
+                      float eps, float radius, float *x01_out, float *y, void *stream);
+
 /* First- and second-order table gradients of the SAME samples in one scatter pass:
  * grad_table += (d y/d table)^T dL_dy + d/d table <v, dy_dx^T g2>  (== rsdf_hashgrid_bwd_table followed by
  * rsdf_hashgrid_bwd_bwd with grad_table only; one atomic per corner instead of two). */

@@ -62,6 +62,7 @@ _SIGS = {
     "rsdf_hashgrid_bwd_table": [c_p, c_p, c_p, c_i, c_p, c_p],
     "rsdf_hashgrid_bwd_input": [c_p, c_p, c_i, c_i, c_p, c_p],
     "rsdf_hashgrid_bwd_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
+    "rsdf_hashgrid_fd6": [c_p, c_p, c_p, c_i, c_f, c_f, c_p, c_p, c_p],
     "rsdf_hashgrid_bwd_table2": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
     "rsdf_hashgrid_jvp": [c_p, c_p, c_i, c_i, c_p, c_p],
     "rsdf_sh_fwd": [c_p, c_i, c_i, c_p, c_p],

@@ -170,6 +170,91 @@ hashgrid_fwd_kernel(const float *__restrict__ x, const float *__restrict__ table
     }
 }
 
+// Encoding of the SIX finite-difference neighbours p +- eps e_d of every sample in one pass (the
+// `grad_type: finite_difference` branch of VolumeSDF, models/geometry.py:229-244, evaluated for every sample of
+// every primary, reflection and third-bounce ray of a relit frame).  Same CTA shape as the forward (warp =
+// level, lane = sample).  The neighbours are built exactly as the reference builds them -- fp32 add of the
+// offset, clamp to +-radius, (p + r) * fl32(1 / 2r) (torch's tensor / scalar on CUDA) -- so the cell lookup is
+// bit-identical to six separate forward passes; but eps is a fraction of a cell on all but the finest levels, so
+// consecutive neighbours usually fall into the cell whose 8 corners are already in registers and are only
+// re-interpolated, not re-gathered.  Rows are written neighbour-major per sample (row = 6 s + k, k = +x,-x,+y,
+// -y,+z,-z), the order of `points_d.view(-1, 3)`.
+constexpr int FD_S = 32;
+constexpr int FD_THREADS = 512;
+
+__global__ void __launch_bounds__(FD_THREADS, 2)
+hashgrid_fd6_kernel(const float *__restrict__ points, const float *__restrict__ table, const Meta m, int n_samples,
+                    float eps, float radius, float inv_2r, float *__restrict__ x01_out, float *__restrict__ y) {
+    extern __shared__ __align__(16) float smem[];
+    const int n_out = m.n_levels * NFEAT;
+    const int ys = n_out + 2;
+    float *sy = smem;                                   // [FD_S * 6][ys]
+    const int warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int s0 = blockIdx.x * FD_S;
+    const int s = s0 + t;
+    const bool ok = s < n_samples;
+    const uint64_t pol = l2_keep_policy();
+    float p[3] = {0.f, 0.f, 0.f};
+    if (ok) { p[0] = __ldg(points + 3 * s); p[1] = __ldg(points + 3 * s + 1); p[2] = __ldg(points + 3 * s + 2); }
+    // the six neighbours in unit-cube coordinates
+    float x[6][3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float q = p[d];
+            if (d == (k >> 1)) q = __fadd_rn(q, (k & 1) ? -eps : eps);
+            q = fminf(fmaxf(q, -radius), radius);
+            x[k][d] = __fmul_rn(__fadd_rn(q, radius), inv_2r);
+        }
+    }
+    if (warp == 0 && ok) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) x01_out[((size_t)s * 6 + k) * 3 + d] = x[k][d];
+    }
+    for (int l = warp; l < m.n_levels; l += FD_THREADS / 32) {
+        const float scale = m.scale[l];
+        const uint32_t res = m.res[l], off = m.offset[l], size = m.offset[l + 1] - off;
+        uint32_t cc[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu};      // cell whose corners are in v[]
+        float2 v[8];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            float r0 = 0.f, r1 = 0.f;
+            if (ok) {
+                const Cell c = locate(x[k][0], x[k][1], x[k][2], scale);
+                if (c.c[0] != cc[0] || c.c[1] != cc[1] || c.c[2] != cc[2]) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t idx = grid_index(c.c[0] + (j & 1), c.c[1] + ((j >> 1) & 1), c.c[2] + (j >> 2), res, size);
+                        v[j] = ldg2_keep(table, off + idx, pol);
+                    }
+                    cc[0] = c.c[0]; cc[1] = c.c[1]; cc[2] = c.c[2];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float wx = (j & 1) ? c.w[0] : 1.0f - c.w[0];
+                    const float wy = (j & 2) ? c.w[1] : 1.0f - c.w[1];
+                    const float wz = (j & 4) ? c.w[2] : 1.0f - c.w[2];
+                    const float wt = wx * wy * wz;
+                    r0 = fmaf(wt, v[j].x, r0);
+                    r1 = fmaf(wt, v[j].y, r1);
+                }
+            }
+            *reinterpret_cast<float2 *>(sy + (t * 6 + k) * ys + 2 * l) = make_float2(r0, r1);
+        }
+    }
+    __syncthreads();
+    const int rows = 6 * min(FD_S, n_samples - s0);
+    const int h = n_out / 2;
+    float2 *yo = reinterpret_cast<float2 *>(y + (size_t)s0 * 6 * n_out);
+    for (int i = threadIdx.x; i < rows * h; i += FD_THREADS) {
+        const int r = i / h, c = i - r * h;
+        __stcs(yo + i, *reinterpret_cast<const float2 *>(sy + r * ys + 2 * c));
+    }
+}
+
 // run-length warp aggregation: lanes with equal `key` that are adjacent are summed; the last
 // lane of each run issues one vector reduction.  Inactive lanes pass key = 0xffffffff, val 0.
 __device__ __forceinline__ void scatter_add2(float *table, uint32_t entry, float a, float b, bool active) {
@@ -532,6 +617,22 @@ int rsdf_hashgrid_bwd_bwd(const float *x, const float *table, const float *v, co
         default: return 0;
     }
 #undef RSDF_BB
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_hashgrid_fd6(const float *points, const float *table, const rsdf_hashgrid_meta *meta, int n_samples,
+                      float eps, float radius, float *x01_out, float *y, void *stream) {
+    if (n_samples == 0) return 0;
+    Meta m;
+    if (!points || !table || !x01_out || !y || !(radius > 0.0f) || !load_meta(meta, m)) return RSDF_EBADARG;
+    const int n_out = m.n_levels * NFEAT;
+    const size_t sm = sizeof(float) * FD_S * 6 * (n_out + 2);
+    cudaError_t e = cudaFuncSetAttribute(hashgrid_fd6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    const float inv_2r = 1.0f / (radius - (-radius));          // fl32(1) / fl32(2r): torch's tensor / scalar on CUDA
+    hashgrid_fd6_kernel<<<rsdf_div_up(n_samples, FD_S), FD_THREADS, sm, (cudaStream_t)stream>>>(
+        points, table, m, n_samples, eps, radius, inv_2r, x01_out, y);
     RSDF_LAUNCH_CHECK();
     return 0;
 }

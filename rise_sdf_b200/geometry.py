@@ -108,6 +108,31 @@ class VolumeSDF(nn.Module):
         out = self.network(self.encoding(x01))
         return out[..., 0] if sdf_only else out
 
+    def _fd6_sdf(self, points, eps):
+        """sdf at the six finite-difference neighbours of `points` [..., 3] -> [..., 6], or None when the fused
+        inference path does not apply.  One hash-grid launch builds the neighbours exactly as the reference
+        does (add, clamp, scale: models/geometry.py:229-237) and re-gathers corners only when a neighbour leaves
+        the previous one's cell; the MLP then writes just the sdf head."""
+        from . import sdf_field, tinycudann as tcnn
+        from .network_utils import VanillaMLP
+        if torch.is_grad_enabled() or not (points.is_cuda and VanillaMLP.fused_inference and points.numel() > 0):
+            return None
+        parts = self._fused_parts()
+        if parts is None or not self.network.config_output_activation_is_identity:
+            return None
+        inner, mask = parts
+        comp = self.encoding
+        x01, y = tcnn.hashgrid_fd6(inner, points.reshape(-1, 3), eps, self.radius)
+        if mask is not None:
+            if self._mask_ones is None:
+                self._mask_ones = bool((mask == 1).all())
+            if not self._mask_ones:
+                y = y * mask
+        if self._packed_sdf is None:
+            self._packed_sdf = sdf_field.PackedSDF(self.network)
+        sdf = self._packed_sdf(x01, comp.xyz_scale, comp.xyz_offset, y, sdf_only=True)
+        return sdf.view(*points.shape[:-1], 6)
+
     _packed_sdf = None
     _mask_ones = None           # cached "progressive level mask is all ones" (refreshed in update_step)
 
@@ -140,11 +165,13 @@ class VolumeSDF(nn.Module):
                                                create_graph=True, retain_graph=True, only_inputs=True)[0]
                 elif self.grad_type == "finite_difference":
                     eps = self._finite_difference_eps
-                    offsets = torch.as_tensor([[eps, 0.0, 0.0], [-eps, 0.0, 0.0], [0.0, eps, 0.0],
-                                               [0.0, -eps, 0.0], [0.0, 0.0, eps], [0.0, 0.0, -eps]]).to(points_)
-                    points_d_ = (points_[..., None, :] + offsets).clamp(-self.radius, self.radius)
-                    points_d = scale_anything(points_d_, (-self.radius, self.radius), (0, 1))
-                    points_d_sdf = self._field(points_d.view(-1, 3), sdf_only=True).view(*points.shape[:-1], 6).float()
+                    points_d_sdf = self._fd6_sdf(points_, eps)
+                    if points_d_sdf is None:
+                        offsets = torch.as_tensor([[eps, 0.0, 0.0], [-eps, 0.0, 0.0], [0.0, eps, 0.0],
+                                                   [0.0, -eps, 0.0], [0.0, 0.0, eps], [0.0, 0.0, -eps]]).to(points_)
+                        points_d_ = (points_[..., None, :] + offsets).clamp(-self.radius, self.radius)
+                        points_d = scale_anything(points_d_, (-self.radius, self.radius), (0, 1))
+                        points_d_sdf = self._field(points_d.view(-1, 3), sdf_only=True).view(*points.shape[:-1], 6).float()
                     grad = 0.5 * (points_d_sdf[..., 0::2] - points_d_sdf[..., 1::2]) / eps
                     if with_laplace:
                         # curvature probe (models/geometry.py:246-282)

@@ -198,6 +198,20 @@ def hashgrid_input_grad(enc, g2, x, dy_dx, link):
     return _HashGridInputGrad.apply(g2, dy_dx, x.contiguous().float(), enc.params, enc.meta, link)
 
 
+@torch.no_grad()
+def hashgrid_fd6(enc, points, eps, radius):
+    """Six finite-difference neighbours per point (inference only): points [S,3] in world units ->
+    (x01 [6S,3], y [6S,n_out]), rows ordered 6 s + k with k = +x,-x,+y,-y,+z,-z."""
+    L.require_cuda(points)
+    points = points.contiguous().float()
+    S = points.shape[0]
+    x01 = torch.empty(6 * S, 3, device=points.device, dtype=torch.float32)
+    y = torch.empty(6 * S, enc.meta.n_output_dims, device=points.device, dtype=torch.float32)
+    L.call("rsdf_hashgrid_fd6", L.ptr(points), L.ptr(enc.params.detach()), enc.meta.ref, S, float(eps), float(radius),
+           L.ptr(x01), L.ptr(y), L.stream())
+    return x01, y
+
+
 class _SHForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, degree):

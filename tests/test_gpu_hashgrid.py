@@ -126,3 +126,28 @@ def test_sh_fwd_bwd(degree):
     (out * go.cuda()).sum().backward()
     (ref * go.double()).sum().backward()
     assert float((uc.grad.cpu() - ref_in.grad).abs().max()) <= 1e-5 * float(ref_in.grad.abs().max())
+
+
+def test_fd6_neighbours_bit_identical_to_six_forward_passes():
+    """rsdf_hashgrid_fd6 == the reference's construction of the finite-difference neighbours
+    (models/geometry.py:229-237: add offset, clamp to +-radius, scale to the unit cube) followed by the plain
+    forward kernel: identical unit-cube coordinates and identical encodings, bit for bit."""
+    from rise_sdf_b200 import tinycudann as tcnn
+    from rise_sdf_b200.geometry import scale_anything
+    enc = tcnn.Encoding(3, dict(otype="HashGrid", n_levels=16, n_features_per_level=2, log2_hashmap_size=19,
+                                base_resolution=32, per_level_scale=1.447269237440378)).cuda()
+    with torch.no_grad():
+        enc.params.uniform_(-1.0, 1.0)
+    g = torch.Generator().manual_seed(11)
+    r = 1.5
+    for S, eps in ((1000, 2 * r / 8180.0), (33, 0.01), (5000, 1e-3)):
+        p = ((torch.rand(S, 3, generator=g) * 2 - 1) * r).cuda()
+        p[:7] = torch.tensor([[r, -r, 0.3], [r, r, r], [-r, -r, -r], [r - 1e-4, 0, 0], [0, -r + 1e-5, 0], [0, 0, r], [0, 0, 0]])
+        x01, y = tcnn.hashgrid_fd6(enc, p, eps, r)
+        offsets = torch.as_tensor([[eps, 0.0, 0.0], [-eps, 0.0, 0.0], [0.0, eps, 0.0],
+                                   [0.0, -eps, 0.0], [0.0, 0.0, eps], [0.0, 0.0, -eps]]).to(p)
+        pd = scale_anything((p[:, None, :] + offsets).clamp(-r, r), (-r, r), (0, 1)).view(-1, 3)
+        with torch.no_grad():
+            y_ref = enc(pd.contiguous())
+        assert torch.equal(x01, pd)
+        assert torch.equal(y, y_ref)
