@@ -699,6 +699,11 @@ __device__ __forceinline__ void ev_arrive(uint64_t *bar) {
 #define EV_DONE() { tc::fence_async_smem(); tc::tc_fence_before(); ev_sync(g); if (tg == 0) ev_arrive(&ct->ready[g]); }
 #define EV_WAIT() { tc::mbar_wait(&ct->done[g], dpar); dpar ^= 1u; tc::tc_fence_after(); }
 
+// SDF_ONLY (6 of every 7 evaluations of a relit frame: the finite-difference neighbours): only out[:, 0] is wanted,
+// so the third GEMM -- 42 % of the kernel's tensor work for one useful row of 128 -- is replaced by an fp32 dot
+// product on the CUDA cores: the a2 epilogue writes w3[0,f] * a2[f,s] into the (now idle) image buffer as
+// [sample][feature] floats and every warp sums 128 features for 8 samples with one 16-byte load and 5 shuffles.
+template <bool SDF_ONLY>
 __global__ void __launch_bounds__(EV_THREADS, 1)
 sdf_eval_kernel(const Net net, const Inputs in, float *__restrict__ out, float *__restrict__ sdf) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -733,7 +738,9 @@ sdf_eval_kernel(const Net net, const Inputs in, float *__restrict__ out, float *
         for (int tile = 2 * blockIdx.x + g; tile < n_tiles; tile += 2 * gridDim.x) {
             EV_ISSUE(gemm3<KP / 16>(tm + 0, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);)
             EV_ISSUE(gemm3<HID / 16>(tm + 64, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);)
-            EV_ISSUE(gemm3<HID / 16>(tm + 128, tc::op_kmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);)
+            if (!SDF_ONLY) {
+                EV_ISSUE(gemm3<HID / 16>(tm + 128, tc::op_kmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);)
+            }
         }
     } else {
         // ---- epilogue group g: thread = feature row f x the 32 sample columns [32*cg, +32) -----------
@@ -741,7 +748,7 @@ sdf_eval_kernel(const Net net, const Inputs in, float *__restrict__ out, float *
         const int cg = (t.warp >> 2) & 1;
         t.tl = tmem + ((uint32_t)(t.q * 32) << 16) + (uint32_t)(192 * g);
         uint8_t *h0_img = smem + EV_H0 + g * IMG_S_BYTES, *a_img = smem + EV_A + g * IMG_B_BYTES;
-        const float b1f = net.b1[t.f], b2f = net.b2[t.f];
+        const float b1f = net.b1[t.f], b2f = net.b2[t.f], w30f = net.w3r0[t.f], b30 = net.b3[0];
         const float b3f = t.f < net.n_out ? net.b3[t.f] : 0.0f;
         // staging: feature row fs = tg % 64 (< 48), chunks cs and cs + 4 of the tile
         const int fs = tg & 63, cs = tg >> 6;
@@ -777,6 +784,27 @@ sdf_eval_kernel(const Net net, const Inputs in, float *__restrict__ out, float *
             }
             EV_DONE()
             EV_WAIT()
+            if (SDF_ONLY) {
+                float *prod = reinterpret_cast<float *>(a_img);        // [64 samples][128 features] fp32 = 32 KB
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {          // w3[0,f] * softplus(Z2 + b2)
+                    t.col0 = 32 * cg + 16 * cc;
+                    float v[16];
+                    ld16(t, 64, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) prod[(t.col0 + j) * HID + t.f] = w30f * sp_act(v[j] + b2f);
+                }
+                tc::tc_fence_before();
+                ev_sync(g);
+                const int wg = t.warp & 7;                // 8 warps x 8 samples
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int sl = 8 * wg + i;
+                    const float4 q = *reinterpret_cast<const float4 *>(prod + sl * HID + 4 * t.lane);
+                    const float sum = warp_sum((q.x + q.y) + (q.z + q.w));
+                    if (t.lane == 0 && s0 + sl < in.S) sdf[s0 + sl] = sum + b30;
+                }
+            } else {
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {              // a2 = softplus(Z2 + b2)  (a1's GEMM has drained)
                 t.col0 = 32 * cg + 16 * cc;
@@ -802,6 +830,7 @@ sdf_eval_kernel(const Net net, const Inputs in, float *__restrict__ out, float *
                             if (sb + j < in.S) sdf[sb + j] = v[j] + b3f;
                     }
                 }
+            }
             }
             tc::tc_fence_before();
             ev_sync(g);                                   // this group's images / TMEM columns are reused next tile
@@ -881,11 +910,17 @@ int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
         if (e != cudaSuccess) return (int)e;
         sdf_fwd_kernel<true><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, g0a, g0b);
     } else {
-        e = cudaFuncSetAttribute(sdf_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV_SMEM);
-        if (e != cudaSuccess) return (int)e;
         const int pairs = (n_tiles + 1) / 2;
-        sdf_eval_kernel<<<pairs < RSDF_NUM_SMS ? pairs : RSDF_NUM_SMS, EV_THREADS, EV_SMEM, (cudaStream_t)stream>>>(
-            to_net(net), in, out, sdf);
+        const int eg = pairs < RSDF_NUM_SMS ? pairs : RSDF_NUM_SMS;
+        if (!out) {
+            e = cudaFuncSetAttribute(sdf_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV_SMEM);
+            if (e != cudaSuccess) return (int)e;
+            sdf_eval_kernel<true><<<eg, EV_THREADS, EV_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf);
+        } else {
+            e = cudaFuncSetAttribute(sdf_eval_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EV_SMEM);
+            if (e != cudaSuccess) return (int)e;
+            sdf_eval_kernel<false><<<eg, EV_THREADS, EV_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf);
+        }
     }
     RSDF_LAUNCH_CHECK();
     return 0;

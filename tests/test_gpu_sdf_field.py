@@ -104,3 +104,22 @@ def test_plain_input_segment():
     assert rel(out, ro.detach()) <= 2e-6
     for a, b in zip(got, want):
         assert rel(a, b) <= 2e-5
+
+
+@pytest.mark.parametrize("S", [1, 64, 65, 129, 148 * 128 + 77])
+def test_inference_kernel_out_and_sdf_only(S):
+    """PackedSDF (two-group inference kernel): full output == the training forward, and the sdf-only variant
+    (third GEMM replaced by an fp32 dot product) == channel 0, both against fp64."""
+    m = make_mlp(seed=3)
+    g = torch.Generator().manual_seed(S)
+    x01 = torch.rand(S, 3, generator=g).cuda()
+    enc = (torch.randn(S, 32, generator=g) * 0.1).cuda()
+    packed = sdf_field.PackedSDF(m)
+    out = packed(x01, 2.0, -1.0, enc)
+    sdf = packed(x01, 2.0, -1.0, enc, sdf_only=True)
+    h0 = torch.cat([x01 * 2 - 1, enc], -1)
+    out1 = packed(h0)                                     # single input segment
+    ro, _ = ref64(m, x01.double(), enc.double(), want_g0=False)
+    assert out.shape == (S, 48) and sdf.shape == (S,)
+    assert rel(out, ro.detach()) <= 2e-6 and rel(out1, ro.detach()) <= 2e-6
+    assert float((sdf.double().cpu() - ro[:, 0].detach().cpu()).abs().max()) <= 2e-6 * max(float(ro[:, 0].abs().max()), 1.0)
