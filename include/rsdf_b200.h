@@ -88,6 +88,15 @@ int rsdf_accumulate_bwd(const int64_t *ray_indices, const float *weights, const 
                         const float *grad_out, int n_samples, int D, float *grad_weights,
                         float *grad_values, void *stream);
 
+/* Per-sample set-up of models/neus.py:247-252 in one launch: dirs = rays_d[ray_indices], midpoints = (t0 + t1) / 2,
+ * positions = rays_o[ray_indices] + dirs * midpoints, dists = t1 - t0 (same fp32 operation order, no contraction). */
+int rsdf_sample_setup(const float *rays_o, const float *rays_d, const long long *ray_indices, const float *t_starts,
+                      const float *t_ends, int n_samples, float *positions, float *dirs, float *midpoints,
+                      float *dists, void *stream);
+/* F.normalize(g[n,3], p=2, dim=-1, eps) (models/neus.py:254) and its backward. */
+int rsdf_normalize3_fwd(const float *g, int n, float eps, float *out, void *stream);
+int rsdf_normalize3_bwd(const float *g, const float *grad_out, int n, float eps, float *grad_g, void *stream);
+
 /* Fused NeuS render (models/neus.py:128-150 get_alpha + :262-277): alpha with cos-annealing,
  * per-ray transmittance scan, accumulation of rgb[3], normal[3], opacity, depth in ONE pass.
  * out[n_rays,8] = (rgb3, normal3 (un-normalised), opacity, depth); alpha/weights [S] saved. */

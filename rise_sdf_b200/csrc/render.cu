@@ -312,7 +312,85 @@ neus_render_bwd_kernel(const int32_t *__restrict__ packed, const float *__restri
 
 }  // namespace
 
+// ---- per-sample set-up and normal normalisation (the elementwise glue of models/neus.py:247-256) ----------
+// positions = o[ray] + d[ray] * (t0 + t1) / 2  with the reference's operation order (add, divide by 2 == * 0.5
+// exactly, multiply, add: no contraction), plus the gathered directions, midpoints and interval lengths.
+__global__ void sample_setup_kernel(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                                    const long long *__restrict__ ray_indices, const float *__restrict__ t_starts,
+                                    const float *__restrict__ t_ends, int n, float *__restrict__ positions,
+                                    float *__restrict__ dirs, float *__restrict__ midpoints, float *__restrict__ dists) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long r = ray_indices[i];
+    const float t0 = t_starts[i], t1 = t_ends[i];
+    const float mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+    midpoints[i] = mid;
+    dists[i] = __fsub_rn(t1, t0);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float o = __ldg(rays_o + 3 * r + d), v = __ldg(rays_d + 3 * r + d);
+        dirs[3 * (size_t)i + d] = v;
+        positions[3 * (size_t)i + d] = __fadd_rn(o, __fmul_rn(v, mid));
+    }
+}
+
+// F.normalize(g, p=2, dim=-1, eps): n = g / max(|g|, eps)
+__global__ void normalize3_fwd_kernel(const float *__restrict__ g, int n, float eps, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = g[3 * (size_t)i], y = g[3 * (size_t)i + 1], z = g[3 * (size_t)i + 2];
+    const float inv = 1.0f / fmaxf(sqrtf(x * x + y * y + z * z), eps);
+    out[3 * (size_t)i] = x * inv; out[3 * (size_t)i + 1] = y * inv; out[3 * (size_t)i + 2] = z * inv;
+}
+// backward: |g| > eps: (gn - n (n . gn)) / |g|;  otherwise gn / eps
+__global__ void normalize3_bwd_kernel(const float *__restrict__ g, const float *__restrict__ gn, int n, float eps,
+                                      float *__restrict__ gg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = g[3 * (size_t)i], y = g[3 * (size_t)i + 1], z = g[3 * (size_t)i + 2];
+    const float a = gn[3 * (size_t)i], b = gn[3 * (size_t)i + 1], c = gn[3 * (size_t)i + 2];
+    const float len = sqrtf(x * x + y * y + z * z);
+    if (len > eps) {
+        const float inv = 1.0f / len;
+        const float nx = x * inv, ny = y * inv, nz = z * inv;
+        const float dot = nx * a + ny * b + nz * c;
+        gg[3 * (size_t)i] = (a - nx * dot) * inv; gg[3 * (size_t)i + 1] = (b - ny * dot) * inv;
+        gg[3 * (size_t)i + 2] = (c - nz * dot) * inv;
+    } else {
+        const float inv = 1.0f / eps;
+        gg[3 * (size_t)i] = a * inv; gg[3 * (size_t)i + 1] = b * inv; gg[3 * (size_t)i + 2] = c * inv;
+    }
+}
+
 extern "C" {
+
+int rsdf_sample_setup(const float *rays_o, const float *rays_d, const long long *ray_indices, const float *t_starts,
+                      const float *t_ends, int n_samples, float *positions, float *dirs, float *midpoints,
+                      float *dists, void *stream) {
+    if (n_samples == 0) return 0;
+    if (!rays_o || !rays_d || !ray_indices || !t_starts || !t_ends || !positions || !dirs || !midpoints || !dists)
+        return RSDF_EBADARG;
+    sample_setup_kernel<<<rsdf_div_up(n_samples, 256), 256, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, ray_indices, t_starts, t_ends, n_samples, positions, dirs, midpoints, dists);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_normalize3_fwd(const float *g, int n, float eps, float *out, void *stream) {
+    if (n == 0) return 0;
+    if (!g || !out) return RSDF_EBADARG;
+    normalize3_fwd_kernel<<<rsdf_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(g, n, eps, out);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_normalize3_bwd(const float *g, const float *grad_out, int n, float eps, float *grad_g, void *stream) {
+    if (n == 0) return 0;
+    if (!g || !grad_out || !grad_g) return RSDF_EBADARG;
+    normalize3_bwd_kernel<<<rsdf_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(g, grad_out, n, eps, grad_g);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
 
 int rsdf_weight_from_alpha_fwd(const int32_t *packed_info, const float *alphas, int n_rays,
                                float *weights, float *trans, void *stream) {

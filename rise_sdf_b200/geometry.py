@@ -16,6 +16,8 @@ from .network_utils import Config, get_encoding, get_mlp, update_module_step
 def scale_anything(dat, inp_scale, tgt_scale):
     """models/utils.py:109-114."""
     dat = (dat - inp_scale[0]) / (inp_scale[1] - inp_scale[0])
+    if tgt_scale[0] == 0 and tgt_scale[1] == 1:
+        return dat                     # `* 1 + 0` is the identity bit for bit (x01 >= 0: no -0.0)
     return dat * (tgt_scale[1] - tgt_scale[0]) + tgt_scale[0]
 
 

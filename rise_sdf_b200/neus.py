@@ -125,6 +125,48 @@ class _NeusRender(torch.autograd.Function):
         return None, None, None, None, g_sdf, g_grad, g_rgb, g_inv.sum().reshape(ctx.inv_shape), None
 
 
+@torch.no_grad()
+def sample_setup(rays_o, rays_d, ray_indices, t_starts, t_ends):
+    """models/neus.py:247-252 in one launch -> (positions [S,3], t_dirs [S,3], midpoints [S,1], dists [S])."""
+    S = ray_indices.shape[0]
+    dev = rays_o.device
+    positions = torch.empty(S, 3, device=dev, dtype=torch.float32)
+    t_dirs = torch.empty(S, 3, device=dev, dtype=torch.float32)
+    midpoints = torch.empty(S, 1, device=dev, dtype=torch.float32)
+    dists = torch.empty(S, device=dev, dtype=torch.float32)
+    L.call("rsdf_sample_setup", L.ptr(rays_o.contiguous()), L.ptr(rays_d.contiguous()), L.ptr(ray_indices.contiguous()),
+           L.ptr(t_starts.contiguous()), L.ptr(t_ends.contiguous()), S, L.ptr(positions), L.ptr(t_dirs),
+           L.ptr(midpoints), L.ptr(dists), L.stream())
+    return positions, t_dirs, midpoints, dists
+
+
+class _Normalize3(torch.autograd.Function):
+    """F.normalize(g, p=2, dim=-1) for [S,3] CUDA tensors: one kernel forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, g, eps):
+        g = g.contiguous().float()
+        out = torch.empty_like(g)
+        L.call("rsdf_normalize3_fwd", L.ptr(g), g.shape[0], float(eps), L.ptr(out), L.stream())
+        ctx.save_for_backward(g)
+        ctx.eps = float(eps)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gn):
+        (g,) = ctx.saved_tensors
+        gg = torch.empty_like(g)
+        L.call("rsdf_normalize3_bwd", L.ptr(g), L.ptr(gn.contiguous().float()), g.shape[0], ctx.eps, L.ptr(gg), L.stream())
+        return gg, None
+
+
+def normalize3(g, eps=1e-12):
+    if g.is_cuda and g.dim() == 2 and g.shape[1] == 3 and g.shape[0] > 0:
+        return _Normalize3.apply(g, eps)
+    return F.normalize(g, p=2, dim=-1, eps=eps)
+
+
 class NeuSModel(nn.Module):
     def __init__(self, config, fused_render=True):
         super().__init__()
@@ -199,13 +241,16 @@ class NeuSModel(nn.Module):
             comp_rgb, comp_normal, opacity, depth = z(n_rays, 3), z(n_rays, 3), z(n_rays, 1), z(n_rays, 1)
             sdf, sdf_grad, weights, midpoints, dists = z(0), z(0, 3), z(0), z(0, 1), z(0)
         else:
-            t_origins = rays_o[ray_indices]
-            t_dirs = rays_d[ray_indices]
-            midpoints = (t_starts + t_ends)[..., None] / 2.0
-            positions = t_origins + t_dirs * midpoints
-            dists = t_ends - t_starts
+            if rays.is_cuda and not (rays_o.requires_grad or rays_d.requires_grad):
+                positions, t_dirs, midpoints, dists = sample_setup(rays_o, rays_d, ray_indices, t_starts, t_ends)
+            else:
+                t_origins = rays_o[ray_indices]
+                t_dirs = rays_d[ray_indices]
+                midpoints = (t_starts + t_ends)[..., None] / 2.0
+                positions = t_origins + t_dirs * midpoints
+                dists = t_ends - t_starts
             sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
-            normal = F.normalize(sdf_grad, p=2, dim=-1)
+            normal = normalize3(sdf_grad)
             rgb = self.texture(feature, t_dirs, normal)
             if self.fused_render:
                 out8, weights, _ = _NeusRender.apply(packed, rays_d, t_starts, t_ends, sdf, sdf_grad, rgb,
