@@ -97,6 +97,13 @@ int rsdf_sample_setup(const float *rays_o, const float *rays_d, const long long 
 int rsdf_normalize3_fwd(const float *g, int n, float eps, float *out, void *stream);
 int rsdf_normalize3_bwd(const float *g, const float *grad_out, int n, float eps, float *grad_g, void *stream);
 
+/* Eikonal and sparsity regularisers of the loss block (systems/neus.py:117-131, systems/split_occ.py:186-204) as
+ * sums over the samples: out2[0] = sum (|sdf_grad_i| - 1)^2, out2[1] = sum exp(-scale |sdf_i|) (the caller divides
+ * by n); backward from the two scalar cotangents cot2 (device). */
+int rsdf_sdf_reg_fwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, float *out2, void *stream);
+int rsdf_sdf_reg_bwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, const float *cot2,
+                     float *grad_sdf_grad, float *grad_sdf, void *stream);
+
 /* Fused NeuS render (models/neus.py:128-150 get_alpha + :262-277): alpha with cos-annealing,
  * per-ray transmittance scan, accumulation of rgb[3], normal[3], opacity, depth in ONE pass.
  * out[n_rays,8] = (rgb3, normal3 (un-normalised), opacity, depth); alpha/weights [S] saved. */

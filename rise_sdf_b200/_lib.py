@@ -58,6 +58,8 @@ _SIGS = {
     "rsdf_neus_render_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_p, c_p, c_p, c_p],
     "rsdf_neus_render_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i,
                              c_p, c_p, c_p, c_p, c_p],
+    "rsdf_sdf_reg_fwd": [c_p, c_p, c_i, c_f, c_p, c_p],
+    "rsdf_sdf_reg_bwd": [c_p, c_p, c_i, c_f, c_p, c_p, c_p, c_p],
     "rsdf_sample_setup": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p],
     "rsdf_normalize3_fwd": [c_p, c_i, c_f, c_p, c_p],
     "rsdf_normalize3_bwd": [c_p, c_p, c_i, c_f, c_p, c_p],

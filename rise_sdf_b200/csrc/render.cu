@@ -362,7 +362,67 @@ __global__ void normalize3_bwd_kernel(const float *__restrict__ g, const float *
     }
 }
 
+// ---- eikonal + sparsity regularisers (systems/neus.py:117-131): sums over the samples in one pass ----------
+//   out[0] += sum_i (|g_i| - 1)^2        out[1] += sum_i exp(-scale * |sdf_i|)
+__global__ void sdf_reg_fwd_kernel(const float *__restrict__ g, const float *__restrict__ sdf, int n, float scale,
+                                   float *__restrict__ out) {
+    float e = 0.f, sp = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = g[3 * (size_t)i], y = g[3 * (size_t)i + 1], z = g[3 * (size_t)i + 2];
+        const float d = sqrtf(x * x + y * y + z * z) - 1.0f;
+        e = fmaf(d, d, e);
+        sp += expf(-scale * fabsf(sdf[i]));
+    }
+    e = warp_sum(e); sp = warp_sum(sp);
+    __shared__ float se[32], ss[32];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { se[w] = e; ss[w] = sp; }
+    __syncthreads();
+    if (w == 0) {
+        e = l < (blockDim.x >> 5) ? se[l] : 0.f; sp = l < (blockDim.x >> 5) ? ss[l] : 0.f;
+        e = warp_sum(e); sp = warp_sum(sp);
+        if (l == 0) { atomicAdd(out, e); atomicAdd(out + 1, sp); }
+    }
+}
+// cotangents ce, cs (device scalars, already divided by n by the caller's mean):
+//   gg_i = ce * 2 (|g_i| - 1) g_i / |g_i|      gs_i = -cs * scale * sign(sdf_i) exp(-scale |sdf_i|)
+__global__ void sdf_reg_bwd_kernel(const float *__restrict__ g, const float *__restrict__ sdf, int n, float scale,
+                                   const float *__restrict__ cot, float *__restrict__ gg, float *__restrict__ gs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float ce = cot[0], cs = cot[1];
+    const float x = g[3 * (size_t)i], y = g[3 * (size_t)i + 1], z = g[3 * (size_t)i + 2];
+    const float len = sqrtf(x * x + y * y + z * z);
+    const float k = len > 0.0f ? ce * 2.0f * (len - 1.0f) / len : 0.0f;
+    gg[3 * (size_t)i] = k * x; gg[3 * (size_t)i + 1] = k * y; gg[3 * (size_t)i + 2] = k * z;
+    const float v = sdf[i];
+    const float sgn = v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f);
+    gs[i] = -cs * scale * sgn * expf(-scale * fabsf(v));
+}
+
 extern "C" {
+
+int rsdf_sdf_reg_fwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, float *out2, void *stream) {
+    if (!out2) return RSDF_EBADARG;
+    cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    if (n == 0) return 0;
+    if (!sdf_grad || !sdf) return RSDF_EBADARG;
+    const int blocks = rsdf_div_up(n, 256) < 8 * RSDF_NUM_SMS ? rsdf_div_up(n, 256) : 8 * RSDF_NUM_SMS;
+    sdf_reg_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sdf_grad, sdf, n, sparsity_scale, out2);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_sdf_reg_bwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, const float *cot2,
+                     float *grad_sdf_grad, float *grad_sdf, void *stream) {
+    if (n == 0) return 0;
+    if (!sdf_grad || !sdf || !cot2 || !grad_sdf_grad || !grad_sdf) return RSDF_EBADARG;
+    sdf_reg_bwd_kernel<<<rsdf_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(sdf_grad, sdf, n, sparsity_scale, cot2,
+                                                                              grad_sdf_grad, grad_sdf);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
 
 int rsdf_sample_setup(const float *rays_o, const float *rays_d, const long long *ray_indices, const float *t_starts,
                       const float *t_ends, int n_samples, float *positions, float *dirs, float *midpoints,

@@ -14,14 +14,50 @@ def binary_cross_entropy(inp, target):
     return -(target * torch.log(inp) + (1 - target) * torch.log(1 - inp)).mean()
 
 
+class _SdfRegularisers(torch.autograd.Function):
+    """(sdf_grad [S,3], sdf [S]) -> (mean (|sdf_grad| - 1)^2, mean exp(-scale |sdf|)): one reduction launch
+    forward, one elementwise launch backward (instead of ~8 + ~10 torch kernels)."""
+
+    @staticmethod
+    def forward(ctx, sdf_grad, sdf, scale):
+        from . import _lib as L
+        sdf_grad, sdf = sdf_grad.contiguous().float(), sdf.contiguous().float()
+        n = sdf.shape[0]
+        out = torch.empty(2, device=sdf.device, dtype=torch.float32)
+        L.call("rsdf_sdf_reg_fwd", L.ptr(sdf_grad), L.ptr(sdf), n, float(scale), L.ptr(out), L.stream())
+        ctx.save_for_backward(sdf_grad, sdf)
+        ctx.scale = float(scale)
+        out = out / max(n, 1)
+        return out[0], out[1]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, ge, gs):
+        from . import _lib as L
+        sdf_grad, sdf = ctx.saved_tensors
+        n = sdf.shape[0]
+        cot = torch.stack([ge, gs]).float() / max(n, 1)
+        g1, g2 = torch.empty_like(sdf_grad), torch.empty_like(sdf)
+        L.call("rsdf_sdf_reg_bwd", L.ptr(sdf_grad), L.ptr(sdf), n, ctx.scale, L.ptr(cot.contiguous()), L.ptr(g1), L.ptr(g2),
+               L.stream())
+        return g1, g2, None
+
+
+def sdf_regularisers(sdf_grad, sdf, sparsity_scale=1.0):
+    """-> (eikonal, sparsity) loss terms (systems/neus.py:117-131)."""
+    if sdf.is_cuda and sdf.shape[0] > 0:
+        return _SdfRegularisers.apply(sdf_grad, sdf, sparsity_scale)
+    eik = ((torch.linalg.norm(sdf_grad, ord=2, dim=-1) - 1.0) ** 2).mean()
+    return eik, torch.exp(-sparsity_scale * sdf.abs()).mean()
+
+
 def neus_loss(out, rgb, fg_mask, lambda_rgb_mse=10.0, lambda_mask=0.1, lambda_eikonal=0.1,
               lambda_sparsity=0.01, sparsity_scale=1.0):
     valid = out["rays_valid_full"][..., 0]
     loss_rgb = F.mse_loss(out["comp_rgb_full"][valid], rgb[valid])
-    loss_eik = ((torch.linalg.norm(out["sdf_grad_samples"], ord=2, dim=-1) - 1.0) ** 2).mean()
+    loss_eik, loss_sparse = sdf_regularisers(out["sdf_grad_samples"], out["sdf_samples"], sparsity_scale)
     opacity = torch.clamp(out["opacity"].squeeze(-1), 1e-3, 1 - 1e-3)
     loss_mask = binary_cross_entropy(opacity, fg_mask.float())
-    loss_sparse = torch.exp(-sparsity_scale * out["sdf_samples"].abs()).mean()
     loss = (loss_rgb * lambda_rgb_mse + loss_eik * lambda_eikonal + loss_mask * lambda_mask
             + loss_sparse * lambda_sparsity)
     return loss, {"rgb_mse": loss_rgb, "eikonal": loss_eik, "mask": loss_mask, "sparsity": loss_sparse}
@@ -48,14 +84,14 @@ def split_loss(model, out, rgb, fg_mask, has_mask=True, **overrides):
         loss = loss + parts["rgb_phys_mse"] * lam["lambda_rgb_phys_mse"]
         if lam["lambda_rgb_phys_l1"]:
             loss = loss + F.l1_loss(out["comp_rgb_phys_full"][valid], rgb[valid]) * lam["lambda_rgb_phys_l1"]
-    parts["eikonal"] = ((torch.linalg.norm(out["sdf_grad_samples"], ord=2, dim=-1) - 1.0) ** 2).mean()
+    parts["eikonal"], parts["sparsity"] = sdf_regularisers(out["sdf_grad_samples"], out["sdf_samples"],
+                                                            lam["sparsity_scale"])
     loss = loss + parts["eikonal"] * lam["lambda_eikonal"]
     opacity = torch.clamp(out["opacity"].squeeze(-1), 1e-3, 1 - 1e-3)
     parts["mask"] = binary_cross_entropy(opacity, fg_mask.float())
     loss = loss + parts["mask"] * (lam["lambda_mask"] if has_mask else 0.0)
     if lam["lambda_opaque"]:
         loss = loss + binary_cross_entropy(opacity, opacity) * lam["lambda_opaque"]
-    parts["sparsity"] = torch.exp(-lam["sparsity_scale"] * out["sdf_samples"].abs()).mean()
     loss = loss + parts["sparsity"] * lam["lambda_sparsity"]
     if lam["lambda_curvature"] > 0:
         assert "sdf_laplace_samples" in out, "Need geometry.grad_type='finite_difference' to get SDF Laplace samples"

@@ -159,3 +159,40 @@ def test_fused_neus_render_fwd_bwd(ratio):
         want = want.numpy()
         err = np.abs(got.cpu().numpy() - want).max()
         assert err <= 2e-4 * max(np.abs(want).max(), 1e-3), (name, err, np.abs(want).max())
+
+
+def test_sample_setup_normalize_and_sdf_regularisers_match_torch():
+    """The single-launch glue ops against the torch expressions they replace (models/neus.py:247-256,
+    systems/neus.py:117-131): sample set-up bit-exact, normalisation / regularisers to fp32 rounding,
+    including their gradients."""
+    import torch.nn.functional as F
+    from rise_sdf_b200.neus import normalize3, sample_setup
+    from rise_sdf_b200.train import sdf_regularisers
+    g = torch.Generator().manual_seed(3)
+    R, S = 300, 20000
+    rays_o = torch.randn(R, 3, generator=g).cuda(); rays_d = F.normalize(torch.randn(R, 3, generator=g), dim=-1).cuda()
+    ri = torch.sort(torch.randint(0, R, (S,), generator=g)).values.cuda()
+    t0 = (torch.rand(S, generator=g) * 4).cuda(); t1 = t0 + 0.005
+    pos, dirs, mid, dists = sample_setup(rays_o, rays_d, ri, t0, t1)
+    mid_ref = (t0 + t1)[..., None] / 2.0
+    assert torch.equal(mid, mid_ref) and torch.equal(dirs, rays_d[ri]) and torch.equal(dists, t1 - t0)
+    assert torch.equal(pos, rays_o[ri] + rays_d[ri] * mid_ref)
+
+    v = (torch.randn(S, 3, generator=g) * 0.7).cuda(); v[:3] = 0.0
+    sdf = torch.randn(S, generator=g).cuda(); sdf[5] = 0.0
+    c = torch.randn(S, 3, generator=g).cuda()
+    va = v.clone().requires_grad_(True); vb = v.clone().double().requires_grad_(True)
+    (ga,) = torch.autograd.grad((normalize3(va) * c).sum(), va)
+    (gb,) = torch.autograd.grad((F.normalize(vb, p=2, dim=-1) * c.double()).sum(), vb)
+    assert float((normalize3(v).double() - F.normalize(v.double(), dim=-1)).abs().max()) <= 1e-6
+    assert float((ga.double() - gb)[3:].abs().max()) <= 1e-5 * float(gb[3:].abs().max())
+
+    va = v.clone().requires_grad_(True); sa = sdf.clone().requires_grad_(True)
+    e, s = sdf_regularisers(va, sa, 1.3)
+    ga, gs = torch.autograd.grad(0.1 * e + 0.01 * s, [va, sa])
+    vb = v.clone().double().requires_grad_(True); sb = sdf.clone().double().requires_grad_(True)
+    e_ref = ((torch.linalg.norm(vb, ord=2, dim=-1) - 1.0) ** 2).mean(); s_ref = torch.exp(-1.3 * sb.abs()).mean()
+    gb, gsb = torch.autograd.grad(0.1 * e_ref + 0.01 * s_ref, [vb, sb])
+    assert abs(float(e) - float(e_ref)) <= 1e-5 * float(e_ref) and abs(float(s) - float(s_ref)) <= 1e-5 * float(s_ref)
+    assert float((ga.double() - gb)[3:].abs().max()) <= 1e-5 * float(gb.abs().max())
+    assert float((gs.double() - gsb).abs().max()) <= 1e-5 * float(gsb.abs().max())
