@@ -31,6 +31,10 @@ struct TestSmem {
     uint32_t tmem_slot;
 };
 
+// mode 3: as mode 0, but the A operand comes from TENSOR MEMORY (tcgen05.mma "TS" form): every thread packs its
+//         sample row as fp16 pairs and writes it with tcgen05.st -- lane = row, 32-bit column j = (k = 2j, 2j+1),
+//         16 k-values (8 columns) per K-step; hi and lo planes side by side.  The A fetch then costs no shared-
+//         memory bandwidth (the 4 KB per instruction that bounds the shared-memory form at N <= 64).
 // mode 0: C[S,N]  = A[S,K]  * W[N,K]^T      (B = W blob, K-major)
 // mode 1: C[S,K]  = A[S,N]  * W[N,K]        (B = W blob seen MN-major = W^T)
 // mode 2: C[Fa,Fb] += A[S,Fa]^T * Y[S,Fb]   (both operands MN-major, contraction over samples)
@@ -51,11 +55,12 @@ tc_gemm_test_kernel(int mode, const float *__restrict__ A, const uint8_t *__rest
         tc::mbar_init(&ts->bar_mma, 1);
         tc::mbar_fence_init();
     }
-    if (warp == 0) tc::tmem_alloc(&ts->tmem_slot, 128);
+    if (warp == 0) tc::tmem_alloc(&ts->tmem_slot, 256);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = ts->tmem_slot;
+    constexpr uint32_t COL_AHI = 128, COL_ALO = 192;       // mode 3: A planes in TMEM (64 columns each)
 
     uint32_t b_plane = 0;
     if (mode != 2) {
@@ -95,11 +100,50 @@ tc_gemm_test_kernel(int mode, const float *__restrict__ A, const uint8_t *__rest
                 tc::store_chunk(b_img, b_plane, TM, tid, c, v);
             }
         }
+        if (mode == 3) {
+            const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+            for (int c8 = 0; c8 < a_pad / 16; ++c8) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = c8 * 16 + 2 * j;
+                    const float x0 = (s < S && k < d_a) ? A[(size_t)s * d_a + k] : 0.0f;
+                    const float x1 = (s < S && k + 1 < d_a) ? A[(size_t)s * d_a + k + 1] : 0.0f;
+                    tc::split2(x0, x1, hi[j], lo[j]);
+                }
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"r"(tl + COL_AHI + c8 * 8), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]),
+                               "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"r"(tl + COL_ALO + c8 * 8), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]),
+                               "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc::tc_fence_before();
+        }
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
             tc::tc_fence_after();
-            if (mode == 0) {
+            if (mode == 3) {
+                const uint32_t idesc = tc::instr_desc(128, w_rows_pad, false, false);
+                const tc::Operand B = tc::op_kmajor(tc::smem_u32(b_img), b_plane, w_rows_pad);
+                const int ksteps = a_pad / 16;
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t a0 = tmem + (term == 0 ? COL_ALO : COL_AHI);
+                    const uint32_t b0 = B.addr + (term == 1 ? B.plane : 0u);
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t bd = tc::smem_desc(b0 + k * B.kstep, B.lbo, B.sbo);
+                        const uint32_t acc = (term > 0 || k > 0) ? 1u : 0u, z = 0u;
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred p;\n\t"
+                            "setp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+                            "}" ::"r"(tmem), "r"(a0 + k * 8), "l"(bd), "r"(idesc), "r"(acc), "r"(z) : "memory");
+                    }
+                }
+            } else if (mode == 0) {
                 // D[128 x N] = A(K-major, K=a_pad) * W(K-major: rows N_pad, K=w_cols_pad)
                 const uint32_t idesc = tc::instr_desc(128, w_rows_pad, false, false);
                 tc::gemm_split3(tmem, tc::op_kmajor(tc::smem_u32(a_img), a_plane, TM),
@@ -121,8 +165,8 @@ tc_gemm_test_kernel(int mode, const float *__restrict__ A, const uint8_t *__rest
         phase ^= 1;
         tc::tc_fence_after();
         if (mode != 2) {
-            const int n_out = mode == 0 ? d_b : d_b;   // logical output width
-            const int n_cols = mode == 0 ? w_rows_pad : w_cols_pad;
+            const int n_out = d_b;                     // logical output width
+            const int n_cols = (mode == 0 || mode == 3) ? w_rows_pad : w_cols_pad;
             for (int c0 = 0; c0 < n_cols; c0 += 16) {
                 float v[16];
                 tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
@@ -148,7 +192,7 @@ tc_gemm_test_kernel(int mode, const float *__restrict__ A, const uint8_t *__rest
         tc::tc_fence_before();
     }
     __syncthreads();
-    if (warp == 0) tc::tmem_free(tmem, 128);
+    if (warp == 0) tc::tmem_free(tmem, 256);
 }
 
 

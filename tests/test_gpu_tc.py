@@ -149,3 +149,16 @@ def test_mm_stream_ragged_and_large():
     for S in (1, 127, 129, 148 * 128 + 5, 300000):
         x = torch.randn(S, 67, generator=g).cuda(); W = torch.randn(128, 67, generator=g).cuda()
         assert err(tca.mm_nt(x, W), x.double().cpu() @ W.double().cpu().T) <= 2e-6, S
+
+
+@pytest.mark.parametrize("S,K,N", [(128, 128, 128), (1000, 35, 128), (333, 128, 48), (257, 64, 16)])
+def test_a_operand_from_tensor_memory(S, K, N):
+    """tcgen05.mma with the A operand in TMEM (lane = row, 32-bit column j = fp16 pair k = 2j, 2j+1, written with
+    tcgen05.st): same product as the shared-memory form, C = A W^T, to fp32-class accuracy."""
+    g = torch.Generator().manual_seed(3 * S + K + N)
+    A = torch.randn(S, K, generator=g).cuda()
+    W = torch.randn(N, K, generator=g).cuda()
+    C = torch.full((S, N), float("nan"), device="cuda")
+    L.call("rsdf_tc_gemm_test", 3, L.ptr(A), L.ptr(pack(W)), None, L.ptr(C), S, K, N, pad16(N), pad16(K), 8, L.stream())
+    torch.cuda.synchronize()
+    assert err(C, A.double().cpu() @ W.double().cpu().T) <= 2e-6
