@@ -106,19 +106,23 @@ def test_plain_input_segment():
         assert rel(a, b) <= 2e-5
 
 
-@pytest.mark.parametrize("S", [1, 64, 65, 129, 148 * 128 + 77])
-def test_inference_kernel_out_and_sdf_only(S):
+@pytest.mark.parametrize("ts", [True, False])
+@pytest.mark.parametrize("S", [1, 64, 65, 129, 2 * 148 * 128 + 77])
+def test_inference_kernel_out_and_sdf_only(S, ts):
     """PackedSDF (two-group inference kernel): full output == the training forward, and the sdf-only variant
     (third GEMM replaced by an fp32 dot product) == channel 0, both against fp64."""
     m = make_mlp(seed=3)
     g = torch.Generator().manual_seed(S)
     x01 = torch.rand(S, 3, generator=g).cuda()
     enc = (torch.randn(S, 32, generator=g) * 0.1).cuda()
+    sdf_field.PackedSDF.tensor_memory_operands = ts       # both inference kernels: TMEM-operand and smem-operand
+    sdf_field.PackedSDF.tensor_memory_full_output = ts
     packed = sdf_field.PackedSDF(m)
     out = packed(x01, 2.0, -1.0, enc)
     sdf = packed(x01, 2.0, -1.0, enc, sdf_only=True)
     h0 = torch.cat([x01 * 2 - 1, enc], -1)
     out1 = packed(h0)                                     # single input segment
+    sdf_field.PackedSDF.tensor_memory_operands, sdf_field.PackedSDF.tensor_memory_full_output = True, False
     ro, _ = ref64(m, x01.double(), enc.double(), want_g0=False)
     assert out.shape == (S, 48) and sdf.shape == (S,)
     assert rel(out, ro.detach()) <= 2e-6 and rel(out1, ro.detach()) <= 2e-6
