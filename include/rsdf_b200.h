@@ -319,6 +319,28 @@ int rsdf_relu_layer_bwd(const rsdf_relu_layer_bwd_args *args_host, void *stream)
 int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *Y, float *C, int S,
                       int d_a, int d_b, int w_rows_pad, int w_cols_pad, int grid, void *stream);
 
+/* ---------------------------------------------------------------- optimizer */
+/* systems/utils.py:309-320 `parse_optimizer` -> torch.optim.Adam with per-group lr
+ * (configs/neus-blender.yaml:92-104, configs/split-mixed-occ-tensoir.yaml:153-166): ONE launch over flat
+ * fp32 buffers params / grads / exp_avg / exp_avg_sq [n] that share one element order (16-byte aligned).
+ * Group k covers elements [end[k-1], end[k]) (end[n_groups-1] == n).  The host folds the step count into
+ * step_size = lr / (1 - beta1^t) and bias2_sqrt = sqrt(1 - beta2^t), exactly as torch's
+ * `_single_tensor_adam` does; weight_decay is the L2 (non-decoupled) form.  zero_grad != 0 clears the
+ * gradient buffer in the same pass (the next step's accumulation target). */
+#define RSDF_ADAM_MAX_GROUPS 8
+typedef struct rsdf_adam_groups {
+    int32_t n_groups;
+    int64_t end[RSDF_ADAM_MAX_GROUPS];
+    float step_size[RSDF_ADAM_MAX_GROUPS];
+    float beta1[RSDF_ADAM_MAX_GROUPS];
+    float beta2[RSDF_ADAM_MAX_GROUPS];
+    float eps[RSDF_ADAM_MAX_GROUPS];
+    float bias2_sqrt[RSDF_ADAM_MAX_GROUPS];
+    float weight_decay[RSDF_ADAM_MAX_GROUPS];
+} rsdf_adam_groups;
+int rsdf_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, long long n,
+                   const rsdf_adam_groups *groups_host, int zero_grad, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,16 @@ class ReluBwdC(ctypes.Structure):
                 ("gb_self", c_p)]
 
 
+ADAM_MAX_GROUPS = 8
+
+
+class AdamGroupsC(ctypes.Structure):
+    _fields_ = [("n_groups", ctypes.c_int32), ("end", ctypes.c_int64 * ADAM_MAX_GROUPS),
+                ("step_size", ctypes.c_float * ADAM_MAX_GROUPS), ("beta1", ctypes.c_float * ADAM_MAX_GROUPS),
+                ("beta2", ctypes.c_float * ADAM_MAX_GROUPS), ("eps", ctypes.c_float * ADAM_MAX_GROUPS),
+                ("bias2_sqrt", ctypes.c_float * ADAM_MAX_GROUPS), ("weight_decay", ctypes.c_float * ADAM_MAX_GROUPS)]
+
+
 # name -> argtypes (restype is int for all but the two string getters)
 _SIGS = {
     "rsdf_ray_aabb_intersect": [c_p, c_p, c_p, c_i, c_p, c_p, c_p],
@@ -91,6 +101,7 @@ _SIGS = {
     "rsdf_absmax2": [c_p, ctypes.c_longlong, c_p, ctypes.c_longlong, c_p, c_i, c_p],
     "rsdf_relu_layer_fwd": [c_p, c_p],
     "rsdf_relu_layer_bwd": [c_p, c_p],
+    "rsdf_adam_step": [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_p, c_i, c_p],
     "rsdf_tc_gemm_test": [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 

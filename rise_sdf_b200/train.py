@@ -8,6 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from .optim import FlatAdam
+
 
 def binary_cross_entropy(inp, target):
     """systems/criterions.py:155-159."""
@@ -108,16 +110,22 @@ def split_loss(model, out, rgb, fg_mask, has_mask=True, **overrides):
 
 class FlatGradBucket:
     """All parameters' gradients as views into one contiguous fp32 buffer, so the data-parallel
-    exchange is a single NCCL all-reduce instead of DDP's 25 MB buckets."""
+    exchange is a single NCCL all-reduce instead of DDP's 25 MB buckets.  Every
+    parameter's slice starts on a 256-byte boundary (`ALIGN` elements; the padding stays zero), which
+    keeps the vectorised kernels' alignment assumptions when `optim.FlatAdam` lays the parameters out
+    the same way."""
+
+    ALIGN = 64
 
     def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
-        off = 0
+        self.params = [p for p in params if p.requires_grad and p.numel() > 0]
+        self.offsets, n = [], 0
         for p in self.params:
+            self.offsets.append(n)
+            n += -(-p.numel() // self.ALIGN) * self.ALIGN
+        self.flat = torch.zeros(n, device=self.params[0].device, dtype=torch.float32)
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
     def zero(self):
         self.flat.zero_()
@@ -136,8 +144,8 @@ class NeusTrainer:
             {"params": [p for p in model.texture.parameters() if p.numel() > 0], "lr": lr},
             {"params": list(model.variance.parameters()), "lr": lr_variance},
         ]
-        self.bucket = FlatGradBucket([p for g in groups for p in g["params"]])
-        self.opt = torch.optim.Adam(groups, lr=lr, betas=(0.9, 0.99), eps=1e-15)
+        self.opt = FlatAdam(groups, lr=lr, betas=(0.9, 0.99), eps=1e-15)
+        self.bucket = self.opt.bucket
         self.global_step = 0
 
     def step(self, rays, rgb, fg_mask, background, optimize=True):
@@ -167,8 +175,8 @@ class SplitTrainer:
             {"params": list(model.variance.parameters()), "lr": lr_variance},
             {"params": list(model.emitter.parameters()), "lr": lr_emitter},
         ]
-        self.bucket = FlatGradBucket([p for g in groups for p in g["params"]])
-        self.opt = torch.optim.Adam(groups, lr=lr, betas=(0.9, 0.999), eps=1e-12)
+        self.opt = FlatAdam(groups, lr=lr, betas=(0.9, 0.999), eps=1e-12)
+        self.bucket = self.opt.bucket
         self.global_step = 0
 
     def step(self, rays, rgb, fg_mask, background, optimize=True):
