@@ -90,9 +90,11 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
                  early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
                  near_plane: Optional[float] = None, far_plane: Optional[float] = None,
                  render_step_size: float = 1e-3, stratified: bool = False, cone_angle: float = 0.0,
-                 _return_packed: bool = False):
+                 _return_packed: bool = False, _return_mask: bool = False):
     """lib/nerfacc/ray_marching.py:14-222 (vendored nerfacc 0.3.5 signature).
-    Returns ray_indices int64[S], t_starts [S,1], t_ends [S,1]."""
+    Returns ray_indices int64[S], t_starts [S,1], t_ends [S,1].  `_return_mask` (ours) appends the visibility
+    mask over the marched candidates (None without sigma_fn / alpha_fn), so a caller can reuse what its
+    alpha_fn computed for the surviving samples."""
     L.require_cuda(rays_o, rays_d)
     if alpha_fn is not None and sigma_fn is not None:
         raise ValueError("Only one of `alpha_fn` and `sigma_fn` should be provided.")
@@ -120,6 +122,7 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
     packed, ri, ts, te = _march(rays_o, rays_d, t_min.contiguous(), t_max.contiguous(), roi_host,
                                 gbin.contiguous(), gbits, render_step_size, cone_angle)
     ts, te = ts[:, None], te[:, None]
+    masks = None
     if sigma_fn is not None or alpha_fn is not None:
         if sigma_fn is not None:
             sigmas = sigma_fn(ts, te, ri)
@@ -132,9 +135,8 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
                                   alpha_thre=alpha_thre)
         ri, ts, te = ri[masks], ts[masks], te[masks]
         packed = None
-    if _return_packed:
-        return ri, ts, te, packed
-    return ri, ts, te
+    rv = (ri, ts, te) + ((packed,) if _return_packed else ()) + ((masks,) if _return_mask else ())
+    return rv
 
 
 @torch.no_grad()
@@ -317,8 +319,10 @@ class OccGridEstimator(nn.Module):
                  alpha_fn: Optional[Callable] = None, near_plane: float = 0.0, far_plane: float = 1e10,
                  t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
                  render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
-                 stratified: bool = False, cone_angle: float = 0.0, _return_packed: bool = False):
-        """-> (ray_indices int64[S], t_starts[S], t_ends[S]) sorted by ray then t."""
+                 stratified: bool = False, cone_angle: float = 0.0, _return_packed: bool = False,
+                 _return_mask: bool = False):
+        """-> (ray_indices int64[S], t_starts[S], t_ends[S]) sorted by ray then t (+ packed_info / the
+        visibility mask over the marched candidates when asked for)."""
         def wrap(fn):
             if fn is None:
                 return None
@@ -327,11 +331,9 @@ class OccGridEstimator(nn.Module):
                            sigma_fn=wrap(sigma_fn), alpha_fn=wrap(alpha_fn), early_stop_eps=early_stop_eps,
                            alpha_thre=min(alpha_thre, float(self.occs.mean())) if alpha_thre > 0 else 0.0,
                            near_plane=near_plane, far_plane=far_plane, render_step_size=render_step_size,
-                           stratified=stratified, cone_angle=cone_angle, _return_packed=True)
-        ri, ts, te, packed = out
-        if _return_packed:
-            return ri, ts[:, 0], te[:, 0], packed
-        return ri, ts[:, 0], te[:, 0]
+                           stratified=stratified, cone_angle=cone_angle, _return_packed=True, _return_mask=True)
+        ri, ts, te, packed, masks = out
+        return (ri, ts[:, 0], te[:, 0]) + ((packed,) if _return_packed else ()) + ((masks,) if _return_mask else ())
 
     @torch.no_grad()
     def _update(self, step: int, occ_eval_fn: Callable, occ_thre: float = 0.01, ema_decay: float = 0.95,

@@ -43,21 +43,40 @@ def balanced_tile(n_rays, world, max_tile=32768, per_rank=4):
 
 
 @torch.no_grad()
-def render_frame_shard(model, rays, envs, rank=0, world=1, tile=None, keys=("comp_rgb_phys_full",)):
+def render_frame_shard(model, rays, envs, rank=0, world=1, tile=None, keys=("comp_rgb_phys_full",),
+                       share_across_envs=True):
     """Render this rank's tiles of one frame under every env map.  rays: [H*W, 6] on the device.
-    Returns {env_index: {key: [n_my_rays, C]}} plus the tile list."""
+    Returns {env_index: {key: [n_my_rays, C]}} plus the tile list.
+
+    share_across_envs: a tile is rendered under all maps back to back with a tile cache installed on the model
+    (`SplitMixedOCCModel._memo`): sampling, field evaluations, material networks and the secondary bounce run once
+    per tile, only the emitter lookups, compositing and the third-bounce shading run per map.  The frames are
+    bit-identical to rendering every map from scratch (share_across_envs=False, the reference's loop order)."""
     if tile is None:
         tile = balanced_tile(rays.shape[0], world)
     tiles = my_tiles(rays.shape[0], tile, rank, world)
-    out = {}
-    for e in range(len(envs.maps)):
-        envs.use(e)
-        parts = {k: [] for k in keys}
-        for a, b in tiles:
-            o = model.forward_(rays[a:b], relighting=True)
-            for k in keys:
-                parts[k].append(o[k])
-        out[e] = {k: torch.cat(v) if v else torch.zeros(0, 3, device=rays.device) for k, v in parts.items()}
+    n_env = len(envs.maps)
+    parts = {e: {k: [] for k in keys} for e in range(n_env)}
+    try:
+        if share_across_envs:
+            for a, b in tiles:
+                model._tile_cache = {}
+                for e in range(n_env):
+                    envs.use(e)
+                    o = model.forward_(rays[a:b], relighting=True)
+                    for k in keys:
+                        parts[e][k].append(o[k])
+        else:
+            for e in range(n_env):
+                envs.use(e)
+                for a, b in tiles:
+                    o = model.forward_(rays[a:b], relighting=True)
+                    for k in keys:
+                        parts[e][k].append(o[k])
+    finally:
+        model._tile_cache = None
+    out = {e: {k: torch.cat(v) if v else torch.zeros(0, 3, device=rays.device) for k, v in parts[e].items()}
+           for e in range(n_env)}
     return out, tiles
 
 

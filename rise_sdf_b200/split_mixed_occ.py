@@ -115,29 +115,62 @@ class SplitMixedOCCModel(nn.Module):
         c = prev_cdf
         return ((p + 1e-5) / (c + 1e-5)).view(-1).clip(0.0, 1.0)
 
-    def _alpha_fn(self, rays_o, rays_d):
+    reuse_sampling_pass = True       # no-grad passes only; results are bit-identical either way (test)
+    _tile_cache = None               # relight.render_frame_shard: one dict per tile, shared by its env maps
+
+    def _memo(self, key, fn):
+        """Relighting renders the same rays under several environment maps (systems/split_occ.py:331-458 runs the
+        whole test loop once per map).  Everything up to the emitter lookups -- sampling, field evaluations,
+        material networks, the secondary bounce -- does not depend on the map, so with a tile cache installed it
+        is computed for the first map and reused for the others (no-grad only; bit-identical, see the test)."""
+        c = self._tile_cache
+        if c is None or torch.is_grad_enabled():
+            return fn()
+        if key not in c:
+            c[key] = fn()
+        return c[key]
+
+
+    def _alpha_fn(self, rays_o, rays_d, keep=None):
+        """`alpha_fn` of models/split_mixed_occ.py:197-208.  With `keep` (a dict) the per-candidate results of the
+        visibility pass are parked in it: the reference evaluates the field a second time on the samples that
+        survive `sampling` (:228-240 / compute_indirect_radiance :183-191), which for a no-grad pass recomputes
+        exactly the same numbers -- the caller gathers them with the visibility mask instead."""
         def alpha_fn(t_starts, t_ends, ray_indices):
             t_origins = rays_o[ray_indices]
             t_dirs = rays_d[ray_indices]
             positions = t_origins + t_dirs * (t_starts + t_ends)[..., None] / 2.0
             if t_origins.shape[0] == 0:
                 return torch.zeros((0,), device=t_origins.device)
-            sdf, sdf_grad = self.geometry(positions, with_grad=True, with_feature=False)
+            if keep is not None and keep.get("feature", False) is None:
+                sdf, sdf_grad, keep["feature"] = self.geometry(positions, with_grad=True, with_feature=True)
+            else:
+                sdf, sdf_grad = self.geometry(positions, with_grad=True, with_feature=False)
             normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
             dists = (t_ends - t_starts)[..., None]
-            return self.get_alpha(sdf, normal, t_dirs, dists)
+            alphas = self.get_alpha(sdf, normal, t_dirs, dists)
+            if keep is not None:
+                keep.update(sdf=sdf, sdf_grad=sdf_grad, normal=normal, alphas=alphas, n=t_starts.shape[0])
+            return alphas
         return alpha_fn
 
     def compute_indirect_radiance(self, rays_o, rays_d):
         n_rays = rays_o.shape[0]
-        alpha_fn = self._alpha_fn(rays_o, rays_d)
+        keep = {} if self.reuse_sampling_pass else None
+        alpha_fn = self._alpha_fn(rays_o, rays_d, keep)
         with torch.no_grad():
             step = (self.secondary_far_plane - self.secondary_near_plane) / (self.num_samples_per_secondary_ray - 1)
-            ray_indices, t_starts, t_ends = self.occupancy_grid.sampling(
+            ray_indices, t_starts, t_ends, mask = self.occupancy_grid.sampling(
                 rays_o, rays_d, alpha_fn=alpha_fn, near_plane=self.secondary_near_plane,
-                far_plane=self.secondary_far_plane, render_step_size=step, stratified=False)
+                far_plane=self.secondary_far_plane, render_step_size=step, stratified=False, _return_mask=True)
+            if keep and mask is not None and keep.get("n") == mask.shape[0]:
+                cached = keep["alphas"][mask]
+                alpha_fn = lambda ts, te, ri: cached          # the survivors' alphas, as computed a moment ago
+                chunk = None
+            else:
+                chunk = self.secondary_shader_chunk
             acc_map, depth_map, _ = secondary_rendering(t_starts, t_ends, ray_indices=ray_indices, n_rays=n_rays,
-                                                        alpha_fn=alpha_fn, chunk_size=self.secondary_shader_chunk)
+                                                        alpha_fn=alpha_fn, chunk_size=chunk)
         return 1.0 - acc_map, depth_map
 
     # ------------------------------------------------------------------ render
@@ -145,7 +178,9 @@ class SplitMixedOCCModel(nn.Module):
         n_rays = rays.shape[0]
         rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
         fd_train = self.config.geometry.grad_type == "finite_difference" and self.training
-        alpha_fn = self._alpha_fn(rays_o, rays_d)
+        # no-grad render (eval / relighting): the shading pass reuses the visibility pass's field evaluation
+        keep = {"feature": None} if (self.reuse_sampling_pass and not torch.is_grad_enabled()) else None
+        alpha_fn = self._alpha_fn(rays_o, rays_d, keep)
 
         def rgb_normal_alpha_fn(t_starts, t_ends, ray_indices):
             t_origins = rays_o[ray_indices]
@@ -154,19 +189,34 @@ class SplitMixedOCCModel(nn.Module):
             if fd_train:
                 sdf, sdf_grad, feature, sdf_laplace = self.geometry(positions, with_grad=True, with_feature=True,
                                                                     with_laplace=True)
-            else:
-                sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
-            normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
-            dists = (t_ends - t_starts)[..., None]
-            alphas = self.get_alpha(sdf, normal, t_dirs, dists)
-            colors = self.texture(feature, t_dirs, normal, positions, self.emitter, self.stage)
-            if fd_train:
+                normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
+                alphas = self.get_alpha(sdf, normal, t_dirs, (t_ends - t_starts)[..., None])
+                colors = self.texture(feature, t_dirs, normal, positions, self.emitter, self.stage)
                 return colors, normal, alphas, sdf, sdf_grad, sdf_laplace
+
+            def fields():
+                if survivors:                      # gathered from the visibility pass instead of re-evaluated
+                    got = tuple(keep[k][survivors[0]] for k in ("sdf", "sdf_grad", "feature", "normal", "alphas"))
+                    keep.clear()
+                    return got
+                sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
+                normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
+                return sdf, sdf_grad, feature, normal, self.get_alpha(sdf, normal, t_dirs, (t_ends - t_starts)[..., None])
+
+            sdf, sdf_grad, feature, normal, alphas = self._memo("fields", fields)
+            mat = self._memo("material", lambda: self.texture.material(feature, t_dirs, normal, positions, self.stage))
+            colors = self.texture.shade(mat, normal, self.emitter, self.stage)
             return colors, normal, alphas, sdf, sdf_grad
 
-        ray_indices, t_starts, t_ends = self.occupancy_grid.sampling(
-            rays_o, rays_d, alpha_fn=alpha_fn, render_step_size=self.render_step_size,
-            stratified=self.randomized, cone_angle=0.0, alpha_thre=0.0)
+        def sample():
+            r = self.occupancy_grid.sampling(
+                rays_o, rays_d, alpha_fn=alpha_fn, render_step_size=self.render_step_size,
+                stratified=self.randomized, cone_angle=0.0, alpha_thre=0.0, _return_mask=True)
+            ok = (keep is not None and r[3] is not None and keep.get("n") == r[3].shape[0]
+                  and keep["feature"] is not None)
+            return r[:3], ([r[3]] if ok else []), keep
+
+        (ray_indices, t_starts, t_ends), survivors, keep = self._memo("sampling", sample)
         rgb_map, normal_map, acc_map, depth_map, extras = rendering_with_normals_sdf(
             t_starts, t_ends, ray_indices=ray_indices, n_rays=n_rays, rgb_alpha_fn=rgb_normal_alpha_fn,
             render_bkgd=None, has_laplace=fd_train, color_dim=7 if self.stage == 0 else 24)
@@ -184,12 +234,15 @@ class SplitMixedOCCModel(nn.Module):
             wo = -rays_d[valid_indices]
             nm = normal_map[valid_indices]
             secondary_rays_d = 2 * torch.sum(wo * nm, dim=-1, keepdim=True) * nm - wo
-            tr, secondary_depth = self.compute_indirect_radiance(secondary_rays_o.detach().contiguous(),
-                                                                 secondary_rays_d.detach().contiguous())
+            tr, secondary_depth = self._memo("indirect", lambda: self.compute_indirect_radiance(
+                secondary_rays_o.detach().contiguous(), secondary_rays_d.detach().contiguous()))
             tr = tr.clamp(0, 1).detach()
             secondary_depth = secondary_depth.detach()
-            _, secondary_feature = self.geometry(secondary_rays_o, with_grad=False, with_feature=True)
-            secondary_rgb = self.texture.secondary_shading(secondary_feature, secondary_rays_d, nm)
+
+            def secondary():
+                _, secondary_feature = self.geometry(secondary_rays_o, with_grad=False, with_feature=True)
+                return self.texture.secondary_shading(secondary_feature, secondary_rays_d, nm)
+            secondary_rgb = self._memo("secondary_rgb", secondary)
             spec_rgb_map[valid_indices] = tr * spec_rgb_map[valid_indices] + (1 - tr) * secondary_rgb
             if self.stage != 0:
                 if not relighting:
@@ -197,10 +250,18 @@ class SplitMixedOCCModel(nn.Module):
                 else:
                     roughness_mask = (roughness_map[valid_indices] <= self.config.relighting_threshold)[..., 0]
                     third_rays_o = secondary_rays_o[roughness_mask] + secondary_depth[roughness_mask] * secondary_rays_d[roughness_mask]
-                    _, third_grad, third_feature = self.geometry(third_rays_o, with_grad=True, with_feature=True)
-                    third_normal = F.normalize(third_grad, p=2, dim=-1, eps=1e-6)
-                    third_rgb = self.texture.secondary_shading_pbr(third_feature, secondary_rays_d[roughness_mask],
-                                                                   third_normal, third_rays_o, self.emitter)
+                    third_dirs = secondary_rays_d[roughness_mask]
+
+                    def third():
+                        _, third_grad, third_feature = self.geometry(third_rays_o, with_grad=True, with_feature=True)
+                        third_normal = F.normalize(third_grad, p=2, dim=-1, eps=1e-6)
+                        if third_dirs.shape[0] == 0:
+                            return third_normal, None
+                        return third_normal, self.texture.secondary_material_pbr(third_feature, third_dirs,
+                                                                                 third_normal, third_rays_o)
+                    third_normal, third_mat = self._memo("third", third)
+                    third_rgb = (torch.zeros((0, 3), device=third_dirs.device) if third_mat is None else
+                                 self.texture.secondary_shade_pbr(third_mat, third_dirs, third_normal, self.emitter))
                     slv = spec_light_map[valid_indices]
                     slv[roughness_mask] = tr[roughness_mask] * slv[roughness_mask] + (1 - tr[roughness_mask]) * third_rgb
                     spec_light_map[valid_indices] = slv

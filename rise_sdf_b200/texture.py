@@ -78,9 +78,10 @@ class VolumeMixedMipSplitOcc(nn.Module):
         return dr.texture(self.FG_LUT, fg_uv.reshape(1, pn, 1, 2).contiguous(), filter_mode="linear",
                           boundary_mode="clamp").reshape(pn, 2)
 
-    def forward(self, features, dirs, normals, positions, emitter, stage=0, *args):
-        if dirs.shape[0] == 0:
-            return torch.zeros((0, 3), device=dirs.device)
+    def material(self, features, dirs, normals, positions, stage=0):
+        """The light-independent half of `forward` (models/texture.py:330-377 up to the emitter lookups): material
+        networks, activations, reflection direction, FG lookup.  A relighting render under several environment
+        maps evaluates it once per tile (`SplitMixedOCCModel._memo`)."""
         wi = -dirs
         wo = torch.sum(wi * normals, -1, keepdim=True) * normals * 2 - wi
         NoV = torch.sum(normals * wi, -1, keepdim=True)
@@ -97,18 +98,30 @@ class VolumeMixedMipSplitOcc(nn.Module):
         metallic, roughness, spec_rgb = self._act(metallic), self._act(roughness), self._act(spec_rgb)
         spec_rgb = blend * spec_rgb
         diff_rgb = (1 - blend) * diff_rgb
+        m = {"diff_rgb": diff_rgb, "spec_rgb": spec_rgb, "blend": blend}
+        if stage != 0:
+            diffuse_albedo = (1 - metallic) * albedo
+            specular_albedo = 0.04 * (1 - metallic) + metallic * albedo
+            fg_lookup = self._fg(NoV, roughness)
+            m.update(wo=wo, albedo=albedo, metallic=metallic, roughness=roughness, diffuse_albedo=diffuse_albedo,
+                     specular_ref=specular_albedo * fg_lookup[:, 0:1] + fg_lookup[:, 1:2])
+        return m
+
+    def shade(self, m, normals, emitter, stage=0):
+        """The emitter-dependent half of `forward`: split-sum lighting lookups + channel packing."""
         if stage == 0:
-            return torch.cat([diff_rgb, spec_rgb, blend], dim=-1)
-        diffuse_albedo = (1 - metallic) * albedo
+            return torch.cat([m["diff_rgb"], m["spec_rgb"], m["blend"]], dim=-1)
         diffuse_light = emitter.eval_mip(normals)
-        diff_rgb_pbr = diffuse_albedo * diffuse_light
-        specular_albedo = 0.04 * (1 - metallic) + metallic * albedo
-        specular_light = emitter.eval_mip(wo, specular=True, roughness=roughness)
-        fg_lookup = self._fg(NoV, roughness)
-        specular_ref = specular_albedo * fg_lookup[:, 0:1] + fg_lookup[:, 1:2]
-        spec_rgb_pbr = specular_ref * specular_light
-        return torch.cat([diff_rgb, spec_rgb, blend, diff_rgb_pbr, spec_rgb_pbr, specular_ref, specular_light,
-                          albedo, metallic, roughness], dim=-1)
+        diff_rgb_pbr = m["diffuse_albedo"] * diffuse_light
+        specular_light = emitter.eval_mip(m["wo"], specular=True, roughness=m["roughness"])
+        spec_rgb_pbr = m["specular_ref"] * specular_light
+        return torch.cat([m["diff_rgb"], m["spec_rgb"], m["blend"], diff_rgb_pbr, spec_rgb_pbr, m["specular_ref"],
+                          specular_light, m["albedo"], m["metallic"], m["roughness"]], dim=-1)
+
+    def forward(self, features, dirs, normals, positions, emitter, stage=0, *args):
+        if dirs.shape[0] == 0:
+            return torch.zeros((0, 3), device=dirs.device)
+        return self.shade(self.material(features, dirs, normals, positions, stage), normals, emitter, stage)
 
     def secondary_shading(self, features, rays_d, *args):
         rays_d = (rays_d + 1.0) / 2.0
@@ -118,9 +131,8 @@ class VolumeMixedMipSplitOcc(nn.Module):
         color = self.secondary_network(network_inp).view(*network_inp.shape[:-1], self.n_output_dims).float()
         return self._act(color)
 
-    def secondary_shading_pbr(self, features, dirs, normals, positions, emitter):
-        if dirs.shape[0] == 0:
-            return torch.zeros((0, 3), device=dirs.device)
+    def secondary_material_pbr(self, features, dirs, normals, positions):
+        """Light-independent half of `secondary_shading_pbr` (models/texture.py:404-434)."""
         wi = -dirs
         NoV = torch.sum(normals * wi, -1, keepdim=True)
         xyz_embd = self.xyz_encoding(positions.view(-1, self.n_pos_dims))
@@ -130,12 +142,21 @@ class VolumeMixedMipSplitOcc(nn.Module):
         metallic = self.metallic_network(network_inp).view(*features.shape[:-1], 2).float()[..., 1:]
         albedo, metallic, roughness = self._act(albedo), self._act(metallic), self._act(roughness)
         diffuse_albedo = (1 - metallic) * albedo
-        diff_rgb_pbr = diffuse_albedo * emitter.eval_mip(normals)
         specular_albedo = 0.04 * (1 - metallic) + metallic * albedo
-        specular_light = emitter.eval_mip(dirs, specular=True, roughness=roughness)
         fg_lookup = self._fg(NoV, roughness)
-        specular_ref = specular_albedo * fg_lookup[:, 0:1] + fg_lookup[:, 1:2]
-        return diff_rgb_pbr + specular_ref * specular_light
+        return {"diffuse_albedo": diffuse_albedo, "roughness": roughness,
+                "specular_ref": specular_albedo * fg_lookup[:, 0:1] + fg_lookup[:, 1:2]}
+
+    def secondary_shade_pbr(self, m, dirs, normals, emitter):
+        diff_rgb_pbr = m["diffuse_albedo"] * emitter.eval_mip(normals)
+        specular_light = emitter.eval_mip(dirs, specular=True, roughness=m["roughness"])
+        return diff_rgb_pbr + m["specular_ref"] * specular_light
+
+    def secondary_shading_pbr(self, features, dirs, normals, positions, emitter):
+        if dirs.shape[0] == 0:
+            return torch.zeros((0, 3), device=dirs.device)
+        return self.secondary_shade_pbr(self.secondary_material_pbr(features, dirs, normals, positions), dirs, normals,
+                                        emitter)
 
     def update_step(self, epoch, global_step):
         update_module_step(self.dir_encoding, epoch, global_step)

@@ -221,3 +221,42 @@ def test_split_sum_training_step_runs_and_reaches_every_parameter_group():
                  "texture.secondary_network.layers.0.weight", "geometry.network.layers.0.weight_v"):
         g = dict(m.named_parameters())[name].grad
         assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, name
+
+
+def test_relighting_reuse_is_bit_identical():
+    """configs[3]: (a) a no-grad render gathers the surviving samples' field values from the visibility pass
+    instead of evaluating the field again, (b) a tile rendered under several env maps computes everything that
+    does not depend on the map once.  Both must reproduce the evaluate-everything-again order of the reference
+    (models/split_mixed_occ.py:197-240, systems/split_occ.py:331-458) bit for bit."""
+    from rise_sdf_b200 import synthetic as syn
+    from rise_sdf_b200.relight import EnvSet, render_frame_shard
+    m = _split_model().eval()
+    m.update_step(0, 20000)
+    m.background_color = torch.ones(3, device="cuda")
+    m.occupancy_grid.binaries = syn.analytic_grid("ball")[None].cuda()
+    m.render_step_size = 1.732 * 2 * 1.5 / 256
+    g = torch.Generator().manual_seed(5)
+    envs = EnvSet(m, [torch.rand(32, 64, 3, generator=g) * 2.0, torch.rand(32, 64, 3, generator=g) ** 4 * 20.0])
+    rays = syn.training_rays(600, seed=9)[0].cuda()
+    keys = ("comp_rgb_phys_full", "comp_rgb_full", "comp_normal", "opacity", "depth", "comp_spec_rgb_phys",
+            "comp_roughness")
+    m.reuse_sampling_pass = False
+    base, tiles = render_frame_shard(m, rays, envs, tile=256, keys=keys, share_across_envs=False)
+    assert len(tiles) == 3
+    assert not torch.equal(base[0]["comp_rgb_phys_full"], base[1]["comp_rgb_phys_full"])    # the maps do differ
+    for reuse, share in ((True, False), (False, True), (True, True)):
+        m.reuse_sampling_pass = reuse
+        out, _ = render_frame_shard(m, rays, envs, tile=256, keys=keys, share_across_envs=share)
+        assert m._tile_cache is None
+        for e in base:
+            for k in keys:
+                assert torch.equal(out[e][k], base[e][k]), (reuse, share, e, k)
+    # the training-mode secondary bounce (no-grad inside a grad-enabled step) reuses its alphas the same way
+    m.train(); m.randomized = False
+    outs = []
+    for reuse in (False, True):
+        m.reuse_sampling_pass = reuse
+        torch.manual_seed(11)                     # the curvature probe draws random tangents
+        outs.append(m(rays[:200]))
+    for k in ("comp_rgb_full", "comp_rgb_phys_full", "opacity"):
+        assert torch.equal(outs[0][k], outs[1][k]), k
