@@ -167,10 +167,13 @@ int rsdf_sh_bwd(const float *u, const float *grad_out, int n_samples, int degree
                 void *stream);
 
 /* ---------------------------------------------------------------- K5: split-sum lookups + prefilter */
-/* nvdiffrast.torch.texture(tex[1,H,W,C], uv[1,S,1,2], filter_mode='linear', boundary_mode='clamp')
- * (models/texture.py:340: FG LUT).  C in {1,2,3}. */
-int rsdf_tex2d_fwd(const float *tex, int H, int W, int C, const float *uv, int n, float *out, void *stream);
-int rsdf_tex2d_bwd(const float *tex, int H, int W, int C, const float *uv, const float *grad_out, int n,
+/* nvdiffrast.torch.texture(tex[1,H,W,C], uv[1,S,1,2], filter_mode='linear', boundary_mode='clamp' | 'wrap'):
+ * wrap == 0 clamps the taps to the edge (models/texture.py:340, FG LUT); wrap != 0 reduces uv to [0,1) and
+ * wraps the taps around (nvdiffrast's default, the lat-long lookups of lib/pbr/utils/light_utils.py:126-139).
+ * C in {1,2,3}. */
+int rsdf_tex2d_fwd(const float *tex, int H, int W, int C, int wrap, const float *uv, int n, float *out,
+                   void *stream);
+int rsdf_tex2d_bwd(const float *tex, int H, int W, int C, int wrap, const float *uv, const float *grad_out, int n,
                    float *grad_tex /* atomic +=, may be NULL */, float *grad_uv /* may be NULL */, void *stream);
 /* nvdiffrast.torch.texture(..., boundary_mode='cube'), filter 'linear' (n_levels == 1 or bias NULL)
  * or 'linear-mipmap-linear' with an explicit mip stack and per-sample mip_level_bias

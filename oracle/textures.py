@@ -17,14 +17,21 @@ import torch
 # ------------------------------------------------------------------------------------ 2-D
 
 
-def tex2d(tex, uv):
-    """tex [H,W,C], uv [n,2] (u -> width, v -> height); bilinear, clamp-to-edge."""
+def tex2d(tex, uv, wrap=False):
+    """tex [H,W,C], uv [n,2] (u -> width, v -> height); bilinear, clamp-to-edge, or -- wrap=True, nvdiffrast's
+    default boundary mode -- uv reduced to [0,1) with the taps wrapping around both axes."""
     H, W, _ = tex.shape
+    if wrap:
+        uv = uv - torch.floor(uv.detach())
     tx, ty = uv[:, 0] * W - 0.5, uv[:, 1] * H - 0.5
     x0f, y0f = torch.floor(tx.detach()), torch.floor(ty.detach())
     ax, ay = (tx - x0f)[:, None], (ty - y0f)[:, None]
-    x0, x1 = x0f.long().clamp(0, W - 1), (x0f.long() + 1).clamp(0, W - 1)
-    y0, y1 = y0f.long().clamp(0, H - 1), (y0f.long() + 1).clamp(0, H - 1)
+    if wrap:
+        x0, x1 = x0f.long() % W, (x0f.long() + 1) % W
+        y0, y1 = y0f.long() % H, (y0f.long() + 1) % H
+    else:
+        x0, x1 = x0f.long().clamp(0, W - 1), (x0f.long() + 1).clamp(0, W - 1)
+        y0, y1 = y0f.long().clamp(0, H - 1), (y0f.long() + 1).clamp(0, H - 1)
     top = tex[y0, x0] * (1 - ax) + tex[y0, x1] * ax
     bot = tex[y1, x0] * (1 - ax) + tex[y1, x1] * ax
     return top * (1 - ay) + bot * ay

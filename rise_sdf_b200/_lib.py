@@ -82,8 +82,8 @@ _SIGS = {
     "rsdf_hashgrid_jvp": [c_p, c_p, c_i, c_i, c_p, c_p],
     "rsdf_sh_fwd": [c_p, c_i, c_i, c_p, c_p],
     "rsdf_sh_bwd": [c_p, c_p, c_i, c_i, c_p, c_p],
-    "rsdf_tex2d_fwd": [c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p],
-    "rsdf_tex2d_bwd": [c_p, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_tex2d_fwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p],
+    "rsdf_tex2d_bwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p],
     "rsdf_cube_sample_fwd": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p],
     "rsdf_cube_sample_bwd": [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p],
     "rsdf_cubemap_texel_table": [c_i, c_p, c_p],

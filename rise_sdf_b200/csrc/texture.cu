@@ -200,17 +200,33 @@ __global__ void cube_sample_bwd_kernel(const MipStack m, const float *__restrict
     }
 }
 
-// 2-D, linear, clamp.  tex [H, W, C]; uv [n, 2] with uv.x -> width, uv.y -> height
+// 2-D, linear, clamp or wrap.  tex [H, W, C]; uv [n, 2] with uv.x -> width, uv.y -> height.
+// wrap (nvdiffrast's default boundary mode, the one the lat-long -> cube conversion uses): the coordinate is
+// reduced to [0,1) and a tap that falls off one edge comes back in at the opposite one.
+__device__ __forceinline__ void tex2d_taps(float u, int N, bool wrap, int &i0, int &i1, float &a) {
+    if (wrap) u -= floorf(u);
+    const float t = u * (float)N - 0.5f;
+    const float f0 = floorf(t);
+    a = t - f0;
+    i0 = (int)f0;
+    i1 = i0 + 1;
+    if (wrap) {
+        if (i0 < 0) i0 += N;
+        if (i1 >= N) i1 -= N;
+    }
+    i0 = min(max(i0, 0), N - 1);
+    i1 = min(max(i1, 0), N - 1);
+}
+
 template <int C>
-__global__ void tex2d_fwd_kernel(const float *__restrict__ tex, int H, int W, const float *__restrict__ uv,
-                                 int n, float *__restrict__ out) {
+__global__ void tex2d_fwd_kernel(const float *__restrict__ tex, int H, int W, bool wrap,
+                                 const float *__restrict__ uv, int n, float *__restrict__ out) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const float tx = uv[2 * s] * (float)W - 0.5f, ty = uv[2 * s + 1] * (float)H - 0.5f;
-    const float fx0 = floorf(tx), fy0 = floorf(ty);
-    const float ax = tx - fx0, ay = ty - fy0;
-    const int x0 = min(max((int)fx0, 0), W - 1), x1 = min(max((int)fx0 + 1, 0), W - 1);
-    const int y0 = min(max((int)fy0, 0), H - 1), y1 = min(max((int)fy0 + 1, 0), H - 1);
+    int x0, x1, y0, y1;
+    float ax, ay;
+    tex2d_taps(uv[2 * s], W, wrap, x0, x1, ax);
+    tex2d_taps(uv[2 * s + 1], H, wrap, y0, y1, ay);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const float v00 = __ldg(tex + ((size_t)y0 * W + x0) * C + c), v10 = __ldg(tex + ((size_t)y0 * W + x1) * C + c);
@@ -221,16 +237,15 @@ __global__ void tex2d_fwd_kernel(const float *__restrict__ tex, int H, int W, co
 }
 
 template <int C>
-__global__ void tex2d_bwd_kernel(const float *__restrict__ tex, int H, int W, const float *__restrict__ uv,
-                                 const float *__restrict__ go, int n, float *__restrict__ g_tex,
+__global__ void tex2d_bwd_kernel(const float *__restrict__ tex, int H, int W, bool wrap,
+                                 const float *__restrict__ uv, const float *__restrict__ go, int n, float *__restrict__ g_tex,
                                  float *__restrict__ g_uv) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const float tx = uv[2 * s] * (float)W - 0.5f, ty = uv[2 * s + 1] * (float)H - 0.5f;
-    const float fx0 = floorf(tx), fy0 = floorf(ty);
-    const float ax = tx - fx0, ay = ty - fy0;
-    const int x0 = min(max((int)fx0, 0), W - 1), x1 = min(max((int)fx0 + 1, 0), W - 1);
-    const int y0 = min(max((int)fy0, 0), H - 1), y1 = min(max((int)fy0 + 1, 0), H - 1);
+    int x0, x1, y0, y1;
+    float ax, ay;
+    tex2d_taps(uv[2 * s], W, wrap, x0, x1, ax);
+    tex2d_taps(uv[2 * s + 1], H, wrap, y0, y1, ay);
     float gu = 0.f, gv = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -253,28 +268,29 @@ __global__ void tex2d_bwd_kernel(const float *__restrict__ tex, int H, int W, co
 
 extern "C" {
 
-int rsdf_tex2d_fwd(const float *tex, int H, int W, int C, const float *uv, int n, float *out, void *stream) {
+int rsdf_tex2d_fwd(const float *tex, int H, int W, int C, int wrap, const float *uv, int n, float *out,
+                   void *stream) {
     if (n == 0) return 0;
     if (!tex || !uv || !out) return RSDF_EBADARG;
     const int blocks = rsdf_div_up(n, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 2) tex2d_fwd_kernel<2><<<blocks, 256, 0, st>>>(tex, H, W, uv, n, out);
-    else if (C == 3) tex2d_fwd_kernel<3><<<blocks, 256, 0, st>>>(tex, H, W, uv, n, out);
-    else if (C == 1) tex2d_fwd_kernel<1><<<blocks, 256, 0, st>>>(tex, H, W, uv, n, out);
+    if (C == 2) tex2d_fwd_kernel<2><<<blocks, 256, 0, st>>>(tex, H, W, wrap != 0, uv, n, out);
+    else if (C == 3) tex2d_fwd_kernel<3><<<blocks, 256, 0, st>>>(tex, H, W, wrap != 0, uv, n, out);
+    else if (C == 1) tex2d_fwd_kernel<1><<<blocks, 256, 0, st>>>(tex, H, W, wrap != 0, uv, n, out);
     else return RSDF_EBADARG;
     RSDF_LAUNCH_CHECK();
     return 0;
 }
 
-int rsdf_tex2d_bwd(const float *tex, int H, int W, int C, const float *uv, const float *grad_out, int n,
+int rsdf_tex2d_bwd(const float *tex, int H, int W, int C, int wrap, const float *uv, const float *grad_out, int n,
                    float *grad_tex, float *grad_uv, void *stream) {
     if (n == 0) return 0;
     if (!tex || !uv || !grad_out) return RSDF_EBADARG;
     const int blocks = rsdf_div_up(n, 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (C == 2) tex2d_bwd_kernel<2><<<blocks, 256, 0, st>>>(tex, H, W, uv, grad_out, n, grad_tex, grad_uv);
-    else if (C == 3) tex2d_bwd_kernel<3><<<blocks, 256, 0, st>>>(tex, H, W, uv, grad_out, n, grad_tex, grad_uv);
-    else if (C == 1) tex2d_bwd_kernel<1><<<blocks, 256, 0, st>>>(tex, H, W, uv, grad_out, n, grad_tex, grad_uv);
+    if (C == 2) tex2d_bwd_kernel<2><<<blocks, 256, 0, st>>>(tex, H, W, wrap != 0, uv, grad_out, n, grad_tex, grad_uv);
+    else if (C == 3) tex2d_bwd_kernel<3><<<blocks, 256, 0, st>>>(tex, H, W, wrap != 0, uv, grad_out, n, grad_tex, grad_uv);
+    else if (C == 1) tex2d_bwd_kernel<1><<<blocks, 256, 0, st>>>(tex, H, W, wrap != 0, uv, grad_out, n, grad_tex, grad_uv);
     else return RSDF_EBADARG;
     RSDF_LAUNCH_CHECK();
     return 0;

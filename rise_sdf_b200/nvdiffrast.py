@@ -1,8 +1,7 @@
 """Drop-in for `nvdiffrast.torch.texture` in the three modes RISE-SDF uses
 (lib/pbr/light.py:194-206, models/texture.py:340-341, lib/pbr/utils/light_utils.py:108,124,138):
 
-    tex[1,H,W,C],     uv[1,S,1,2] | [1,H',W',2], filter 'linear', boundary 'clamp' (default 'wrap' is
-                                                 accepted for latlong lookups and treated as clamp+wrap-u)
+    tex[1,H,W,C],     uv[1,S,1,2] | [1,H',W',2], filter 'linear', boundary 'clamp' | 'wrap' (the default; taps wrap around both axes)
     tex[1,6,N,N,3],   uv[1,S,1,3] | [1,H',W',3], filter 'linear', boundary 'cube'
     tex[1,6,N,N,3] + mip=[...] + mip_level_bias[1,S,1], filter 'linear-mipmap-linear', boundary 'cube'
 
@@ -30,12 +29,13 @@ def _int_array(vals):
 
 class _Tex2D(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tex, uv):
+    def forward(ctx, tex, uv, wrap=False):
         H, W, C = tex.shape
         n = uv.shape[0]
         out = torch.empty(n, C, device=uv.device, dtype=torch.float32)
-        L.call("rsdf_tex2d_fwd", L.ptr(tex), H, W, C, L.ptr(uv), n, L.ptr(out), L.stream())
+        L.call("rsdf_tex2d_fwd", L.ptr(tex), H, W, C, int(wrap), L.ptr(uv), n, L.ptr(out), L.stream())
         ctx.save_for_backward(tex, uv)
+        ctx.wrap = int(wrap)
         return out
 
     @staticmethod
@@ -47,9 +47,9 @@ class _Tex2D(torch.autograd.Function):
         g_tex = torch.zeros_like(tex) if ctx.needs_input_grad[0] else None
         g_uv = torch.empty_like(uv) if ctx.needs_input_grad[1] else None
         if g_tex is not None or g_uv is not None:
-            L.call("rsdf_tex2d_bwd", L.ptr(tex), H, W, C, L.ptr(uv), L.ptr(go.contiguous()), n, L.ptr(g_tex),
-                   L.ptr(g_uv), L.stream())
-        return g_tex, g_uv
+            L.call("rsdf_tex2d_bwd", L.ptr(tex), H, W, C, ctx.wrap, L.ptr(uv), L.ptr(go.contiguous()), n,
+                   L.ptr(g_tex), L.ptr(g_uv), L.stream())
+        return g_tex, g_uv, None
 
 
 class _CubeSample(torch.autograd.Function):
@@ -107,7 +107,5 @@ def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode="aut
         raise NotImplementedError(filter_mode)
     assert tex.dim() == 4 and tex.shape[0] == 1, tex.shape
     uv2 = uv.reshape(-1, 2).contiguous().float()
-    if boundary_mode == "wrap":
-        uv2 = uv2 - torch.floor(uv2)
-    out = _Tex2D.apply(tex[0].contiguous().float(), uv2)
+    out = _Tex2D.apply(tex[0].contiguous().float(), uv2, boundary_mode == "wrap")
     return out.view(*lead, tex.shape[-1])

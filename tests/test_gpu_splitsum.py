@@ -41,6 +41,29 @@ def test_tex2d_fwd_bwd():
     assert float((uc.grad.cpu() - u0.grad).abs()[interior].max()) <= 1e-3 * float(u0.grad.abs().max())
 
 
+def test_tex2d_wrap_fwd_bwd():
+    """boundary_mode='wrap' (nvdiffrast's default; the lat-long -> cube conversion,
+    lib/pbr/utils/light_utils.py:126-139): coordinates outside [0,1) and taps across the u = 0/1 seam."""
+    g = torch.Generator().manual_seed(2)
+    tex = torch.rand(1, 32, 64, 3, generator=g)
+    uv = torch.rand(4096, 2, generator=g) * 3.0 - 1.0
+    uv[:8] = torch.tensor([[0, 0], [1, 1], [0.999, 0.5], [0.001, 0.5], [0.5, 0.001], [0.5, 0.999], [-0.25, 1.75],
+                           [1 / 128, 1 / 64]])
+    tc, uc = tex.cuda().requires_grad_(True), uv.cuda().requires_grad_(True)
+    out = dr.texture(tc, uc.view(1, -1, 1, 2), filter_mode="linear").view(-1, 3)          # default boundary mode
+    t0, u0 = tex[0].double().requires_grad_(True), uv.double().requires_grad_(True)
+    ref = ot.tex2d(t0, u0, wrap=True)
+    clamp = ot.tex2d(tex[0].double(), uv.double() - torch.floor(uv.double()))
+    assert float((ref.detach() - clamp).abs().max()) > 0.05           # the seam taps really differ from clamping
+    frac = (uv * torch.tensor([64.0, 32.0]) - 0.5) - torch.floor(uv * torch.tensor([64.0, 32.0]) - 0.5)
+    interior = (frac - 0.5).abs().max(-1).values < 0.49               # fp32 uv next to a texel centre may pick the other cell
+    assert float((out.detach().cpu() - ref.detach()).abs()[interior].max()) <= 1e-5
+    go = torch.randn(4096, 3, generator=g) * interior[:, None]
+    (out * go.cuda()).sum().backward(); (ref * go.double()).sum().backward()
+    assert float((tc.grad[0].cpu() - t0.grad).abs().max()) <= 1e-4 * float(t0.grad.abs().max())
+    assert float((uc.grad.cpu() - u0.grad).abs()[interior].max()) <= 1e-3 * float(u0.grad.abs().max())
+
+
 @pytest.mark.parametrize("N", [16, 64])
 def test_cube_linear_fwd_bwd(N):
     g = torch.Generator().manual_seed(N)
