@@ -351,7 +351,8 @@ def run_ours(args):
     barrier()
     # ---- timed: resident inputs -----------------------------------------------------------
     timed = ["rsdf_hashgrid_fwd", "rsdf_hashgrid_bwd_table", "rsdf_hashgrid_bwd_input", "rsdf_hashgrid_bwd_bwd",
-             "rsdf_march_count", "rsdf_march_fill", "rsdf_neus_render_fwd", "rsdf_neus_render_bwd",
+             "rsdf_march_count", "rsdf_march_fill", "rsdf_march_count_keep", "rsdf_march_compact", "rsdf_adam_step",
+             "rsdf_neus_render_fwd", "rsdf_neus_render_bwd",
              "rsdf_sdf_mlp_fwd", "rsdf_sdf_mlp_bwd", "rsdf_relu_layer_fwd", "rsdf_relu_layer_bwd", "rsdf_absmax2",
              "rsdf_hashgrid_bwd_table2", "rsdf_hashgrid_jvp", "rsdf_sh_fwd", "rsdf_sh_bwd"]
     L.stats_reset(True, timed)

@@ -61,6 +61,19 @@ int rsdf_march_fill(const float *rays_o, const float *rays_d, const float *t_min
                     float cone_angle, int n_rays, const int32_t *packed_info,
                     int64_t *ray_indices, float *t_starts, float *t_ends, void *stream);
 
+/* One-march variant of the two rounds above: the count round also keeps the first `cap` intervals (t_start,
+ * t_end) of every ray in keep[n_rays, cap, 2], and the fill round becomes a copy into the packed layout
+ * (rsdf_march_compact, one warp per ray) instead of a second march.  total2[0] = S, total2[1] != 0 when some ray
+ * produced more than `cap` samples (the caller then falls back to rsdf_march_fill).  Same arithmetic, same
+ * bits as the two-round path. */
+int rsdf_march_count_keep(const float *rays_o, const float *rays_d, const float *t_min,
+                          const float *t_max, const float *roi_host6, const uint8_t *grid_binary,
+                          const uint32_t *grid_bits, int rx, int ry, int rz, float step_size,
+                          float cone_angle, int n_rays, int32_t *packed_info, int32_t *scan_tmp,
+                          int32_t *total2, float *keep, int cap, void *stream);
+int rsdf_march_compact(const int32_t *packed_info, const float *keep, int cap, int n_rays,
+                       int64_t *ray_indices, float *t_starts, float *t_ends, void *stream);
+
 /* lib/nerfacc/cuda/csrc/ray_marching.cu:322-363 `grid_query` (bool grid) */
 int rsdf_grid_query(const float *samples, const float *roi_host6, const uint8_t *grid_binary,
                     int rx, int ry, int rz, int n_samples, uint8_t *out, void *stream);
@@ -335,8 +348,9 @@ typedef struct rsdf_adam_groups {
     int32_t n_groups;
     int64_t end[RSDF_ADAM_MAX_GROUPS];
     float step_size[RSDF_ADAM_MAX_GROUPS];
-    float beta1[RSDF_ADAM_MAX_GROUPS];
+    float one_minus_beta1[RSDF_ADAM_MAX_GROUPS];   /* rounded from the host's double, as torch passes it to lerp_ */
     float beta2[RSDF_ADAM_MAX_GROUPS];
+    float one_minus_beta2[RSDF_ADAM_MAX_GROUPS];
     float eps[RSDF_ADAM_MAX_GROUPS];
     float bias2_sqrt[RSDF_ADAM_MAX_GROUPS];
     float weight_decay[RSDF_ADAM_MAX_GROUPS];

@@ -48,8 +48,9 @@ ADAM_MAX_GROUPS = 8
 
 class AdamGroupsC(ctypes.Structure):
     _fields_ = [("n_groups", ctypes.c_int32), ("end", ctypes.c_int64 * ADAM_MAX_GROUPS),
-                ("step_size", ctypes.c_float * ADAM_MAX_GROUPS), ("beta1", ctypes.c_float * ADAM_MAX_GROUPS),
-                ("beta2", ctypes.c_float * ADAM_MAX_GROUPS), ("eps", ctypes.c_float * ADAM_MAX_GROUPS),
+                ("step_size", ctypes.c_float * ADAM_MAX_GROUPS), ("one_minus_beta1", ctypes.c_float * ADAM_MAX_GROUPS),
+                ("beta2", ctypes.c_float * ADAM_MAX_GROUPS), ("one_minus_beta2", ctypes.c_float * ADAM_MAX_GROUPS),
+                ("eps", ctypes.c_float * ADAM_MAX_GROUPS),
                 ("bias2_sqrt", ctypes.c_float * ADAM_MAX_GROUPS), ("weight_decay", ctypes.c_float * ADAM_MAX_GROUPS)]
 
 
@@ -59,6 +60,8 @@ _SIGS = {
     "rsdf_grid_pack_bits": [c_p, c_i, c_p, c_p],
     "rsdf_march_count": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_p, c_p, c_p, c_p],
     "rsdf_march_fill": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_p, c_p, c_p, c_p, c_p],
+    "rsdf_march_count_keep": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_p, c_p, c_p, c_p, c_i, c_p],
+    "rsdf_march_compact": [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
     "rsdf_grid_query": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
     "rsdf_pack_info": [c_p, c_i, c_i, c_p, c_p],
     "rsdf_weight_from_alpha_fwd": [c_p, c_p, c_i, c_p, c_p, c_p],
@@ -142,7 +145,7 @@ def stream():
 
 
 # kernels launched per C-ABI entry point (for bench.py's gpu_launches count)
-LAUNCHES = {"rsdf_march_count": 4}
+LAUNCHES = {"rsdf_march_count": 4, "rsdf_march_count_keep": 4}
 STATS = {"enabled": False, "launches": 0, "timed": set(), "events": {}}
 
 

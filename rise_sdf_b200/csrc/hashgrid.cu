@@ -531,13 +531,28 @@ __device__ __forceinline__ void sh_grad(float x, float y, float z, int degree, c
     d[0] = gx; d[1] = gy; d[2] = gz;
 }
 
-__global__ void sh_fwd_kernel(const float *__restrict__ u, int n, int degree, float *__restrict__ out) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    float o[25];
-    sh_eval(u[3 * s] * 2.0f - 1.0f, u[3 * s + 1] * 2.0f - 1.0f, u[3 * s + 2] * 2.0f - 1.0f, degree, o);
+// A thread evaluates one direction; the block's [256, nd] output range is contiguous in global memory, so the
+// values go through a padded shared tile ([k][sample], stride 257: conflict-free writes, 2-way reads) and leave
+// as fully coalesced streaming stores instead of 32 scattered 4-byte stores per instruction.
+__global__ void __launch_bounds__(256) sh_fwd_kernel(const float *__restrict__ u, int n, int degree,
+                                                     float *__restrict__ out) {
+    __shared__ float tile[25 * 257];
+    const int s0 = blockIdx.x * 256, s = s0 + threadIdx.x;
     const int nd = degree * degree;
-    for (int k = 0; k < nd; ++k) out[(size_t)s * nd + k] = o[k];
+    if (s < n) {
+        float o[25];
+        sh_eval(u[3 * s] * 2.0f - 1.0f, u[3 * s + 1] * 2.0f - 1.0f, u[3 * s + 2] * 2.0f - 1.0f, degree, o);
+#pragma unroll
+        for (int k = 0; k < 25; ++k)
+            if (k < nd) tile[k * 257 + threadIdx.x] = o[k];
+    }
+    __syncthreads();
+    const int cnt = min(256, n - s0) * nd;
+    float *dst = out + (size_t)s0 * nd;
+    for (int i = threadIdx.x; i < cnt; i += 256) {
+        const int sl = i / nd, k = i - sl * nd;
+        __stcs(dst + i, tile[k * 257 + sl]);
+    }
 }
 
 __global__ void sh_bwd_kernel(const float *__restrict__ u, const float *__restrict__ go, int n, int degree,

@@ -48,14 +48,18 @@ __device__ __forceinline__ float axis_exit(float x, float lo, float hi, float r,
     return __fmul_rn(__fdiv_rn(__fmul_rn(__fsub_rn(f, u), inv_dir), r), __fsub_rn(hi, lo));
 }
 
-template <bool FILL>
+// MODE 0: count; 1: fill (second march); 2: count and keep the first `cap` intervals of every ray in
+// keep[ray][cap] so that the fill round is a copy (compact_kernel) instead of a second march.
+template <int MODE>
 __global__ void __launch_bounds__(64)
 march_kernel(const int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
              const float *__restrict__ t_min, const float *__restrict__ t_max, const MarchGrid g,
              const float step_size, const float cone_angle,
              const int32_t *__restrict__ packed_info, int32_t *__restrict__ num_steps,
              int64_t *__restrict__ ray_indices, float *__restrict__ t_starts,
-             float *__restrict__ t_ends) {
+             float *__restrict__ t_ends, float2 *__restrict__ keep = nullptr, const int cap = 0,
+             int32_t *__restrict__ overflow = nullptr) {
+    constexpr bool FILL = MODE == 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rays) return;
     const float ox = rays_o[3 * i], oy = rays_o[3 * i + 1], oz = rays_o[3 * i + 2];
@@ -81,6 +85,7 @@ march_kernel(const int n_rays, const float *__restrict__ rays_o, const float *__
                 t_ends[base + j] = t1;
                 ray_indices[base + j] = i;
             }
+            if (MODE == 2 && j < cap) __stcs(keep + (size_t)i * cap + j, make_float2(t0, t1));
             ++j;
             t0 = t1;
             t1 = __fadd_rn(t0, clamp_ref(__fmul_rn(t0, cone_angle), dt_min, dt_max));
@@ -100,6 +105,24 @@ march_kernel(const int n_rays, const float *__restrict__ rays_o, const float *__
         }
     }
     if (!FILL) num_steps[i] = j;
+    if (MODE == 2 && j > cap) *overflow = 1;
+}
+
+// fill round of MODE 2: one warp per ray copies its kept intervals to their packed position.
+__global__ void __launch_bounds__(256)
+compact_kernel(const int n_rays, const int32_t *__restrict__ packed_info, const float2 *__restrict__ keep,
+               const int cap, int64_t *__restrict__ ray_indices, float *__restrict__ t_starts,
+               float *__restrict__ t_ends) {
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (ray >= n_rays) return;
+    const int base = packed_info[2 * ray], count = packed_info[2 * ray + 1];
+    const float2 *src = keep + (size_t)ray * cap;
+    for (int j = lane; j < count; j += 32) {
+        const float2 v = __ldcs(src + j);
+        t_starts[base + j] = v.x;
+        t_ends[base + j] = v.y;
+        ray_indices[base + j] = ray;
+    }
 }
 
 // ---- int32 exclusive scan of per-ray counts -> packed_info (base, count) -----------------
@@ -298,13 +321,51 @@ int rsdf_march_count(const float *rays_o, const float *rays_d, const float *t_mi
     const int nb = rsdf_div_up(n_rays, SCAN_B);
     int32_t *sums = scan_tmp;
     int32_t *num = scan_tmp + nb + 1;
-    march_kernel<false><<<rsdf_div_up(n_rays, 64), 64, 0, st>>>(
+    march_kernel<0><<<rsdf_div_up(n_rays, 64), 64, 0, st>>>(
         n_rays, rays_o, rays_d, t_min, t_max, g, step_size, cone_angle, nullptr, num, nullptr,
         nullptr, nullptr);
     RSDF_LAUNCH_CHECK();
     scan_block_sums<<<nb, SCAN_T, 0, st>>>(num, n_rays, sums);
     scan_sums<<<1, SCAN_T, 0, st>>>(sums, nb, total);
     scan_finalize<<<nb, SCAN_T, 0, st>>>(num, n_rays, sums, packed_info);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_march_count_keep(const float *rays_o, const float *rays_d, const float *t_min,
+                          const float *t_max, const float *roi, const uint8_t *grid_binary,
+                          const uint32_t *grid_bits, int rx, int ry, int rz, float step_size,
+                          float cone_angle, int n_rays, int32_t *packed_info, int32_t *scan_tmp,
+                          int32_t *total2, float *keep, int cap, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!total2) return RSDF_EBADARG;
+    cudaError_t e = cudaMemsetAsync(total2, 0, 2 * sizeof(int32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    if (n_rays == 0) return 0;
+    if (!rays_o || !rays_d || !t_min || !t_max || !roi || (!grid_binary && !grid_bits) ||
+        !packed_info || !scan_tmp || !keep || cap < 1 || (((uintptr_t)keep) & 7))
+        return RSDF_EBADARG;
+    const MarchGrid g = make_grid(roi, grid_binary, grid_bits, rx, ry, rz);
+    const int nb = rsdf_div_up(n_rays, SCAN_B);
+    int32_t *sums = scan_tmp;
+    int32_t *num = scan_tmp + nb + 1;
+    march_kernel<2><<<rsdf_div_up(n_rays, 64), 64, 0, st>>>(
+        n_rays, rays_o, rays_d, t_min, t_max, g, step_size, cone_angle, nullptr, num, nullptr,
+        nullptr, nullptr, reinterpret_cast<float2 *>(keep), cap, total2 + 1);
+    RSDF_LAUNCH_CHECK();
+    scan_block_sums<<<nb, SCAN_T, 0, st>>>(num, n_rays, sums);
+    scan_sums<<<1, SCAN_T, 0, st>>>(sums, nb, total2);
+    scan_finalize<<<nb, SCAN_T, 0, st>>>(num, n_rays, sums, packed_info);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_march_compact(const int32_t *packed_info, const float *keep, int cap, int n_rays,
+                       int64_t *ray_indices, float *t_starts, float *t_ends, void *stream) {
+    if (n_rays == 0) return 0;
+    if (!packed_info || !keep || cap < 1 || !ray_indices || !t_starts || !t_ends) return RSDF_EBADARG;
+    compact_kernel<<<rsdf_div_up((long long)n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        n_rays, packed_info, reinterpret_cast<const float2 *>(keep), cap, ray_indices, t_starts, t_ends);
     RSDF_LAUNCH_CHECK();
     return 0;
 }
@@ -319,7 +380,7 @@ int rsdf_march_fill(const float *rays_o, const float *rays_d, const float *t_min
         !packed_info)
         return RSDF_EBADARG;
     const MarchGrid g = make_grid(roi, grid_binary, grid_bits, rx, ry, rz);
-    march_kernel<true><<<rsdf_div_up(n_rays, 64), 64, 0, (cudaStream_t)stream>>>(
+    march_kernel<1><<<rsdf_div_up(n_rays, 64), 64, 0, (cudaStream_t)stream>>>(
         n_rays, rays_o, rays_d, t_min, t_max, g, step_size, cone_angle, packed_info, nullptr,
         ray_indices, t_starts, t_ends);
     RSDF_LAUNCH_CHECK();

@@ -9,7 +9,7 @@
 namespace {
 
 struct AdamElem {
-    float step_size, b1, b2, eps, bc2_sqrt, wd;
+    float step_size, omb1, b2, omb2, eps, bc2_sqrt, wd;
 };
 
 __device__ __forceinline__ int find_seg(const rsdf_adam_groups &G, long long i) {
@@ -22,8 +22,9 @@ __device__ __forceinline__ int find_seg(const rsdf_adam_groups &G, long long i) 
 __device__ __forceinline__ AdamElem load_seg(const rsdf_adam_groups &G, int s) {
     AdamElem e;
     e.step_size = G.step_size[s];
-    e.b1 = G.beta1[s];
+    e.omb1 = G.one_minus_beta1[s];
     e.b2 = G.beta2[s];
+    e.omb2 = G.one_minus_beta2[s];
     e.eps = G.eps[s];
     e.bc2_sqrt = G.bias2_sqrt[s];
     e.wd = G.weight_decay[s];
@@ -34,8 +35,8 @@ __device__ __forceinline__ AdamElem load_seg(const rsdf_adam_groups &G, int s) {
 // lerp_ / mul_.addcmul_ / sqrt / div / add / addcdiv_ kept, every product rounded on its own.
 __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, const AdamElem &e) {
     if (e.wd != 0.0f) g = __fmaf_rn(e.wd, p, g);                       // grad.add(param, alpha=wd)
-    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), __fsub_rn(1.0f, e.b1)));            // exp_avg.lerp_(grad, 1-b1)
-    v = __fadd_rn(__fmul_rn(v, e.b2), __fmul_rn(__fmul_rn(__fsub_rn(1.0f, e.b2), g), g));  // mul_(b2).addcmul_(g,g,1-b2)
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), e.omb1));            // exp_avg.lerp_(grad, 1-b1)
+    v = __fadd_rn(__fmul_rn(v, e.b2), __fmul_rn(__fmul_rn(e.omb2, g), g));  // mul_(b2).addcmul_(g,g,1-b2)
     float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), e.bc2_sqrt), e.eps);
     p = __fsub_rn(p, __fmul_rn(e.step_size, __fdiv_rn(m, denom)));
 }

@@ -51,9 +51,7 @@ def load_reference_state_dict(model, state_dict, strict=False):
     missing = [k for k in own if k not in picked]
     if strict and (missing or unexpected):
         raise RuntimeError(f"load_reference_state_dict: missing {missing}, unexpected {unexpected}")
-    with torch.no_grad():
-        for name, v in picked.items():
-            own[name].copy_(v)               # state_dict() tensors alias the module's storage
+    model.load_state_dict(picked, strict=False)       # runs the modules' own load hooks (occupancy box, bit cache)
     return missing, unexpected
 
 

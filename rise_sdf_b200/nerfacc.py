@@ -57,29 +57,51 @@ def pack_bits(grid_binary: Tensor) -> Tensor:
     return bits
 
 
+KEEP_BUDGET_BYTES = 1 << 30      # scratch of the one-march path: n_rays * cap * 8 bytes
+
+
 @torch.no_grad()
-def _march(rays_o, rays_d, t_min, t_max, roi_host, grid_binary, grid_bits, step, cone):
+def _march(rays_o, rays_d, t_min, t_max, roi_host, grid_binary, grid_bits, step, cone, span=None):
     """== _C.ray_marching (lib/nerfacc/cuda/csrc/ray_marching.cu:194-289).
-    Returns packed_info int32[R,2], ray_indices int64[S], t_starts[S], t_ends[S]."""
+    Returns packed_info int32[R,2], ray_indices int64[S], t_starts[S], t_ends[S].
+
+    `span`: an upper bound of t_max - t_min known on the host (AABB diagonal, far - near plane).  With it the
+    count round keeps every ray's intervals (at most span/step + 2 of them) and the fill round is a copy; without
+    it, when the scratch would exceed KEEP_BUDGET_BYTES, or if a ray overflows its slots after all, the fill
+    round marches a second time like the reference.  Both orders produce the same bits (test_gpu_march)."""
     n = rays_o.shape[0]
     dev = rays_o.device
     rx, ry, rz = grid_binary.shape[-3:]
     packed = torch.empty(n, 2, device=dev, dtype=torch.int32)
     tmp = torch.empty(n + n // 1024 + 3, device=dev, dtype=torch.int32)
-    total = torch.zeros(1, device=dev, dtype=torch.int32)
+    total = torch.zeros(2, device=dev, dtype=torch.int32)
     gb = grid_binary.view(torch.uint8) if grid_binary.dtype == torch.bool else grid_binary
     st = L.stream()
-    L.call("rsdf_march_count", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), roi_host,
-           L.ptr(gb), L.ptr(grid_bits), rx, ry, rz, float(step), float(cone), n, L.ptr(packed),
-           L.ptr(tmp), L.ptr(total), st)
-    S = int(total.item())   # the one host sync of the march (reference: ray_marching.cu:261)
+    cap = 0
+    if span is not None and step > 0 and n > 0 and span / step < 1e6:
+        cap = int(span / step) + 2
+        if cap * n * 8 > KEEP_BUDGET_BYTES:
+            cap = 0
+    if cap:
+        keep = torch.empty(n, cap, 2, device=dev, dtype=torch.float32)
+        L.call("rsdf_march_count_keep", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), roi_host,
+               L.ptr(gb), L.ptr(grid_bits), rx, ry, rz, float(step), float(cone), n, L.ptr(packed),
+               L.ptr(tmp), L.ptr(total), L.ptr(keep), cap, st)
+    else:
+        L.call("rsdf_march_count", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), roi_host,
+               L.ptr(gb), L.ptr(grid_bits), rx, ry, rz, float(step), float(cone), n, L.ptr(packed),
+               L.ptr(tmp), L.ptr(total), st)
+    S, overflow = total.tolist()   # the one host sync of the march (reference: ray_marching.cu:261)
     ri = torch.empty(S, device=dev, dtype=torch.int64)
     ts = torch.empty(S, device=dev, dtype=torch.float32)
     te = torch.empty(S, device=dev, dtype=torch.float32)
     if S > 0:
-        L.call("rsdf_march_fill", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), roi_host,
-               L.ptr(gb), L.ptr(grid_bits), rx, ry, rz, float(step), float(cone), n, L.ptr(packed),
-               L.ptr(ri), L.ptr(ts), L.ptr(te), st)
+        if cap and not overflow:
+            L.call("rsdf_march_compact", L.ptr(packed), L.ptr(keep), cap, n, L.ptr(ri), L.ptr(ts), L.ptr(te), st)
+        else:
+            L.call("rsdf_march_fill", L.ptr(rays_o), L.ptr(rays_d), L.ptr(t_min), L.ptr(t_max), roi_host,
+                   L.ptr(gb), L.ptr(grid_bits), rx, ry, rz, float(step), float(cone), n, L.ptr(packed),
+                   L.ptr(ri), L.ptr(ts), L.ptr(te), st)
     return packed, ri, ts, te
 
 
@@ -99,9 +121,13 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
     if alpha_fn is not None and sigma_fn is not None:
         raise ValueError("Only one of `alpha_fn` and `sigma_fn` should be provided.")
     rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    span = None          # host-side upper bound of t_max - t_min (unit directions; _march re-checks on the device)
     if t_min is None or t_max is None:
         if scene_aabb is not None:
-            t_min, t_max = ray_aabb_intersect(rays_o, rays_d, scene_aabb)
+            box = grid.roi_host if (grid is not None and scene_aabb is getattr(grid, "_aabb0", None)) \
+                else L.host6(scene_aabb)
+            t_min, t_max = ray_aabb_intersect(rays_o, rays_d, box)
+            span = sum((box[k + 3] - box[k]) ** 2 for k in range(3)) ** 0.5
         else:
             t_min = torch.zeros_like(rays_o[..., 0])
             t_max = torch.ones_like(rays_o[..., 0]) * 1e10
@@ -109,6 +135,8 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
         t_min = torch.clamp(t_min, min=near_plane)
     if far_plane is not None:
         t_max = torch.clamp(t_max, max=far_plane)
+        if far_plane < 1e9:
+            span = min(span if span is not None else 1e30, far_plane - max(near_plane or 0.0, 0.0))
     if stratified:
         t_min = t_min + torch.rand_like(t_min) * render_step_size
     if grid is not None:
@@ -120,7 +148,7 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
         gbin = torch.ones(1, 1, 1, dtype=torch.bool, device=rays_o.device)
         gbits = None
     packed, ri, ts, te = _march(rays_o, rays_d, t_min.contiguous(), t_max.contiguous(), roi_host,
-                                gbin.contiguous(), gbits, render_step_size, cone_angle)
+                                gbin.contiguous(), gbits, render_step_size, cone_angle, span)
     ts, te = ts[:, None], te[:, None]
     masks = None
     if sigma_fn is not None or alpha_fn is not None:
@@ -314,6 +342,11 @@ class OccGridEstimator(nn.Module):
         self._bits = None
         return super()._apply(fn, *a, **k)
 
+    def _load_from_state_dict(self, *a, **k):
+        super()._load_from_state_dict(*a, **k)
+        self.roi_host = L.host6(self.aabbs[0])        # a checkpoint may carry another box
+        self._bits = None
+
     @torch.no_grad()
     def sampling(self, rays_o: Tensor, rays_d: Tensor, sigma_fn: Optional[Callable] = None,
                  alpha_fn: Optional[Callable] = None, near_plane: float = 0.0, far_plane: float = 1e10,
@@ -327,7 +360,8 @@ class OccGridEstimator(nn.Module):
             if fn is None:
                 return None
             return lambda ts, te, ri: fn(ts[:, 0], te[:, 0], ri).reshape(-1, 1)
-        out = ray_marching(rays_o, rays_d, t_min=t_min, t_max=t_max, scene_aabb=self.aabbs[0], grid=self,
+        self._aabb0 = self.aabbs[0]          # lets ray_marching reuse roi_host instead of copying the box back
+        out = ray_marching(rays_o, rays_d, t_min=t_min, t_max=t_max, scene_aabb=self._aabb0, grid=self,
                            sigma_fn=wrap(sigma_fn), alpha_fn=wrap(alpha_fn), early_stop_eps=early_stop_eps,
                            alpha_thre=min(alpha_thre, float(self.occs.mean())) if alpha_thre > 0 else 0.0,
                            near_plane=near_plane, far_plane=far_plane, render_step_size=render_step_size,

@@ -96,7 +96,7 @@ class FlatAdam(torch.optim.Optimizer):
             b1, b2 = g["betas"]
             G.end[k] = self._group_end[k]
             G.step_size[k] = float(g["lr"]) / (1.0 - b1 ** t)          # torch/optim/adam.py: lr / bias_correction1
-            G.beta1[k], G.beta2[k], G.eps[k] = b1, b2, g["eps"]
+            G.one_minus_beta1[k], G.beta2[k], G.one_minus_beta2[k], G.eps[k] = 1.0 - b1, b2, 1.0 - b2, g["eps"]
             G.bias2_sqrt[k] = math.sqrt(1.0 - b2 ** t)
             G.weight_decay[k] = g["weight_decay"]
         return G

@@ -69,6 +69,44 @@ def test_march_bit_exact_vs_oracle(kind, R, use_bits):
     assert np.array_equal(bits(ts), bits(ots)) and np.array_equal(bits(te), bits(ote))
 
 
+@pytest.mark.parametrize("kind", ["ball", "ones", "random", "zeros"])
+def test_one_march_path_equals_two_round_path(kind, monkeypatch):
+    """The count round that keeps its intervals + the copy (rsdf_march_count_keep / rsdf_march_compact) against
+    the reference's count-then-march-again order (already pinned to the oracle above): same bits.  Also the two
+    fallbacks: a ray overflowing its slots (span too small) and a scratch over budget."""
+    rays = rays_for(4096)
+    grid = syn.analytic_grid(kind)
+    step = 1.732 * 2 * 1.5 / (128 if kind == "ones" else 1024)
+    o, d = rays[:, :3].contiguous().cuda(), rays[:, 3:].contiguous().cuda()
+    g = grid.cuda().contiguous()
+    tmin, tmax = rn.ray_aabb_intersect(o, d, torch.tensor(ROI))
+    gb = rn.pack_bits(g)
+    calls = []
+    real = L.call
+    monkeypatch.setattr(L, "call", lambda name, *a: (calls.append(name), real(name, *a))[1])
+    base = rn._march(o, d, tmin, tmax, L.host6(ROI), g, gb, step, 0.0)
+    assert "rsdf_march_count" in calls and "rsdf_march_count_keep" not in calls
+    for span, budget, want_compact in ((3.0 * 3 ** 0.5, 1 << 30, True), (0.05, 1 << 30, kind == "zeros"),
+                                       (3.0 * 3 ** 0.5, 1 << 20, False)):
+        calls.clear()
+        monkeypatch.setattr(rn, "KEEP_BUDGET_BYTES", budget)
+        got = rn._march(o, d, tmin, tmax, L.host6(ROI), g, gb, step, 0.0, span)
+        if int(base[0][:, 1].sum()) > 0:
+            assert ("rsdf_march_compact" in calls) == want_compact, (span, budget, calls)
+        for a, b in zip(base, got):
+            assert a.dtype == b.dtype and torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a,
+                                                      b.view(torch.int32) if b.dtype == torch.float32 else b)
+    # through the public entry point (span from the estimator's box): the keep path is the one that runs
+    calls.clear()
+    monkeypatch.setattr(rn, "KEEP_BUDGET_BYTES", 1 << 30)
+    est = rn.OccGridEstimator(torch.tensor(ROI), resolution=128).cuda()
+    est.binaries = g[None]
+    ri, ts, te, packed = est.sampling(o, d, render_step_size=step, _return_packed=True)
+    assert "rsdf_march_count_keep" in calls
+    assert torch.equal(ri, base[1]) and torch.equal(ts.view(torch.int32), base[2].view(torch.int32)) \
+        and torch.equal(te.view(torch.int32), base[3].view(torch.int32)) and torch.equal(packed, base[0])
+
+
 @pytest.mark.parametrize("kind", ["ball", "shell", "random"])
 def test_march_bit_exact_vs_reference_kernel(kind):
     C = oref.nerfacc_cuda()
