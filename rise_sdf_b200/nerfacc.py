@@ -114,9 +114,9 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
                  render_step_size: float = 1e-3, stratified: bool = False, cone_angle: float = 0.0,
                  _return_packed: bool = False, _return_mask: bool = False):
     """lib/nerfacc/ray_marching.py:14-222 (vendored nerfacc 0.3.5 signature).
-    Returns ray_indices int64[S], t_starts [S,1], t_ends [S,1].  `_return_mask` (ours) appends the visibility
-    mask over the marched candidates (None without sigma_fn / alpha_fn), so a caller can reuse what its
-    alpha_fn computed for the surviving samples."""
+    Returns ray_indices int64[S], t_starts [S,1], t_ends [S,1].  `_return_mask` (ours) appends, for every
+    surviving sample, its row in the concatenated outputs of the alpha_fn / sigma_fn calls (None without one), so
+    a caller can reuse what the visibility pass computed instead of evaluating the survivors again."""
     L.require_cuda(rays_o, rays_d)
     if alpha_fn is not None and sigma_fn is not None:
         raise ValueError("Only one of `alpha_fn` and `sigma_fn` should be provided.")
@@ -150,12 +150,14 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
     packed, ri, ts, te = _march(rays_o, rays_d, t_min.contiguous(), t_max.contiguous(), roi_host,
                                 gbin.contiguous(), gbits, render_step_size, cone_angle, span)
     ts, te = ts[:, None], te[:, None]
-    masks = None
+    masks = rows = None
     if sigma_fn is not None or alpha_fn is not None:
         if sigma_fn is not None:
             sigmas = sigma_fn(ts, te, ri)
             assert sigmas.shape == ts.shape, f"sigmas must have shape of (N, 1)! Got {sigmas.shape}"
             alphas = 1.0 - torch.exp(-sigmas * (te - ts))
+        elif VISIBILITY_CHUNKS and early_stop_eps > 0 and ts.shape[0] > 0:
+            alphas, rows = _alphas_front_to_back(alpha_fn, packed, ri, ts, te, early_stop_eps)
         else:
             alphas = alpha_fn(ts, te, ri)
             assert alphas.shape == ts.shape, f"alphas must have shape of (N, 1)! Got {alphas.shape}"
@@ -163,8 +165,62 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
                                   alpha_thre=alpha_thre)
         ri, ts, te = ri[masks], ts[masks], te[masks]
         packed = None
-    rv = (ri, ts, te) + ((packed,) if _return_packed else ()) + ((masks,) if _return_mask else ())
+    rv = (ri, ts, te) + ((packed,) if _return_packed else ())
+    if _return_mask:
+        # row of every surviving sample in the concatenation of alpha_fn's outputs over its calls
+        rv += (None if masks is None else (rows[masks] if rows is not None else torch.nonzero(masks)[:, 0]),)
     return rv
+
+
+VISIBILITY_CHUNKS = (64, 128, 256)      # samples per ray in rounds 1, 2, 3; a last round takes the rest
+
+
+def _transmittance(packed, alphas):
+    """T [S] of the scan kernel behind render_weight_from_alpha / render_visibility (no autograd)."""
+    T = torch.empty(alphas.shape[0], device=alphas.device, dtype=torch.float32)
+    L.call("rsdf_weight_from_alpha_fwd", L.ptr(packed), L.ptr(alphas), packed.shape[0], None, L.ptr(T), L.stream())
+    return T
+
+
+def _alphas_front_to_back(alpha_fn, packed, ri, ts, te, early_stop_eps):
+    """The visibility pass of lib/nerfacc/ray_marching.py:198-218 evaluates `alpha_fn` on every marched candidate
+    and then masks the ones behind `T < early_stop_eps`.  A sample's transmittance depends only on the samples in
+    front of it, so the candidates are evaluated front to back in rounds; a ray whose transmittance AT ITS NEXT
+    SAMPLE -- computed by the same scan kernel, from the same alphas, as the final mask -- is already below the
+    threshold is dropped from the later rounds.  Never-evaluated samples keep alpha 0 and are masked by their
+    transmittance exactly as before: the surviving set and its alphas are bit-identical to the one-shot pass
+    (tests/test_gpu_march.py::test_front_to_back_visibility_*).
+
+    Returns alphas [S0, 1] and rows int64[S0]: the row of each sample in the concatenation of alpha_fn's outputs
+    over the rounds (-1: never evaluated)."""
+    S0, dev = ts.shape[0], ts.device
+    n_rays = packed.shape[0]
+    base, count = packed[:, 0].long(), packed[:, 1].long()
+    alphas = torch.zeros(S0, 1, device=dev, dtype=torch.float32)
+    rows = torch.full((S0,), -1, device=dev, dtype=torch.int64)
+    ray_ids = torch.arange(n_rays, device=dev)
+    max_count = int(count.max())
+    done = n_eval = k = 0
+    while done < max_count:
+        chunk = VISIBILITY_CHUNKS[k] if k < len(VISIBILITY_CHUNKS) else max_count
+        active = count > done
+        if done > 0:
+            active &= _transmittance(packed, alphas)[(base + done).clamp(max=S0 - 1)] >= early_stop_eps
+        lens = torch.where(active, (count - done).clamp(max=chunk), torch.zeros_like(count))
+        total = int(lens.sum())
+        if total == 0:
+            break
+        first = torch.cumsum(lens, 0) - lens
+        ray_of = torch.repeat_interleave(ray_ids, lens, output_size=total)
+        idx = (base + done)[ray_of] + (torch.arange(total, device=dev) - first[ray_of])
+        a = alpha_fn(ts[idx], te[idx], ri[idx])
+        assert a.shape == (total, 1), f"alphas must have shape of (N, 1)! Got {a.shape}"
+        alphas[idx] = a.float()
+        rows[idx] = torch.arange(n_eval, n_eval + total, device=dev)
+        n_eval += total
+        done += chunk
+        k += 1
+    return alphas, rows
 
 
 @torch.no_grad()
@@ -354,8 +410,8 @@ class OccGridEstimator(nn.Module):
                  render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
                  stratified: bool = False, cone_angle: float = 0.0, _return_packed: bool = False,
                  _return_mask: bool = False):
-        """-> (ray_indices int64[S], t_starts[S], t_ends[S]) sorted by ray then t (+ packed_info / the
-        visibility mask over the marched candidates when asked for)."""
+        """-> (ray_indices int64[S], t_starts[S], t_ends[S]) sorted by ray then t (+ packed_info / the survivors'
+        rows in the visibility pass's outputs when asked for, see `ray_marching`)."""
         def wrap(fn):
             if fn is None:
                 return None

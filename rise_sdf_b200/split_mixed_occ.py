@@ -131,40 +131,46 @@ class SplitMixedOCCModel(nn.Module):
         return c[key]
 
 
-    def _alpha_fn(self, rays_o, rays_d, keep=None):
-        """`alpha_fn` of models/split_mixed_occ.py:197-208.  With `keep` (a dict) the per-candidate results of the
-        visibility pass are parked in it: the reference evaluates the field a second time on the samples that
-        survive `sampling` (:228-240 / compute_indirect_radiance :183-191), which for a no-grad pass recomputes
-        exactly the same numbers -- the caller gathers them with the visibility mask instead."""
+    def _alpha_fn(self, rays_o, rays_d, keep=None, with_feature=False):
+        """`alpha_fn` of models/split_mixed_occ.py:197-208.  With `keep` (a list) the results of every call are
+        appended to it: the reference evaluates the field a second time on the samples that survive `sampling`
+        (:228-240 / compute_indirect_radiance :183-191), which for a no-grad pass recomputes exactly the same
+        numbers -- the caller gathers them by the rows `sampling(..., _return_mask=True)` reports instead."""
         def alpha_fn(t_starts, t_ends, ray_indices):
             t_origins = rays_o[ray_indices]
             t_dirs = rays_d[ray_indices]
             positions = t_origins + t_dirs * (t_starts + t_ends)[..., None] / 2.0
             if t_origins.shape[0] == 0:
                 return torch.zeros((0,), device=t_origins.device)
-            if keep is not None and keep.get("feature", False) is None:
-                sdf, sdf_grad, keep["feature"] = self.geometry(positions, with_grad=True, with_feature=True)
+            feature = None
+            if keep is not None and with_feature:
+                sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
             else:
                 sdf, sdf_grad = self.geometry(positions, with_grad=True, with_feature=False)
             normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
             dists = (t_ends - t_starts)[..., None]
             alphas = self.get_alpha(sdf, normal, t_dirs, dists)
             if keep is not None:
-                keep.update(sdf=sdf, sdf_grad=sdf_grad, normal=normal, alphas=alphas, n=t_starts.shape[0])
+                keep.append(dict(sdf=sdf, sdf_grad=sdf_grad, normal=normal, alphas=alphas, feature=feature))
             return alphas
         return alpha_fn
 
+    @staticmethod
+    def _kept(keep, key, rows):
+        """rows of the concatenated per-call results of the visibility pass"""
+        return (keep[0][key] if len(keep) == 1 else torch.cat([c[key] for c in keep]))[rows]
+
     def compute_indirect_radiance(self, rays_o, rays_d):
         n_rays = rays_o.shape[0]
-        keep = {} if self.reuse_sampling_pass else None
+        keep = [] if self.reuse_sampling_pass else None
         alpha_fn = self._alpha_fn(rays_o, rays_d, keep)
         with torch.no_grad():
             step = (self.secondary_far_plane - self.secondary_near_plane) / (self.num_samples_per_secondary_ray - 1)
-            ray_indices, t_starts, t_ends, mask = self.occupancy_grid.sampling(
+            ray_indices, t_starts, t_ends, rows = self.occupancy_grid.sampling(
                 rays_o, rays_d, alpha_fn=alpha_fn, near_plane=self.secondary_near_plane,
                 far_plane=self.secondary_far_plane, render_step_size=step, stratified=False, _return_mask=True)
-            if keep and mask is not None and keep.get("n") == mask.shape[0]:
-                cached = keep["alphas"][mask]
+            if keep and rows is not None:
+                cached = self._kept(keep, "alphas", rows)
                 alpha_fn = lambda ts, te, ri: cached          # the survivors' alphas, as computed a moment ago
                 chunk = None
             else:
@@ -179,8 +185,8 @@ class SplitMixedOCCModel(nn.Module):
         rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
         fd_train = self.config.geometry.grad_type == "finite_difference" and self.training
         # no-grad render (eval / relighting): the shading pass reuses the visibility pass's field evaluation
-        keep = {"feature": None} if (self.reuse_sampling_pass and not torch.is_grad_enabled()) else None
-        alpha_fn = self._alpha_fn(rays_o, rays_d, keep)
+        keep = [] if (self.reuse_sampling_pass and not torch.is_grad_enabled()) else None
+        alpha_fn = self._alpha_fn(rays_o, rays_d, keep, with_feature=True)
 
         def rgb_normal_alpha_fn(t_starts, t_ends, ray_indices):
             t_origins = rays_o[ray_indices]
@@ -196,7 +202,8 @@ class SplitMixedOCCModel(nn.Module):
 
             def fields():
                 if survivors:                      # gathered from the visibility pass instead of re-evaluated
-                    got = tuple(keep[k][survivors[0]] for k in ("sdf", "sdf_grad", "feature", "normal", "alphas"))
+                    got = tuple(self._kept(keep, k, survivors[0])
+                                for k in ("sdf", "sdf_grad", "feature", "normal", "alphas"))
                     keep.clear()
                     return got
                 sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
@@ -212,8 +219,7 @@ class SplitMixedOCCModel(nn.Module):
             r = self.occupancy_grid.sampling(
                 rays_o, rays_d, alpha_fn=alpha_fn, render_step_size=self.render_step_size,
                 stratified=self.randomized, cone_angle=0.0, alpha_thre=0.0, _return_mask=True)
-            ok = (keep is not None and r[3] is not None and keep.get("n") == r[3].shape[0]
-                  and keep["feature"] is not None)
+            ok = bool(keep) and r[3] is not None
             return r[:3], ([r[3]] if ok else []), keep
 
         (ray_indices, t_starts, t_ends), survivors, keep = self._memo("sampling", sample)

@@ -107,6 +107,45 @@ def test_one_march_path_equals_two_round_path(kind, monkeypatch):
         and torch.equal(te.view(torch.int32), base[3].view(torch.int32)) and torch.equal(packed, base[0])
 
 
+@pytest.mark.parametrize("chunks", [(4,), (16, 32), (64, 128, 256)])
+def test_front_to_back_visibility_equals_one_shot(chunks, monkeypatch):
+    """`ray_marching(alpha_fn=...)`: evaluating the candidates in front-to-back rounds and dropping rays whose
+    transmittance is already under `early_stop_eps` must give the same survivors, with the same alphas, as
+    lib/nerfacc/ray_marching.py:198-218 (evaluate everything, then mask), while calling alpha_fn on fewer samples."""
+    rays = rays_for(2048, seed=3)
+    o, d = rays[:, :3].contiguous().cuda(), rays[:, 3:].contiguous().cuda()
+    est = rn.OccGridEstimator(torch.tensor(ROI), resolution=128).cuda()
+    est.binaries = syn.analytic_grid("ball").cuda()[None]
+    step = 1.732 * 2 * 1.5 / 512
+    seen = []
+
+    def alpha_fn(ts, te, ri):           # a dense ball of radius 1 inside thin haze: per-sample, batch-independent
+        x = o[ri] + d[ri] * ((ts + te) * 0.5)[:, None]
+        r = x.norm(dim=-1)
+        a = torch.where(r < 1.0, 0.5 + 0.1 * torch.sin(40.0 * r), 0.002 + 0.001 * torch.sin(40.0 * r))
+        seen.append((a, ts.shape[0]))
+        return a
+
+    monkeypatch.setattr(rn, "VISIBILITY_CHUNKS", ())
+    ri0, ts0, te0, rows0 = est.sampling(o, d, alpha_fn=alpha_fn, render_step_size=step, _return_mask=True)
+    a0, n0 = seen[0][0][rows0], seen[0][1]
+    assert len(seen) == 1 and 0 < ri0.shape[0] < n0
+    seen.clear()
+    monkeypatch.setattr(rn, "VISIBILITY_CHUNKS", chunks)
+    ri1, ts1, te1, rows1 = est.sampling(o, d, alpha_fn=alpha_fn, render_step_size=step, _return_mask=True)
+    assert torch.equal(ri0, ri1) and torch.equal(ts0, ts1) and torch.equal(te0, te1)
+    assert int(rows1.min()) >= 0                                   # every survivor was evaluated
+    assert torch.equal(torch.cat([a for a, _ in seen])[rows1], a0)
+    n1 = sum(n for _, n in seen)
+    assert len(seen) <= len(chunks) + 1 and n1 <= n0, (len(seen), n1, n0)
+    if chunks[0] >= 16:                 # rays go opaque ~15 samples into the ball: later rounds only see the misses
+        assert n1 < 0.5 * n0, (n1, n0)
+    # early_stop_eps = 0: nothing can be dropped -> the one-shot pass is used
+    seen.clear()
+    est.sampling(o, d, alpha_fn=alpha_fn, render_step_size=step, early_stop_eps=0.0)
+    assert len(seen) == 1 and seen[0][1] == n0
+
+
 @pytest.mark.parametrize("kind", ["ball", "shell", "random"])
 def test_march_bit_exact_vs_reference_kernel(kind):
     C = oref.nerfacc_cuda()

@@ -246,10 +246,11 @@ def test_split_sum_training_step_runs_and_reaches_every_parameter_group():
         assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0, name
 
 
-def test_relighting_reuse_is_bit_identical():
+def test_relighting_reuse_is_bit_identical(monkeypatch):
     """configs[3]: (a) a no-grad render gathers the surviving samples' field values from the visibility pass
     instead of evaluating the field again, (b) a tile rendered under several env maps computes everything that
-    does not depend on the map once.  Both must reproduce the evaluate-everything-again order of the reference
+    does not depend on the map once, (c) the visibility pass walks the candidates front to back and stops at
+    rays that are already opaque.  All three must reproduce the evaluate-everything-again order of the reference
     (models/split_mixed_occ.py:197-240, systems/split_occ.py:331-458) bit for bit."""
     from rise_sdf_b200 import synthetic as syn
     from rise_sdf_b200.relight import EnvSet, render_frame_shard
@@ -263,17 +264,23 @@ def test_relighting_reuse_is_bit_identical():
     rays = syn.training_rays(600, seed=9)[0].cuda()
     keys = ("comp_rgb_phys_full", "comp_rgb_full", "comp_normal", "opacity", "depth", "comp_spec_rgb_phys",
             "comp_roughness")
+    from rise_sdf_b200 import nerfacc as rn
+    chunks = rn.VISIBILITY_CHUNKS
     m.reuse_sampling_pass = False
+    monkeypatch.setattr(rn, "VISIBILITY_CHUNKS", ())           # one-shot visibility pass: the reference's order
     base, tiles = render_frame_shard(m, rays, envs, tile=256, keys=keys, share_across_envs=False)
     assert len(tiles) == 3
     assert not torch.equal(base[0]["comp_rgb_phys_full"], base[1]["comp_rgb_phys_full"])    # the maps do differ
-    for reuse, share in ((True, False), (False, True), (True, True)):
+    for front_to_back, reuse, share in ((False, True, False), (False, False, True), (True, False, False),
+                                        (True, True, True)):
+        monkeypatch.setattr(rn, "VISIBILITY_CHUNKS", (8, 16) if front_to_back else ())
         m.reuse_sampling_pass = reuse
         out, _ = render_frame_shard(m, rays, envs, tile=256, keys=keys, share_across_envs=share)
         assert m._tile_cache is None
         for e in base:
             for k in keys:
-                assert torch.equal(out[e][k], base[e][k]), (reuse, share, e, k)
+                assert torch.equal(out[e][k], base[e][k]), (front_to_back, reuse, share, e, k)
+    monkeypatch.setattr(rn, "VISIBILITY_CHUNKS", chunks)
     # the training-mode secondary bounce (no-grad inside a grad-enabled step) reuses its alphas the same way
     m.train(); m.randomized = False
     outs = []
