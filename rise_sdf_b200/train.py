@@ -11,6 +11,22 @@ import torch.nn.functional as F
 from .optim import FlatAdam
 
 
+def masked_mean(err, valid):
+    """`err[valid].mean()` for err [R, C] and a row mask valid [R] (systems/neus.py:103, systems/split_occ.py:163-177
+    index with the boolean mask, which costs a host sync in the middle of the step): the masked sum over the row
+    count.  No valid row -> 0/0 = nan, like the mean of an empty selection."""
+    v = valid.to(err.dtype)
+    return (err * v[:, None]).sum() / (v.sum() * err.shape[1])
+
+
+def masked_mse(a, b, valid):
+    return masked_mean((a - b) ** 2, valid)
+
+
+def masked_l1(a, b, valid):
+    return masked_mean((a - b).abs(), valid)
+
+
 def binary_cross_entropy(inp, target):
     """systems/criterions.py:155-159."""
     return -(target * torch.log(inp) + (1 - target) * torch.log(1 - inp)).mean()
@@ -56,7 +72,7 @@ def sdf_regularisers(sdf_grad, sdf, sparsity_scale=1.0):
 def neus_loss(out, rgb, fg_mask, lambda_rgb_mse=10.0, lambda_mask=0.1, lambda_eikonal=0.1,
               lambda_sparsity=0.01, sparsity_scale=1.0):
     valid = out["rays_valid_full"][..., 0]
-    loss_rgb = F.mse_loss(out["comp_rgb_full"][valid], rgb[valid])
+    loss_rgb = masked_mse(out["comp_rgb_full"], rgb, valid)
     loss_eik, loss_sparse = sdf_regularisers(out["sdf_grad_samples"], out["sdf_samples"], sparsity_scale)
     opacity = torch.clamp(out["opacity"].squeeze(-1), 1e-3, 1 - 1e-3)
     loss_mask = binary_cross_entropy(opacity, fg_mask.float())
@@ -77,15 +93,15 @@ def split_loss(model, out, rgb, fg_mask, has_mask=True, **overrides):
     lam = dict(SPLIT_LAMBDAS, **overrides)
     valid = out["rays_valid_full"][..., 0]
     parts = {}
-    parts["rgb_mse"] = F.mse_loss(out["comp_rgb_full"][valid], rgb[valid])
+    parts["rgb_mse"] = masked_mse(out["comp_rgb_full"], rgb, valid)
     loss = parts["rgb_mse"] * lam["lambda_rgb_mse"]
     if lam["lambda_rgb_l1"]:
-        loss = loss + F.l1_loss(out["comp_rgb_full"][valid], rgb[valid]) * lam["lambda_rgb_l1"]
+        loss = loss + masked_l1(out["comp_rgb_full"], rgb, valid) * lam["lambda_rgb_l1"]
     if model.stage != 0:
-        parts["rgb_phys_mse"] = F.mse_loss(out["comp_rgb_phys_full"][valid], rgb[valid])
+        parts["rgb_phys_mse"] = masked_mse(out["comp_rgb_phys_full"], rgb, valid)
         loss = loss + parts["rgb_phys_mse"] * lam["lambda_rgb_phys_mse"]
         if lam["lambda_rgb_phys_l1"]:
-            loss = loss + F.l1_loss(out["comp_rgb_phys_full"][valid], rgb[valid]) * lam["lambda_rgb_phys_l1"]
+            loss = loss + masked_l1(out["comp_rgb_phys_full"], rgb, valid) * lam["lambda_rgb_phys_l1"]
     parts["eikonal"], parts["sparsity"] = sdf_regularisers(out["sdf_grad_samples"], out["sdf_samples"],
                                                             lam["sparsity_scale"])
     loss = loss + parts["eikonal"] * lam["lambda_eikonal"]
@@ -100,7 +116,7 @@ def split_loss(model, out, rgb, fg_mask, has_mask=True, **overrides):
         parts["curvature"] = out["sdf_laplace_samples"].abs().mean()
         loss = loss + parts["curvature"] * lam["lambda_curvature"]
     if lam["lambda_emitter_distillation"] > 0 and model.stage != 0:
-        loss = loss + F.mse_loss(out["comp_spec_rgb_full"][valid], out["comp_spec_rgb_phys_full"][valid]) \
+        loss = loss + masked_mse(out["comp_spec_rgb_full"], out["comp_spec_rgb_phys_full"], valid) \
             * lam["lambda_emitter_distillation"]
     for name, value in model.geometry.regularizations(out).items():      # normal_orientation
         parts[name] = value
