@@ -349,22 +349,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Every step hands the trainer the NEXT step's rays as well: their march runs on a side stream while the GPU is
-    # still busy with this step (NeuSModel.presample), so the sample-count read-back no longer drains the queue.
     def step_resident(i):
         rays, rgb, fg, bg = devb[i % n_batches]
-        loss, out, _ = trainer.step(rays, rgb, fg, bg, next_rays=devb[(i + 1) % n_batches][0])
+        loss, out = trainer.step(rays, rgb, fg, bg)
         return loss, out
 
-    uploaded = {}
-
     def step_e2e(i):
-        h = host[i % n_batches]
-        rays = uploaded.pop(i, None)           # uploaded (pinned host -> device) by the previous step's prefetch
-        if rays is None:
-            rays = h[0].to(dev, non_blocking=True)
-        rgb, fg, bg = (t.to(dev, non_blocking=True) for t in h[1:])
-        loss, out, uploaded[i + 1] = trainer.step(rays, rgb, fg, bg, next_host_rays=host[(i + 1) % n_batches][0])
+        rays, rgb, fg, bg = (t.to(dev, non_blocking=True) for t in host[i % n_batches])
+        loss, out = trainer.step(rays, rgb, fg, bg)
         return float(loss.item())              # D2H read of the step's result
 
     # Prime the caching allocator: stratified jitter makes the sample count differ from step to step, and a size the

@@ -227,63 +227,14 @@ class NeuSModel(nn.Module):
         c = prev_cdf
         return ((p + 1e-5) / (c + 1e-5)).view(-1).clip(0.0, 1.0)
 
-    # ------------------------------------------------------------------ sampling
-    @torch.no_grad()
-    def _sample(self, rays_o, rays_d):
-        return self.occupancy_grid.sampling(
-            rays_o, rays_d, render_step_size=self.render_step_size, stratified=self.randomized,
-            cone_angle=0.0, alpha_thre=0.0, _return_packed=True)
-
-    def _grid_key(self):
-        b = self.occupancy_grid.binaries
-        return (b.data_ptr(), b._version, self.render_step_size, self.randomized)
-
-    _presampled = None
-    _side_stream = None
-
-    @torch.no_grad()
-    def presample(self, rays, host_rays=None):
-        """March the rays of the NEXT forward on a side stream while the GPU is still busy with the current step.
-        The march (models/neus.py:235-246) depends on the rays and the occupancy grid only, and its sample count has
-        to come back to the host before the sample buffers can be sized: done here, that read-back waits for the
-        side stream alone instead of draining the whole queued step.  `forward_` picks the result up when it is
-        called with the same rays tensor and the grid has not changed in between; otherwise it marches as usual.
-        host_rays: pinned host copy to upload on the side stream first (then `rays` is ignored and the device tensor
-        is returned)."""
-        main = torch.cuda.current_stream()
-        if self._side_stream is None:
-            self._side_stream = torch.cuda.Stream()
-        side = self._side_stream
-        grid = self.occupancy_grid
-        had_bits = grid._bits is not None and grid._bits_version == (grid.binaries.data_ptr(), grid.binaries._version)
-        grid.bits                                    # (re)pack on the main stream, where every other user runs
-        if not had_bits:
-            side.wait_stream(main)
-        with torch.cuda.stream(side):
-            if host_rays is not None:
-                rays = host_rays.to(main.device, non_blocking=True)
-            rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
-            res = self._sample(rays_o, rays_d)
-            done = torch.cuda.Event()
-            done.record(side)
-        for t in (rays, rays_o, rays_d) + tuple(res):
-            t.record_stream(main)                    # allocated on the side stream, consumed on the main one
-        self._presampled = (rays, self._grid_key(), res, done)
-        return rays
-
-    def _take_presampled(self, rays):
-        pre, self._presampled = self._presampled, None
-        if pre is None or pre[0] is not rays or pre[1] != self._grid_key():
-            return None
-        torch.cuda.current_stream().wait_event(pre[3])
-        return pre[2]
-
     # ------------------------------------------------------------------ render
     def forward_(self, rays):
         n_rays = rays.shape[0]
-        pre = self._take_presampled(rays)            # first: it orders this stream after a side-stream upload of `rays`
         rays_o, rays_d = rays[:, 0:3].contiguous(), rays[:, 3:6].contiguous()
-        ray_indices, t_starts, t_ends, packed = pre or self._sample(rays_o, rays_d)
+        with torch.no_grad():
+            ray_indices, t_starts, t_ends, packed = self.occupancy_grid.sampling(
+                rays_o, rays_d, render_step_size=self.render_step_size, stratified=self.randomized,
+                cone_angle=0.0, alpha_thre=0.0, _return_packed=True)
         dev = rays.device
         if t_starts.shape[0] == 0:
             z = lambda *s: torch.zeros(*s, device=dev)

@@ -164,10 +164,7 @@ class NeusTrainer:
         self.bucket = self.opt.bucket
         self.global_step = 0
 
-    def step(self, rays, rgb, fg_mask, background, optimize=True, next_rays=None, next_host_rays=None):
-        """One training step.  next_rays (device) / next_host_rays (pinned host): the rays of the FOLLOWING step, whose
-        march is started on a side stream once this step is queued (`NeuSModel.presample`); returns the device
-        tensor to pass as `rays` next time as a third value when one of them is given."""
+    def step(self, rays, rgb, fg_mask, background, optimize=True):
         m = self.model
         m.background_color = background
         self.bucket.zero()
@@ -178,8 +175,6 @@ class NeusTrainer:
         if optimize:
             self.opt.step()
         self.global_step += 1
-        if next_rays is not None or next_host_rays is not None:
-            return loss, out, m.presample(next_rays, host_rays=next_host_rays)
         return loss, out
 
 
