@@ -52,15 +52,24 @@ def cube_to_dir(s, x, y):
     return torch.stack((rx, ry, rz), dim=-1)
 
 
+_FACE_DIRS = {}
+
+
 def _face_dirs(res, device):
-    lin = torch.linspace(-1.0 + 1.0 / res, 1.0 - 1.0 / res, res, device=device)
-    gy, gx = torch.meshgrid(lin, lin, indexing="ij")
-    return [safe_normalize(cube_to_dir(s, gx, gy)) for s in range(6)]
+    """Unit directions of the texel centres of the six faces, [6, res, res, 3]: constants of (res, device), cached
+    (the reference rebuilds them in every cubemap_mip backward, lib/pbr/utils/light_utils.py:99-109: ~56 launches)."""
+    key = (int(res), str(device))
+    if key not in _FACE_DIRS:
+        lin = torch.linspace(-1.0 + 1.0 / res, 1.0 - 1.0 / res, res, device=device)
+        gy, gx = torch.meshgrid(lin, lin, indexing="ij")
+        _FACE_DIRS[key] = torch.stack([safe_normalize(cube_to_dir(s, gx, gy)) for s in range(6)]).contiguous()
+    return _FACE_DIRS[key]
 
 
 class cubemap_mip(torch.autograd.Function):
     """2x2 average-pool mip; the backward is the reference's own (a cube-filtered upsample of
-    0.25*dout, lib/pbr/utils/light_utils.py:99-109), not the adjoint of avg-pool."""
+    0.25*dout, lib/pbr/utils/light_utils.py:99-109), not the adjoint of avg-pool.  The six per-face lookups of the
+    reference are one lookup over all 6*res^2 directions (same kernel, same per-texel arithmetic)."""
 
     @staticmethod
     def forward(ctx, cubemap):
@@ -69,11 +78,10 @@ class cubemap_mip(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         res = dout.shape[1] * 2
-        out = torch.zeros(6, res, res, dout.shape[-1], dtype=torch.float32, device=dout.device)
-        for s, v in enumerate(_face_dirs(res, dout.device)):
-            out[s, ...] = dr.texture(dout[None, ...] * 0.25, v[None, ...].contiguous(), filter_mode="linear",
-                                     boundary_mode="cube")
-        return out
+        dirs = _face_dirs(res, dout.device)
+        out = dr.texture(dout[None, ...] * 0.25, dirs.view(1, 6 * res, res, 3), filter_mode="linear",
+                         boundary_mode="cube")
+        return out.view(6, res, res, dout.shape[-1])
 
 
 def blender_latlong_to_cubemap(latlong_map, res):

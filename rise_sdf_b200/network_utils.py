@@ -56,11 +56,21 @@ class VanillaFrequency(nn.Module):
         self.update_step(None, None)
 
     def forward(self, x):
+        """[..., C] -> [..., 2*F*C] in the reference's order (sin f0 | cos f0 | sin f1 | ...), models/network_utils.py:
+        27-33.  All bands in one multiply / sin / cos instead of a Python loop of 4 launches per band: the products
+        `freq * x` are the same fp32 multiplies (the bands are powers of two), so the values are bit-identical."""
         x = x * self.x_scale + self.x_offset
-        out = []
-        for freq, mask in zip(self.freq_bands.tolist(), self.mask.tolist()):
-            out += [torch.sin(freq * x) * mask, torch.cos(freq * x) * mask]
-        return torch.cat(out, -1)
+        if self._bands is None or self._bands.device != x.device:
+            self._bands = self.freq_bands.to(device=x.device, dtype=x.dtype)
+            self._mask_dev = None if bool((self.mask == 1).all()) else self.mask.to(device=x.device, dtype=x.dtype)
+        fx = x[..., None, :] * self._bands[:, None]                       # [..., F, C]
+        out = torch.stack((torch.sin(fx), torch.cos(fx)), dim=-2)          # [..., F, 2, C]
+        if self._mask_dev is not None:
+            out = out * self._mask_dev[:, None, None]
+        return out.reshape(*x.shape[:-1], self.n_output_dims)
+
+    _bands = None
+    _mask_dev = None
 
     def update_step(self, epoch, global_step):
         if self.n_masking_step <= 0 or global_step is None:
@@ -68,6 +78,7 @@ class VanillaFrequency(nn.Module):
         else:
             k = torch.arange(0, self.N_freqs)
             self.mask = (1.0 - torch.cos(math.pi * (global_step / self.n_masking_step * self.N_freqs - k).clamp(0, 1))) / 2.0
+        self._bands = None                       # re-derive the device copies of bands / mask on the next call
 
 
 class ProgressiveBandHashGrid(nn.Module):
