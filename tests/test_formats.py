@@ -46,6 +46,17 @@ def test_hdr_reader_and_writer_agree_with_opencv(tmp_path):
     assert np.array_equal(fm.read_hdr(theirs), cv2.imread(theirs, cv2.IMREAD_UNCHANGED)[..., ::-1])
 
 
+def test_hdr_reader_against_committed_opencv_golden():
+    """tests/golden/env_cv2_rle.hdr was written by OpenCV (RLE scanlines) and env_cv2_rle_decoded.npy is what
+    cv2.imdecode -- the reference's decoder -- returns for it (tests/golden/make_hdr_golden.py): bit-exact."""
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    got = fm.read_hdr(os.path.join(here, "env_cv2_rle.hdr"))
+    want = np.load(os.path.join(here, "env_cv2_rle_decoded.npy"))
+    assert got.dtype == np.float32 and got.shape == want.shape == (24, 48, 3)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[0, :5], np.zeros((5, 3), np.float32)) and float(got.max()) >= 1e3
+
+
 def test_hdr_rejects_other_files(tmp_path):
     p = tmp_path / "x.hdr"
     p.write_bytes(b"P6\n1 1\n255\n\0\0\0")
