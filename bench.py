@@ -238,8 +238,8 @@ def run_relight(args, dev, world, rank, n_frames=2):
     return {"metric": "relit_800x800_frames_per_s", "value": n_relit / (ms / 1e3), "unit": "frames/s",
             "ms_per_frame": ms / n_relit, "frames": n_relit, "env_maps": len(envs.maps), "n_gpus": world,
             "scaling": "strong", "occupied_fraction": round(float(model.occupancy_grid.binaries.float().mean()), 4),
-            "sharding": f"{balanced_tile(640000, world)}-ray tiles round-robin over ranks (equal tile count per rank), "
-                        "no collective",
+            "sharding": f"pixels interleaved over the ranks (rank r renders pixels r, r+{world}, ...), "
+                        f"{balanced_tile(640000, world)}-ray tiles inside a shard, no collective",
             "env_sharing": "each tile is rendered under both env maps back to back; sampling, field evaluations, "
                            "material networks and the secondary bounce run once per tile, emitter lookups + "
                            "compositing per map (frames bit-identical to independent renders: "

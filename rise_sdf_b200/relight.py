@@ -1,9 +1,9 @@
 """Relighting render (BASELINE configs[3]; systems/split_occ.py:331-458): 800x800 frames of a
 split-sum model under new environment maps, pixels sharded across GPUs with NO communication
-(SURVEY.md §8e): the frame is cut into `tile`-ray tiles dealt round-robin to ranks (the object
-is centred, so row blocks would be imbalanced); every rank holds the full model, occupancy grid,
-prefiltered mip pyramids and LUT, renders its tiles and keeps the result sharded (an optional
-all_gather assembles the frame)."""
+(SURVEY.md §8e): the pixels are interleaved over the ranks (rank r takes pixels r, r + world, ...; the
+object is centred, so row blocks -- and even round-robin row bands -- would be imbalanced) and each shard
+is rendered in `tile`-ray tiles; every rank holds the full model, occupancy grid, prefiltered mip
+pyramids and LUT and keeps its result sharded (`frame[rank::world] = shard` assembles it)."""
 import torch
 
 from . import synthetic as syn
@@ -29,32 +29,44 @@ class EnvSet:
 
 
 def my_tiles(n_rays, tile, rank, world):
+    """contiguous tiles dealt round-robin (kept for callers that want row blocks; see `my_pixels`)"""
     return [(s, min(s + tile, n_rays)) for k, s in enumerate(range(0, n_rays, tile)) if k % world == rank]
 
 
+def my_pixels(n_rays, rank, world):
+    """Pixel-interleaved shard of a frame: rank r renders rays r, r + world, r + 2 world, ...  Every rank (and every
+    tile inside a rank's shard) sees the whole image subsampled, so the work per rank is balanced whatever the
+    object covers -- row blocks or round-robin row bands put the dense centre on a few ranks.  Returns the slice."""
+    return slice(rank, n_rays, world)
+
+
 def balanced_tile(n_rays, world, max_tile=32768, per_rank=4):
-    """Tile size such that every rank gets the same NUMBER of tiles (>= per_rank of them when the frame is
-    large enough): 640 000 rays -> 32 000 for 1/2/4 ranks (20 tiles), 20 032 for 8 ranks (32 tiles, 4 each)."""
-    t = min(max_tile, -(-n_rays // (world * per_rank)))
+    """Tile size for a rank's shard of ceil(n_rays / world) rays: at most max_tile, at least per_rank tiles when the
+    shard is large enough, a multiple of 64, all tiles (almost) equal: 640 000 rays -> 32 000 on 1 GPU (20 tiles),
+    20 032 on 8 GPUs (4 tiles of the 80 000-ray shard)."""
+    n = -(-n_rays // world)
+    t = min(max_tile, -(-n // per_rank))
     t = -(-t // 64) * 64
-    n = -(-n_rays // t)
-    n = -(-n // world) * world                # round the tile count up to a multiple of the ranks
-    return -(-(-(-n_rays // n)) // 64) * 64
+    k = -(-n // t)
+    return -(-(-(-n // k)) // 64) * 64
 
 
 @torch.no_grad()
 def render_frame_shard(model, rays, envs, rank=0, world=1, tile=None, keys=("comp_rgb_phys_full",),
                        share_across_envs=True):
-    """Render this rank's tiles of one frame under every env map.  rays: [H*W, 6] on the device.
-    Returns {env_index: {key: [n_my_rays, C]}} plus the tile list.
+    """Render this rank's pixels of one frame under every env map.  rays: [H*W, 6] on the device (the whole frame:
+    the rank keeps `rays[rank::world]`).  Returns {env_index: {key: [n_my_rays, C]}} -- row i is pixel
+    rank + i * world of the frame -- plus the tile list (ranges inside the shard).
 
     share_across_envs: a tile is rendered under all maps back to back with a tile cache installed on the model
     (`SplitMixedOCCModel._memo`): sampling, field evaluations, material networks and the secondary bounce run once
     per tile, only the emitter lookups, compositing and the third-bounce shading run per map.  The frames are
     bit-identical to rendering every map from scratch (share_across_envs=False, the reference's loop order)."""
+    if world > 1:
+        rays = rays[my_pixels(rays.shape[0], rank, world)]          # rows of the outputs follow this order
     if tile is None:
-        tile = balanced_tile(rays.shape[0], world)
-    tiles = my_tiles(rays.shape[0], tile, rank, world)
+        tile = balanced_tile(rays.shape[0], 1)
+    tiles = my_tiles(rays.shape[0], tile, 0, 1)
     n_env = len(envs.maps)
     parts = {e: {k: [] for k in keys} for e in range(n_env)}
     try:

@@ -281,6 +281,13 @@ def test_relighting_reuse_is_bit_identical(monkeypatch):
             for k in keys:
                 assert torch.equal(out[e][k], base[e][k]), (front_to_back, reuse, share, e, k)
     monkeypatch.setattr(rn, "VISIBILITY_CHUNKS", chunks)
+    # multi-GPU sharding (run here rank by rank): the interleaved shards assemble into the single-GPU frame
+    for world in (2, 3):
+        frame = torch.empty_like(base[1]["comp_rgb_phys_full"])
+        for rank in range(world):
+            shard, _ = render_frame_shard(m, rays, envs, rank=rank, world=world, tile=128, keys=keys)
+            frame[rank::world] = shard[1]["comp_rgb_phys_full"]
+        assert torch.equal(frame, base[1]["comp_rgb_phys_full"]), world
     # the training-mode secondary bounce (no-grad inside a grad-enabled step) reuses its alphas the same way
     m.train(); m.randomized = False
     outs = []

@@ -15,7 +15,7 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from rise_sdf_b200.relight import balanced_tile, my_tiles
+    from rise_sdf_b200.relight import balanced_tile, my_pixels, my_tiles
     from rise_sdf_b200.train import FlatGradBucket
     torch.manual_seed(0)                                   # identical "weights" on every rank
     params = [torch.nn.Parameter(torch.randn(7, 3)), torch.nn.Parameter(torch.randn(11)), torch.nn.Parameter(torch.tensor(0.3))]
@@ -27,8 +27,9 @@ def _worker(rank, world, port, q):
     assert params[0].grad.data_ptr() == bucket.flat.data_ptr()      # grads really live in the flat buffer
     local = bucket.flat.clone()
     bucket.all_reduce_mean()
-    tiles = my_tiles(640000, balanced_tile(640000, world), rank, world)
-    q.put((rank, local, bucket.flat.clone(), tiles))
+    mine = torch.arange(640000)[my_pixels(640000, rank, world)]          # this rank's pixels of an 800x800 frame
+    tiles = my_tiles(mine.numel(), balanced_tile(640000, world), 0, 1)
+    q.put((rank, local, bucket.flat.clone(), (mine, tiles)))
     dist.destroy_process_group()
 
 
@@ -45,15 +46,23 @@ def test_flat_bucket_allreduce_and_tile_sharding():
     for r in range(world):
         assert torch.allclose(res[r][2], mean, rtol=1e-6, atol=1e-7)          # == DDP's averaged gradient
     assert not torch.allclose(res[0][1], res[1][1])
-    covered = sorted(res[0][3] + res[1][3])
-    assert covered[0][0] == 0 and covered[-1][1] == 640000
-    assert all(a[1] == b[0] for a, b in zip(covered[:-1], covered[1:]))       # disjoint, complete cover
-    assert len(res[0][3]) == len(res[1][3])                                   # same tile count on every rank
+    pixels = torch.cat([res[r][3][0] for r in range(world)])
+    assert torch.equal(torch.sort(pixels).values, torch.arange(640000))       # disjoint, complete cover
+    for r in range(world):
+        mine, tiles = res[r][3]
+        assert tiles[0][0] == 0 and tiles[-1][1] == mine.numel()
+        assert all(a[1] == b[0] for a, b in zip(tiles[:-1], tiles[1:]))       # the shard is tiled without gaps
+        rows = mine // 800
+        assert rows.min() == 0 and rows.max() == 799                          # every rank sees the whole image
+    assert len(res[0][3][1]) == len(res[1][3][1])                             # same tile count on every rank
 
 
 def test_balanced_tile_counts():
-    from rise_sdf_b200.relight import balanced_tile, my_tiles
+    from rise_sdf_b200.relight import balanced_tile, my_pixels, my_tiles
     for world in (1, 2, 3, 4, 8):
         t = balanced_tile(640000, world)
-        counts = [len(my_tiles(640000, t, r, world)) for r in range(world)]
-        assert t % 64 == 0 and t <= 32768 and len(set(counts)) == 1 and sum(counts) * t >= 640000
+        shard = [len(range(640000)[my_pixels(640000, r, world)]) for r in range(world)]
+        counts = [len(my_tiles(n, t, 0, 1)) for n in shard]
+        assert sum(shard) == 640000 and max(shard) - min(shard) <= 1
+        assert t % 64 == 0 and t <= 32768 and len(set(counts)) == 1 and counts[0] * t >= max(shard)
+        assert counts[0] >= 4 or t == 32000
