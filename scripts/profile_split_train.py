@@ -17,4 +17,5 @@ torch.cuda.synchronize(); print('ms/step', (time.time() - t) / 3 * 1e3, 'loss', 
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     tr.step(*b); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(sys.argv[1]) if len(sys.argv) > 1 else 40, max_name_column_width=70))
+print(prof.key_averages().table(sort_by=sys.argv[2] if len(sys.argv) > 2 else "cuda_time_total",
+                                row_limit=int(sys.argv[1]) if len(sys.argv) > 1 else 40, max_name_column_width=70))
