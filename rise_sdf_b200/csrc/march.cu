@@ -108,6 +108,82 @@ march_kernel(const int n_rays, const float *__restrict__ rays_o, const float *__
     if (MODE == 2 && j > cap) *overflow = 1;
 }
 
+// Count round that keeps its intervals, ONE WARP PER RAY (the thread-per-ray kernel above runs 8192 rays as 8192
+// threads: 3 % of the warp slots, every iteration a dependent chain of IEEE divisions).  Inside an occupied run the
+// march is a pure recurrence (t0 <- t1, t1 <- t0 + dt), so lane k evaluates the state after k occupied steps: the
+// same fp32 additions in the same order as the sequential loop, hence the same bits.  A ballot finds the first lane
+// whose sample is empty or beyond t_max; the lanes before it emit their intervals (coalesced), and the skip to the
+// next voxel -- the only step whose outcome the following state depends on -- is done once, warp-uniformly.
+template <bool CONE0>
+__global__ void __launch_bounds__(128)
+march_warp_kernel(const int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+                  const float *__restrict__ t_min, const float *__restrict__ t_max, const MarchGrid g,
+                  const float step_size, const float cone_angle, int32_t *__restrict__ num_steps,
+                  float2 *__restrict__ keep, const int cap, int32_t *__restrict__ overflow) {
+    const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (ray >= n_rays) return;
+    const float ox = rays_o[3 * ray], oy = rays_o[3 * ray + 1], oz = rays_o[3 * ray + 2];
+    const float dx = rays_d[3 * ray], dy = rays_d[3 * ray + 1], dz = rays_d[3 * ray + 2];
+    const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+    const float near = t_min[ray], far = t_max[ray];
+    const float dt_min = step_size, dt_max = 1e10f;
+    float2 *my_keep = keep + (size_t)ray * cap;
+
+    int j = 0;
+    float t0 = near;
+    float t1 = __fadd_rn(t0, clamp_ref(__fmul_rn(t0, cone_angle), dt_min, dt_max));
+    float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+    while (t_mid < far) {                                  // warp-uniform state (t0, t1, t_mid, j)
+        float a0 = t0, a1 = t1;                            // lane k: the state after k occupied steps
+#pragma unroll 1
+        for (int k = 0; k < 31; ++k) {
+            const float n1 = __fadd_rn(a1, CONE0 ? dt_min : clamp_ref(__fmul_rn(a1, cone_angle), dt_min, dt_max));
+            if (k < lane) { a0 = a1; a1 = n1; }
+        }
+        const float am = lane == 0 ? t_mid : __fmul_rn(__fadd_rn(a0, a1), 0.5f);
+        const bool valid = am < far;
+        float x = 0.f, y = 0.f, z = 0.f;
+        bool occ = false;
+        if (valid) {
+            x = __fmaf_rn(am, dx, ox);
+            y = __fmaf_rn(am, dy, oy);
+            z = __fmaf_rn(am, dz, oz);
+            occ = occupied_at(x, y, z, g);
+        }
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const unsigned stop = ~__ballot_sync(0xffffffffu, occ);
+        const int f = stop ? __ffs(stop) - 1 : 32;         // lanes < f continue the occupied run
+        if (lane < f && j + lane < cap) __stcs(my_keep + j + lane, make_float2(a0, a1));
+        j += f;
+        if (f == 32) {                                     // whole window occupied: carry on from lane 31's successor
+            t0 = __shfl_sync(0xffffffffu, a1, 31);
+            t1 = __fadd_rn(t0, clamp_ref(__fmul_rn(t0, cone_angle), dt_min, dt_max));
+            t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+            continue;
+        }
+        if (!((vmask >> f) & 1u)) break;                   // lane f is beyond t_max: the ray is done
+        // lane f sits in an empty cell: advance to the next voxel exactly like the sequential loop
+        const float fm = __shfl_sync(0xffffffffu, am, f);
+        const float fx = __shfl_sync(0xffffffffu, x, f), fy = __shfl_sync(0xffffffffu, y, f),
+                    fz = __shfl_sync(0xffffffffu, z, f);
+        const float tx = axis_exit(fx, g.roi[0], g.roi[3], (float)g.rx, dx, ix);
+        const float ty = axis_exit(fy, g.roi[1], g.roi[4], (float)g.ry, dy, iy);
+        const float tz = axis_exit(fz, g.roi[2], g.roi[5], (float)g.rz, dz, iz);
+        const float tt = fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
+        const float t_target = fminf(__fadd_rn(fm, tt), far);
+        float _t = fm;
+        do { _t = __fadd_rn(_t, dt_min); } while (_t < t_target);
+        t_mid = _t;
+        const float dt = clamp_ref(__fmul_rn(t_mid, cone_angle), dt_min, dt_max);
+        t0 = __fsub_rn(t_mid, __fmul_rn(dt, 0.5f));
+        t1 = __fadd_rn(t_mid, __fmul_rn(dt, 0.5f));
+    }
+    if (lane == 0) {
+        num_steps[ray] = j;
+        if (j > cap) *overflow = 1;
+    }
+}
+
 // fill round of MODE 2: one warp per ray copies its kept intervals to their packed position.
 __global__ void __launch_bounds__(256)
 compact_kernel(const int n_rays, const int32_t *__restrict__ packed_info, const float2 *__restrict__ keep,
@@ -349,9 +425,15 @@ int rsdf_march_count_keep(const float *rays_o, const float *rays_d, const float 
     const int nb = rsdf_div_up(n_rays, SCAN_B);
     int32_t *sums = scan_tmp;
     int32_t *num = scan_tmp + nb + 1;
-    march_kernel<2><<<rsdf_div_up(n_rays, 64), 64, 0, st>>>(
-        n_rays, rays_o, rays_d, t_min, t_max, g, step_size, cone_angle, nullptr, num, nullptr,
-        nullptr, nullptr, reinterpret_cast<float2 *>(keep), cap, total2 + 1);
+    const int wblocks = rsdf_div_up((long long)n_rays * 32, 128);
+    if (cone_angle == 0.0f)
+        march_warp_kernel<true><<<wblocks, 128, 0, st>>>(n_rays, rays_o, rays_d, t_min, t_max, g, step_size,
+                                                         cone_angle, num, reinterpret_cast<float2 *>(keep), cap,
+                                                         total2 + 1);
+    else
+        march_warp_kernel<false><<<wblocks, 128, 0, st>>>(n_rays, rays_o, rays_d, t_min, t_max, g, step_size,
+                                                          cone_angle, num, reinterpret_cast<float2 *>(keep), cap,
+                                                          total2 + 1);
     RSDF_LAUNCH_CHECK();
     scan_block_sums<<<nb, SCAN_T, 0, st>>>(num, n_rays, sums);
     scan_sums<<<1, SCAN_T, 0, st>>>(sums, nb, total2);
