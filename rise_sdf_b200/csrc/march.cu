@@ -114,6 +114,7 @@ march_kernel(const int n_rays, const float *__restrict__ rays_o, const float *__
 // same fp32 additions in the same order as the sequential loop, hence the same bits.  A ballot finds the first lane
 // whose sample is empty or beyond t_max; the lanes before it emit their intervals (coalesced), and the skip to the
 // next voxel -- the only step whose outcome the following state depends on -- is done once, warp-uniformly.
+// While a ray crosses empty space the window shrinks to one lane (no speculation to throw away).
 template <bool CONE0>
 __global__ void __launch_bounds__(128)
 march_warp_kernel(const int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
@@ -130,18 +131,19 @@ march_warp_kernel(const int n_rays, const float *__restrict__ rays_o, const floa
     float2 *my_keep = keep + (size_t)ray * cap;
 
     int j = 0;
+    int W = 32;                                            // speculation window: 32 lanes, or 1 while crossing empty space
     float t0 = near;
     float t1 = __fadd_rn(t0, clamp_ref(__fmul_rn(t0, cone_angle), dt_min, dt_max));
     float t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-    while (t_mid < far) {                                  // warp-uniform state (t0, t1, t_mid, j)
+    while (t_mid < far) {                                  // warp-uniform state (t0, t1, t_mid, j, W)
         float a0 = t0, a1 = t1;                            // lane k: the state after k occupied steps
-#pragma unroll 1
-        for (int k = 0; k < 31; ++k) {
+#pragma unroll 4
+        for (int k = 0; k < W - 1; ++k) {
             const float n1 = __fadd_rn(a1, CONE0 ? dt_min : clamp_ref(__fmul_rn(a1, cone_angle), dt_min, dt_max));
             if (k < lane) { a0 = a1; a1 = n1; }
         }
         const float am = lane == 0 ? t_mid : __fmul_rn(__fadd_rn(a0, a1), 0.5f);
-        const bool valid = am < far;
+        const bool valid = lane < W && am < far;
         float x = 0.f, y = 0.f, z = 0.f;
         bool occ = false;
         if (valid) {
@@ -152,13 +154,14 @@ march_warp_kernel(const int n_rays, const float *__restrict__ rays_o, const floa
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         const unsigned stop = ~__ballot_sync(0xffffffffu, occ);
-        const int f = stop ? __ffs(stop) - 1 : 32;         // lanes < f continue the occupied run
+        const int f = min(stop ? __ffs(stop) - 1 : 32, W);   // lanes < f continue the occupied run
         if (lane < f && j + lane < cap) __stcs(my_keep + j + lane, make_float2(a0, a1));
         j += f;
-        if (f == 32) {                                     // whole window occupied: carry on from lane 31's successor
-            t0 = __shfl_sync(0xffffffffu, a1, 31);
+        if (f == W) {                                      // whole window occupied: carry on from its last lane's successor
+            t0 = __shfl_sync(0xffffffffu, a1, W - 1);
             t1 = __fadd_rn(t0, clamp_ref(__fmul_rn(t0, cone_angle), dt_min, dt_max));
             t_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+            W = 32;
             continue;
         }
         if (!((vmask >> f) & 1u)) break;                   // lane f is beyond t_max: the ray is done
@@ -177,6 +180,7 @@ march_warp_kernel(const int n_rays, const float *__restrict__ rays_o, const floa
         const float dt = clamp_ref(__fmul_rn(t_mid, cone_angle), dt_min, dt_max);
         t0 = __fsub_rn(t_mid, __fmul_rn(dt, 0.5f));
         t1 = __fadd_rn(t_mid, __fmul_rn(dt, 0.5f));
+        W = f == 0 ? 1 : 32;                               // still in empty space: probe one sample before fanning out
     }
     if (lane == 0) {
         num_steps[ray] = j;
