@@ -109,3 +109,44 @@ def test_schedule_values():
     assert math.isclose(lrs[500][0], 0.01, rel_tol=1e-6)
     assert math.isclose(lrs[999][0], 0.01 * gamma ** 499, rel_tol=1e-6)
     assert math.isclose(lrs[999][1], 0.001 * gamma ** 499, rel_tol=1e-6)
+
+
+@pytest.mark.parametrize("betas,eps", [((0.9, 0.99), 1e-15), ((0.9, 0.999), 1e-12)])
+def test_adam_restatement_matches_torch_cpu(betas, eps):
+    """oracle/adam.py (the arithmetic of csrc/optim.cu, operation by operation) against torch.optim.Adam on the host:
+    gradients over 12 decades with exact zeros, 12 steps."""
+    import numpy as np
+    from oracle import adam as oadam
+    g_ = torch.Generator().manual_seed(0)
+    p0 = torch.randn(5000, generator=g_)
+    p0[:100] *= 0.01
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([pt], lr=0.01, betas=betas, eps=eps, foreach=False)
+    p, m, v = p0.numpy().copy(), np.zeros(5000, np.float32), np.zeros(5000, np.float32)
+    for t in range(1, 13):
+        gr = torch.randn(5000, generator=g_) * 10.0 ** float(torch.randint(-9, 3, (1,), generator=g_))
+        gr = torch.where(torch.rand(5000, generator=g_) < 0.3, torch.zeros(()), gr)
+        pt.grad = gr.clone()
+        opt.step()
+        p, m, v = oadam.adam_step(p, gr.numpy(), m, v, t, 0.01, betas[0], betas[1], eps)
+        assert np.abs(p - pt.detach().numpy()).max() <= 5e-7            # a few ulps of |p| <= 4
+    st = opt.state[pt]
+    assert np.abs(m - st["exp_avg"].numpy()).max() <= 2e-7 * np.abs(m).max()
+    assert np.abs(v - st["exp_avg_sq"].numpy()).max() <= 2e-7 * np.abs(v).max()
+
+
+def test_masked_losses_equal_boolean_indexing():
+    """train.masked_mse / masked_l1 (no host sync) against `F.mse_loss(a[valid], b[valid])` of systems/neus.py:103."""
+    import torch.nn.functional as F
+    from rise_sdf_b200.train import masked_l1, masked_mse
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(1000, 3, generator=g).requires_grad_(True)
+    b = torch.randn(1000, 3, generator=g)
+    valid = torch.rand(1000, generator=g) < 0.6
+    for ours, ref in ((masked_mse, F.mse_loss), (masked_l1, F.l1_loss)):
+        x, y = ours(a, b, valid), ref(a[valid], b[valid])
+        assert abs(float(x) - float(y)) <= 1e-6 * abs(float(y))
+        gx, = torch.autograd.grad(x, a)
+        gy, = torch.autograd.grad(y, a)
+        assert float((gx - gy).abs().max()) <= 1e-8 and float(gx[~valid].abs().max()) == 0.0
+    assert torch.isnan(masked_mse(a, b, torch.zeros(1000, dtype=torch.bool)))      # mean of an empty selection
