@@ -40,10 +40,10 @@ def my_pixels(n_rays, rank, world):
     return slice(rank, n_rays, world)
 
 
-def balanced_tile(n_rays, world, max_tile=32768, per_rank=4):
-    """Tile size for a rank's shard of ceil(n_rays / world) rays: at most max_tile, at least per_rank tiles when the
-    shard is large enough, a multiple of 64, all tiles (almost) equal: 640 000 rays -> 32 000 on 1 GPU (20 tiles),
-    20 032 on 8 GPUs (4 tiles of the 80 000-ray shard)."""
+def balanced_tile(n_rays, world, max_tile=32768, per_rank=1):
+    """Tile size for a rank's shard of ceil(n_rays / world) rays: the fewest tiles of at most max_tile rays (every
+    tile pays ~25 host read-backs; interleaved pixels already balance the ranks), all (almost) equal, a multiple of
+    64: 640 000 rays -> 20 tiles of 32 000 on 1 GPU, 3 tiles of 26 688 for the 80 000-ray shard of 8 GPUs."""
     n = -(-n_rays // world)
     t = min(max_tile, -(-n // per_rank))
     t = -(-t // 64) * 64
