@@ -11,6 +11,7 @@ flat fp32 buffer each for parameters, gradients (the data-parallel exchange buck
 `rsdf_adam_step` launch (csrc/optim.cu; 28 B/parameter of HBM traffic) instead of a multi-tensor sweep, and
 the gradient bucket can be cleared in the same pass.  CUDA only: there is no CPU path.
 """
+import ctypes
 import math
 
 import torch
@@ -110,7 +111,6 @@ class FlatAdam(torch.optim.Optimizer):
         self._attach_grads()
         self._t += 1
         G = self._groups_struct(self._t)
-        import ctypes
         L.call("rsdf_adam_step", L.ptr(self.flat_p), L.ptr(self.bucket.flat), L.ptr(self.flat_m), L.ptr(self.flat_v),
                self.n, ctypes.addressof(G), int(self.zero_grad_in_step), L.stream())
         # the kernel wrote through raw pointers: tell autograd / the packed-weight caches

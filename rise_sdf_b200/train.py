@@ -6,7 +6,6 @@ GPUs -- the DDP-equivalent gradient exchange of launch.py:84-97: ONE flat fp32 b
 """
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 from .optim import FlatAdam
 
