@@ -189,9 +189,14 @@ def cuda_scalar_div(x, s):
     `scale_anything` (models/utils.py:109-114) feeds the hash-grid cell lookup, where one ulp
     of x01 moves the fine-level interpolation weights by ~1e-4, so the oracle follows the
     CUDA semantics here."""
-    if x.dtype == torch.float32:
+    if x.dtype == torch.float32 and CUDA_SCALAR_DIV:
         return x * float(np.float32(1.0) / np.float32(s))
     return x / s
+
+
+# True: follow the CUDA execution of `tensor / scalar` (what every product comparison needs).  tests/test_reference_host_cpu.py
+# clears it while it compares with the reference's Python running on the CPU, where the same line is a true division.
+CUDA_SCALAR_DIV = True
 
 
 def scale_to_unit(p, radius):

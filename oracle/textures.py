@@ -255,16 +255,17 @@ def specular_cubemap(cubemap, roughness, cutoff=0.99, bounds=None):
 
 
 def specular_cubemap_chunked(cubemap, roughness, c, bounds, chunk=512):
-    """Same filter for N = 64 (forward only): output texels processed `chunk` rows at a time."""
+    """Same filter for N = 64: output texels processed `chunk` rows at a time (the weights are constants of the
+    geometry, so every chunk is a differentiable `W_chunk @ cubemap`)."""
     N = cubemap.shape[1]
     D = texel_dirs(N).reshape(-1, 3).astype(np.float64)
     area = np.tile(pixel_area(N).reshape(-1), 6).astype(np.float64)
     xs = np.tile(np.tile(np.arange(N), N), 6); ys = np.tile(np.repeat(np.arange(N), N), 6)
     ss = np.repeat(np.arange(6), N * N)
     b = bounds.reshape(-1, 6, 4)
-    cube = cubemap.detach().double().reshape(-1, 3).numpy()
+    cube = cubemap.reshape(-1, 3)
     a2 = float(roughness) ** 4
-    out = np.zeros((len(D), 3))
+    out = []
     for p0 in range(0, len(D), chunk):
         V = D[p0:p0 + chunk]
         dp = V @ D.T
@@ -276,5 +277,6 @@ def specular_cubemap_chunked(cubemap, roughness, c, bounds, chunk=512):
         bx = b[p0:p0 + chunk][:, ss, :]
         inbox = (xs[None] >= bx[..., 0]) & (xs[None] <= bx[..., 1]) & (ys[None] >= bx[..., 2]) & (ys[None] <= bx[..., 3])
         W = W * (inbox & (dp >= np.float32(c)))
-        out[p0:p0 + chunk] = (W @ cube) / W.sum(1, keepdims=True)
-    return torch.from_numpy(out).to(cubemap.dtype).reshape(6, N, N, 3)
+        Wt = torch.from_numpy(W / W.sum(1, keepdims=True))
+        out.append((Wt @ cube.double()).to(cubemap.dtype))
+    return torch.cat(out).reshape(6, N, N, 3)

@@ -20,8 +20,13 @@ def main(out_dir):
     os.makedirs(out_dir, exist_ok=True)
     C = oref.nerfacc_cuda()
     assert C is not None, "build oracle/_ref first"
-    for kind, res, R, step in [("ball", 128, 1024, 1.732 * 3 / 1024), ("shell", 128, 1024, 1.732 * 3 / 1024),
-                               ("random", 32, 768, 0.01), ("ones", 16, 512, 1.732 * 3 / 128)]:
+    only = os.environ.get("RSDF_GOLDEN_ONLY")            # e.g. "ball_cone": regenerate one file
+    for kind, res, R, step, cone in [("ball", 128, 1024, 1.732 * 3 / 1024, 0.0), ("shell", 128, 1024, 1.732 * 3 / 1024, 0.0),
+                                     ("random", 32, 768, 0.01, 0.0), ("ones", 16, 512, 1.732 * 3 / 128, 0.0),
+                                     ("ball", 128, 512, 1.732 * 3 / 512, 0.004)]:
+        tag = kind + ("_cone" if cone else "")
+        if only and tag != only:
+            continue
         rays, _, _, _ = syn.training_rays(R, seed=21)
         sp_o = torch.tensor([[0, 0, -4], [0, 0, 0], [5, 5, 5], [0.3, -0.2, 0.1], [1.5, 0, -4]], dtype=torch.float32)
         sp_d = torch.tensor([[0, 0, 1], [0.6, 0.8, 0], [0, 0, 1], [0, 1, 0], [0, 0, 1]], dtype=torch.float32)
@@ -30,20 +35,20 @@ def main(out_dir):
         o, d = rays[:, :3].contiguous().cuda(), rays[:, 3:].contiguous().cuda()
         roi = torch.tensor(ROI, device="cuda")
         tmin, tmax = C.ray_aabb_intersect(o, d, roi)
-        pk, ri, ts, te = C.ray_marching(o, d, tmin, tmax, roi, grid.cuda(), C.ContractionType.AABB, float(np.float32(step)), 0.0)
+        pk, ri, ts, te = C.ray_marching(o, d, tmin, tmax, roi, grid.cuda(), C.ContractionType.AABB, float(np.float32(step)), float(cone))
         a = torch.rand(ri.shape[0], 1, device="cuda", generator=torch.Generator("cuda").manual_seed(1)) * 0.2
         w = C.weight_from_alpha_forward_naive(pk, a)
         T = C.transmittance_from_alpha_forward_naive(pk, a)
         gw = torch.randn_like(w)
         ga = C.weight_from_alpha_backward_naive(w, gw, pk, a)
         np.savez_compressed(
-            os.path.join(out_dir, f"march_{kind}.npz"), rays_o=o.cpu().numpy(), rays_d=d.cpu().numpy(),
+            os.path.join(out_dir, f"march_{tag}.npz"), cone=np.float32(cone), rays_o=o.cpu().numpy(), rays_d=d.cpu().numpy(),
             roi=np.array(ROI, np.float32), grid=grid.numpy(), step=np.float32(step), t_min=tmin.cpu().numpy(),
             t_max=tmax.cpu().numpy(), packed_info=pk.cpu().numpy(), ray_indices=ri.cpu().numpy(),
             t_starts=ts[:, 0].cpu().numpy(), t_ends=te[:, 0].cpu().numpy(), alphas=a[:, 0].cpu().numpy(),
             weights=w[:, 0].cpu().numpy(), trans=T[:, 0].cpu().numpy(), grad_weights=gw[:, 0].cpu().numpy(),
             grad_alphas=ga[:, 0].cpu().numpy())
-        print(kind, "rays", R, "samples", ri.shape[0])
+        print(tag, "rays", R, "samples", ri.shape[0])
 
 
 if __name__ == "__main__":

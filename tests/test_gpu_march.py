@@ -42,24 +42,44 @@ def bits(a):
     return a.view(np.uint32)
 
 
-def run_ours(rays, grid, step, use_bits=True, near=None, far=None):
+SPAN = 3.0 * 3 ** 0.5          # AABB diagonal: the host-side bound `OccGridEstimator.sampling` passes to `_march`
+PATHS = ["warp", "thread"]     # the hot path (march_warp_kernel: rsdf_march_count_keep + rsdf_march_compact) and the
+                               # reference-ordered two-round march (march_kernel: rsdf_march_count + rsdf_march_fill)
+
+
+def run_ours(rays, grid, step, use_bits=True, path="warp", cone=0.0, calls=None):
+    """`path="warp"` passes the span, so the kernel compared is the one `sampling()` launches on the render path."""
     dev = "cuda"
     o, d = rays[:, :3].contiguous().to(dev), rays[:, 3:].contiguous().to(dev)
     g = grid.to(dev).contiguous()
     tmin, tmax = rn.ray_aabb_intersect(o, d, torch.tensor(ROI))
     gb = rn.pack_bits(g) if use_bits else None
-    packed, ri, ts, te = rn._march(o, d, tmin, tmax, L.host6(ROI), g, gb, step, 0.0)
+    real = L.call
+    seen = []
+    L.call = lambda name, *a: (seen.append(name), real(name, *a))[1]
+    try:
+        packed, ri, ts, te = rn._march(o, d, tmin, tmax, L.host6(ROI), g, gb, step, cone,
+                                       SPAN if path == "warp" else None)
+    finally:
+        L.call = real
+    if path == "warp":          # the warp kernel really ran, and (no overflow at this span) the copy round, not a re-march
+        assert "rsdf_march_count_keep" in seen and "rsdf_march_fill" not in seen, seen
+    else:
+        assert "rsdf_march_count" in seen and "rsdf_march_count_keep" not in seen, seen
+    if calls is not None:
+        calls.extend(seen)
     return [t.cpu().numpy() for t in (tmin, tmax, packed, ri, ts, te)]
 
 
 @pytest.mark.parametrize("kind", ["ball", "shell", "ones", "zeros", "voxel", "random"])
 @pytest.mark.parametrize("R", [1, 4096])
 @pytest.mark.parametrize("use_bits", [True, False])
-def test_march_bit_exact_vs_oracle(kind, R, use_bits):
+@pytest.mark.parametrize("path", PATHS)
+def test_march_bit_exact_vs_oracle(kind, R, use_bits, path):
     rays = rays_for(R)
     grid = syn.analytic_grid(kind)
     step = 1.732 * 2 * 1.5 / (128 if kind == "ones" else 1024)
-    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step, use_bits)
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step, use_bits, path)
     o, d = rays[:, :3].numpy(), rays[:, 3:].numpy()
     otmin, otmax = omarch.ray_aabb_intersect(o, d, np.array(ROI, np.float32))
     assert np.array_equal(bits(tmin), bits(otmin)) and np.array_equal(bits(tmax), bits(otmax))
@@ -147,31 +167,55 @@ def test_front_to_back_visibility_equals_one_shot(chunks, monkeypatch):
 
 
 @pytest.mark.parametrize("kind", ["ball", "shell", "random"])
-def test_march_bit_exact_vs_reference_kernel(kind):
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("cone", [0.0, 0.004])
+def test_march_bit_exact_vs_reference_kernel(kind, path, cone):
+    """Both of our kernels against the reference's compiled `ray_marching` (lib/nerfacc/cuda/csrc/ray_marching.cu:81-192),
+    with cone_angle = 0 (both configs) and cone_angle > 0 (dt grows with t: march_warp_kernel<false>)."""
     C = oref.nerfacc_cuda()
     if C is None:
         pytest.skip("oracle/_ref/nerfacc_cuda.so not built")
     rays = rays_for(8192, seed=5)
     grid = syn.analytic_grid(kind)
     step = 1.732 * 2 * 1.5 / 1024
-    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step)
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step, path=path, cone=cone)
     o, d = rays[:, :3].contiguous().cuda(), rays[:, 3:].contiguous().cuda()
     roi = torch.tensor(ROI, device="cuda")
     rtmin, rtmax = C.ray_aabb_intersect(o, d, roi)
     assert np.array_equal(bits(tmin), bits(rtmin.cpu().numpy()))
     assert np.array_equal(bits(tmax), bits(rtmax.cpu().numpy()))
-    rp, rri, rts, rte = C.ray_marching(o, d, rtmin, rtmax, roi, grid.cuda(), C.ContractionType.AABB, step, 0.0)
+    rp, rri, rts, rte = C.ray_marching(o, d, rtmin, rtmax, roi, grid.cuda(), C.ContractionType.AABB, step, cone)
     assert np.array_equal(packed, rp.cpu().numpy())
     assert np.array_equal(ri, rri.cpu().numpy())
     assert np.array_equal(bits(ts), bits(rts[:, 0].cpu().numpy()))
     assert np.array_equal(bits(te), bits(rte[:, 0].cpu().numpy()))
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "march_*.npz"))))
-def test_march_vs_golden(path):
-    z = np.load(path)
+@pytest.mark.parametrize("kind", ["ball", "shell", "random", "ones"])
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("cone", [0.003, 0.02])
+def test_march_cone_angle_vs_oracle(kind, path, cone):
+    """cone_angle > 0 (`dt = clamp(t * cone, step, 1e10)`, ray_marching.cu:121-125,165-176): never taken by the two
+    configs, but part of the `ray_marching` / `sampling` signature -> both kernels against the C oracle."""
+    rays = rays_for(2048, seed=17)
+    grid = syn.analytic_grid(kind)
+    step = 1.732 * 2 * 1.5 / (128 if kind == "ones" else 512)
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step, path=path, cone=cone)
+    o, d = rays[:, :3].numpy(), rays[:, 3:].numpy()
+    pk, ori, ots, ote = omarch.ray_marching_raw(o, d, tmin, tmax, np.array(ROI, np.float32), grid.numpy(), step, cone)
+    assert np.array_equal(packed, pk) and np.array_equal(ri, ori)
+    assert np.array_equal(bits(ts), bits(ots)) and np.array_equal(bits(te), bits(ote))
+    if len(ts):
+        assert float((te - ts).max()) > step * 1.5      # the cone really widened the far intervals
+
+
+@pytest.mark.parametrize("gold", sorted(glob.glob(os.path.join(GOLD, "march_*.npz"))))
+@pytest.mark.parametrize("path", PATHS)
+def test_march_vs_golden(gold, path):
+    z = np.load(gold)
     rays = torch.from_numpy(np.concatenate([z["rays_o"], z["rays_d"]], 1))
-    tmin, tmax, packed, ri, ts, te = run_ours(rays, torch.from_numpy(z["grid"]), float(z["step"]))
+    cone = float(z["cone"]) if "cone" in z else 0.0
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, torch.from_numpy(z["grid"]), float(z["step"]), path=path, cone=cone)
     assert np.array_equal(packed, z["packed_info"]) and np.array_equal(ri, z["ray_indices"])
     assert np.array_equal(bits(ts), bits(z["t_starts"])) and np.array_equal(bits(te), bits(z["t_ends"]))
 
@@ -181,7 +225,10 @@ def test_frame_sized_march_properties():
     rays = syn.frame_rays(3)
     grid = syn.analytic_grid("ball")
     step = 1.732 * 2 * 1.5 / 1024
-    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step)
+    tmin, tmax, packed, ri, ts, te = run_ours(rays, grid, step, path="thread")
+    warp = run_ours(rays[::8], grid, step, path="warp")      # (the keep scratch of a whole frame exceeds its budget)
+    sel = np.arange(0, len(rays), 8)
+    assert np.array_equal(warp[2][:, 1], packed[sel, 1])
     assert packed[:, 1].sum() == len(ri) and packed[-1, 0] + packed[-1, 1] == len(ri)
     assert np.all(np.diff(ri) >= 0)
     assert np.array_equal(packed[:, 0], np.concatenate([[0], np.cumsum(packed[:-1, 1])]))

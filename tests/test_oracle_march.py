@@ -107,7 +107,7 @@ def test_oracle_vs_reference_golden(path):
     ga = march.weight_from_alpha_backward(z["packed_info"], z["alphas"], w, z["grad_weights"])
     np.testing.assert_allclose(ga, z["grad_alphas"], rtol=1e-5, atol=1e-6)
     pk, ri, ts, te = march.ray_marching_raw(z["rays_o"], z["rays_d"], z["t_min"], z["t_max"], z["roi"],
-                                            z["grid"], float(z["step"]), 0.0)
+                                            z["grid"], float(z["step"]), float(z["cone"]) if "cone" in z else 0.0)
     assert np.array_equal(pk, z["packed_info"])
     assert np.array_equal(ri, z["ray_indices"])
     assert np.array_equal(ts.view(np.uint32), z["t_starts"].view(np.uint32))
