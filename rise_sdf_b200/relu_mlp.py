@@ -73,8 +73,13 @@ class _ReluMLP(torch.autograd.Function):
         return out
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, g_out):
+        if torch.is_grad_enabled():
+            # `once_differentiable` only raises when the cotangent requires grad and otherwise hands back constants:
+            # a caller differentiating through this backward (create_graph=True) would silently lose terms.  Nothing
+            # on the render path does (the texture nets are first order), so refuse loudly.
+            raise NotImplementedError("relu_mlp is first-order only: VanillaMLP.fused_training = False routes the "
+                                      "network through the twice-differentiable GEMM primitives (tc_autograd)")
         params = ctx.saved_tensors
         Ws, bs = params[0::2], params[1::2]
         S, dev = ctx.S, g_out.device

@@ -71,7 +71,7 @@ class _FusedSDF(torch.autograd.Function):
             L.call("rsdf_sdf_mlp_fwd", ctypes.byref(net), L.ptr(in0), w0, float(scale0), float(shift0), L.ptr(in1), w1,
                    S, L.ptr(out), L.ptr(sdf), L.ptr(g0a), L.ptr(g0b), L.stream())
         ctx.save_for_backward(in0, in1, W1, b1, W2, b2, W3, b3)
-        ctx.net, ctx.keep, ctx.scale0, ctx.shift0 = net, keep, float(scale0), float(shift0)
+        ctx.net, ctx.keep, ctx.scale0, ctx.shift0, ctx.want_g0 = net, keep, float(scale0), float(shift0), bool(want_g0)
         empty = []
         if g0a is None:
             g0a = in0.new_zeros(0); empty.append(g0a)
@@ -82,8 +82,58 @@ class _FusedSDF(torch.autograd.Function):
         return out, sdf, g0a, g0b
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
+    def _backward_twice_differentiable(ctx, g_out, g_sdf, g_g0a, g_g0b):
+        """The backward under `create_graph=True`: the curvature probe of models/geometry.py:246-282 takes
+        `autograd.grad(sdf_t, points_t, create_graph=True)` through this node and then differentiates that gradient
+        again (w.r.t. the weights AND the probe position), which the one-kernel backward cannot offer.  The same
+        quantities are rebuilt here from differentiable primitives -- tcgen05 streaming GEMMs that are closed under
+        differentiation (tc_autograd) + torch elementwise ops -- so that autograd can recurse as it does through the
+        reference's nn.Linear stack.  (`once_differentiable` would not do: it only raises when a COTANGENT requires
+        grad, and silently returns constants for the `ones_like(sdf)` cotangent of the probe.)"""
+        import torch.nn.functional as F
+
+        from . import tc_autograd as tca
+        in0, in1, W1, b1, W2, b2, W3, b3 = ctx.saved_tensors
+        w0 = in0.shape[1]
+        with torch.enable_grad():
+            h0 = in0 * ctx.scale0 + ctx.shift0
+            if in1 is not None:
+                h0 = torch.cat([h0, in1], -1)
+            z1 = tca.linear(h0, W1, b1)
+            a1 = F.softplus(z1, beta=100)
+            z2 = tca.linear(a1, W2, b2)
+            a2 = F.softplus(z2, beta=100)
+            out = tca.linear(a2, W3, b3)
+            outs, cots = [], []
+            if g_out is not None:
+                outs.append(out); cots.append(g_out)
+            if g_sdf is not None:
+                outs.append(out[:, 0]); cots.append(g_sdf)
+            has_a = g_g0a is not None and g_g0a.numel() > 0
+            has_b = g_g0b is not None and g_g0b.numel() > 0
+            if ctx.want_g0 and (has_a or has_b):
+                # softplus' with torch's threshold rule (aten softplus_backward): sigmoid(beta z), 1 above beta z = 20
+                sp1 = torch.where(z1 * 100.0 > 20.0, torch.ones_like(z1), torch.sigmoid(z1 * 100.0))
+                sp2 = torch.where(z2 * 100.0 > 20.0, torch.ones_like(z2), torch.sigmoid(z2 * 100.0))
+                u1 = sp1 * tca.mm_nn(sp2 * W3[0], W2)
+                g0 = tca.mm_nn(u1, W1)
+                if has_a:
+                    outs.append(g0[:, :w0]); cots.append(g_g0a)
+                if has_b:
+                    outs.append(g0[:, w0:]); cots.append(g_g0b)
+            tensors = (in0, in1, W1, b1, W2, b2, W3, b3)
+            idx = [i for i, t in enumerate(tensors) if t is not None and ctx.needs_input_grad[i] and t.requires_grad]
+            grads = [None] * 8
+            if outs and idx:
+                got = torch.autograd.grad(outs, [tensors[i] for i in idx], cots, create_graph=True, allow_unused=True)
+                for i, g in zip(idx, got):
+                    grads[i] = g
+        return (*grads, None, None, None)
+
+    @staticmethod
     def backward(ctx, g_out, g_sdf, g_g0a, g_g0b):
+        if torch.is_grad_enabled():            # create_graph=True: the caller differentiates this backward again
+            return _FusedSDF._backward_twice_differentiable(ctx, g_out, g_sdf, g_g0a, g_g0b)
         in0, in1, W1, b1, W2, b2, W3, b3 = ctx.saved_tensors
         S, w0 = in0.shape
         w1 = 0 if in1 is None else in1.shape[1]

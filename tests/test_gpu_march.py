@@ -205,7 +205,7 @@ def test_march_cone_angle_vs_oracle(kind, path, cone):
     pk, ori, ots, ote = omarch.ray_marching_raw(o, d, tmin, tmax, np.array(ROI, np.float32), grid.numpy(), step, cone)
     assert np.array_equal(packed, pk) and np.array_equal(ri, ori)
     assert np.array_equal(bits(ts), bits(ots)) and np.array_equal(bits(te), bits(ote))
-    if len(ts):
+    if len(ts) and cone >= 0.02:
         assert float((te - ts).max()) > step * 1.5      # the cone really widened the far intervals
 
 

@@ -1,0 +1,200 @@
+"""The drop-in claim, exercised: the reference's OWN host code -- models/neus.py, models/split_mixed_occ.py,
+models/geometry.py, models/texture.py, models/network_utils.py, models/volrend.py, lib/pbr/light.py, imported
+UNMODIFIED from the reference tree -- runs on librsdf_b200.so through the shims named after its third-party imports
+(`nerfacc`, `lib.nerfacc`, `tinycudann`, `nvdiffrast.torch`, `lib.renderutils`), loads the
+same state_dict as the repo's host mirrors and produces the same images and gradients.
+
+Needs the reference tree next to the GPU: the driver's GPU box does not carry /root/reference, so there these tests
+skip (the same facts travel as tests/test_reference_host_cpu.py + tests/golden/).  `scripts/gpu_reference_host.sh`
+ships a scratch copy of the tree with one gpurun call, runs this file and removes the copy; its log is committed as
+profiles/reference_host_r02.txt.
+
+What differs between the two sides is only the MLP arithmetic -- the reference's VanillaMLP is nn.Linear (cuBLAS
+SGEMM) under torch autograd, the mirrors run the tcgen05 kernels -- so the bounds are fp32-vs-fp32 ones.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+from helpers import rel_l2  # noqa: E402
+from oracle import ref_host  # noqa: E402
+from rise_sdf_b200 import synthetic as syn  # noqa: E402
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(ref_host.reference_root() is None, reason="reference tree not present on this box")]
+
+
+def _neus_pair(models):
+    from rise_sdf_b200.neus import NeuSModel, neus_blender_config
+    torch.manual_seed(0)
+    ours = NeuSModel(neus_blender_config()).cuda()
+    with torch.no_grad():
+        ours.geometry.encoding.encoding.params.uniform_(-0.05, 0.05)
+        ours.geometry.network.layers[0].weight_v[:, 3:].normal_(0.0, 0.05)
+    ref = models.make("neus", ref_host.ref_config(neus_blender_config())).cuda()
+    # models/neus.py:57 leaves contraction_type unset (commented out; "assigned in system", which no system does)
+    ref.geometry.contraction_type = sys.modules["models.geometry"].ContractionType.AABB
+    missing, unexpected = ref.load_state_dict(ours.state_dict(), strict=False)
+    assert not unexpected and not [k for k in missing if "occupancy_grid" not in k], (missing, unexpected)
+    for mdl in (ours, ref):
+        mdl.occupancy_grid.binaries = syn.analytic_grid("ball")[None].cuda()
+        mdl.render_step_size = 1.732 * 2 * 1.5 / 256
+        mdl.cos_anneal_ratio = 0.37
+    return ours, ref
+
+
+def test_reference_neus_on_the_shims_equals_the_mirror():
+    """configs[1] shape at 256 rays: forward + every loss + all parameter gradients."""
+    from rise_sdf_b200.train import neus_loss
+    with ref_host.reference_modules("product") as models:
+        ours, ref = _neus_pair(models)
+        rays, rgb, fg, bg = (t.cuda() for t in syn.training_rays(256, seed=2))
+        outs = []
+        for mdl in (ours, ref):
+            mdl.train()
+            mdl.randomized = False
+            mdl.background_color = bg
+            out = mdl(rays)
+            loss, parts = neus_loss(out, rgb, fg)
+            loss.backward()
+            outs.append((out, loss, parts))
+        (a, la, pa), (b, lb, pb) = outs
+        assert int(a["num_samples"]) == int(b["num_samples"]) > 5000
+        assert torch.equal(a["ray_indices"], b["ray_indices"])          # bit-exact sample set
+        for k in ("comp_rgb", "comp_normal", "opacity", "depth", "comp_rgb_full", "sdf_samples", "sdf_grad_samples", "weights"):
+            e = float((a[k] - b[k]).abs().max())
+            assert e <= 1e-5 * max(float(b[k].abs().max()), 1.0), (k, e)
+        assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
+        report = []
+        for (n1, p1), (n2, p2) in zip(sorted(ours.named_parameters()), sorted(ref.named_parameters())):
+            assert n1 == n2
+            if p1.numel() == 0:
+                continue
+            e = rel_l2(p1.grad.cpu().numpy(), p2.grad.cpu().numpy())
+            report.append(f"{n1}: {e:.2e}")
+            assert e <= 1e-4, (n1, e)
+        print("\n".join(report))
+
+
+def test_reference_neus_eval_and_occupancy_update_on_the_shims():
+    """models/neus.py:319-327 (chunk_batch, .cpu() per chunk) and :90-122 (update_step -> update_every_n_steps)."""
+    with ref_host.reference_modules("product") as models:
+        ours, ref = _neus_pair(models)
+        rays, _, _, bg = (t.cuda() for t in syn.training_rays(5000, seed=5))
+        jit = torch.rand(128 ** 3, 3, generator=torch.Generator().manual_seed(9)).cuda()
+        res = []
+        for mdl in (ours, ref):
+            mdl.train()
+            real = torch.rand_like
+            torch.rand_like = lambda x, *a, **k: jit if x.shape == jit.shape else real(x, *a, **k)
+            try:
+                mdl.update_step(0, 0)                       # warm-up branch: all 128^3 cells through occ_eval_fn
+            finally:
+                torch.rand_like = real
+            mdl.eval()
+            mdl.background_color = bg
+            with torch.no_grad():
+                res.append(mdl(rays))
+        assert int((ours.occupancy_grid.binaries != ref.occupancy_grid.binaries).sum()) <= 16   # cells AT the threshold
+        ref.occupancy_grid.binaries = ours.occupancy_grid.binaries.clone()
+        with torch.no_grad():
+            res[1] = ref(rays)
+        a, b = res
+        assert int(a["num_samples"].sum()) == int(b["num_samples"].sum())
+        for k in ("comp_rgb", "opacity", "depth", "comp_rgb_full"):
+            assert not a[k].is_cuda and not b[k].is_cuda                 # chunk_batch(move_to_cpu=True)
+            e = float((a[k] - b[k]).abs().max())
+            assert e <= 2e-5 * max(float(b[k].abs().max()), 1.0), (k, e)
+
+
+def _split_pair(models, base_res=512):
+    from rise_sdf_b200.split_mixed_occ import SplitMixedOCCModel, split_mixed_occ_config
+    torch.manual_seed(0)
+    cfg = split_mixed_occ_config()
+    cfg["light"]["envlight_config"]["base_res"] = base_res
+    ours = SplitMixedOCCModel(cfg).cuda()
+    with torch.no_grad():
+        ours.geometry.network.layers[0].weight_v[:, 3:].normal_(0.0, 0.05)
+        ours.variance.variance.fill_(0.5)
+        ours.geometry.encoding.encoding.encoding.params.uniform_(-0.02, 0.02)
+    ref_host.write_bsdf_lut(ours.texture.FG_LUT)
+    ref = models.make("split-mixed-occ", ref_host.ref_config(cfg)).cuda()
+    missing, unexpected = ref.load_state_dict(ours.state_dict(), strict=False)
+    assert not unexpected and not [k for k in missing if "occupancy_grid" not in k], (missing, unexpected)
+    assert torch.equal(ref.emitter.base, ours.emitter.base) and torch.equal(ref.texture.FG_LUT, ours.texture.FG_LUT)
+    for mdl in (ours, ref):
+        mdl.eval()
+        mdl.update_step(0, 20000)
+        assert mdl.stage == 1
+        mdl.occupancy_grid.binaries = syn.analytic_grid("ball")[None].cuda()
+        mdl.render_step_size = 1.732 * 2 * 1.5 / 256
+    return ours, ref
+
+
+@pytest.mark.parametrize("relighting", [False, True])
+def test_reference_split_eval_on_the_shims_equals_the_mirror(relighting):
+    """configs[3] shape: the mirror (fused tcgen05 inference kernels, survivors gathered from the visibility pass) vs
+    the reference's forward_ (nn.Linear, field evaluated again).  Finite-difference normals: fp32-vs-fp32 bound."""
+    with ref_host.reference_modules("product") as models:
+        ours, ref = _split_pair(models)
+        rays, _, _, bg = (t.cuda() for t in syn.training_rays(256, seed=3))
+        res = []
+        for mdl in (ours, ref):
+            mdl.background_color = bg
+            with torch.no_grad():
+                mdl.emitter.build_mips()
+                res.append(mdl(rays, relighting))
+        for x, y in zip(ours.emitter.specular + [ours.emitter.diffuse], ref.emitter.specular + [ref.emitter.diffuse]):
+            assert torch.equal(x, y)                                       # same kernels through lib.renderutils
+        a, b = res
+        assert abs(int(a["num_samples"].sum()) - int(b["num_samples"].sum())) <= 4
+        report = []
+        for k in ("comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic", "comp_rgb",
+                  "comp_rgb_phys", "comp_rgb_full", "comp_rgb_phys_full"):
+            e = (a[k] - b[k]).abs().max(-1).values
+            report.append(f"{k}: mean {float(e.mean()):.1e} p99 {float(torch.quantile(e, 0.99)):.1e} max {float(e.max()):.1e}")
+            assert float(e.mean()) <= 1e-3 and float(torch.quantile(e, 0.99)) <= 2e-2, report[-1]
+        print("\n".join(report))
+
+
+def test_reference_split_training_step_on_the_shims_equals_the_mirror():
+    """configs[2] shape at 256 rays: curvature probe (double backward through the hash grid shim and cuBLAS on the
+    reference side), reflection bounce, build_mips with the learnable 512^2 base, all losses, all gradients."""
+    from rise_sdf_b200.train import split_loss
+    with ref_host.reference_modules("product") as models:
+        ours, ref = _split_pair(models)
+        rays, rgb, fg, bg = (t.cuda() for t in syn.training_rays(256, seed=4))
+        res = []
+        for mdl in (ours, ref):
+            mdl.train()
+            mdl.randomized = False
+            mdl.background_color = bg
+            torch.manual_seed(11)
+            torch.cuda.manual_seed(11)                       # the curvature probe's random tangents: same draw
+            mdl.emitter.build_mips()
+            out = mdl(rays)
+            loss, parts = split_loss(mdl, out, rgb, fg)
+            loss.backward()
+            res.append((out, loss, parts))
+        (a, la, pa), (b, lb, pb) = res
+        assert torch.equal(a["ray_indices"], b["ray_indices"]) or abs(len(a["ray_indices"]) - len(b["ray_indices"])) <= 4
+        report = [f"loss {float(la):.6f} vs {float(lb):.6f}"]
+        for k in pb:
+            report.append(f"loss.{k}: {float(pa[k]):.6e} vs {float(pb[k]):.6e}")
+            assert abs(float(pa[k]) - float(pb[k])) <= 2e-3 * max(abs(float(pb[k])), 1e-3), report[-1]
+        g1 = dict(ours.named_parameters()); g1["emitter.base"] = ours.emitter.base
+        g2 = dict(ref.named_parameters()); g2["emitter.base"] = ref.emitter.base
+        for n in sorted(g1):
+            if g1[n].numel() == 0:
+                continue
+            assert g2[n].grad is not None and g1[n].grad is not None, n
+            e = rel_l2(g1[n].grad.cpu().numpy(), g2[n].grad.cpu().numpy())
+            report.append(f"grad {n}: rel-L2 {e:.2e}")
+        print("\n".join(report))
+        for line in report:
+            if line.startswith("grad "):
+                assert float(line.split()[-1]) <= 5e-2, line   # fp32 FD normals on both sides (see test_gpu_split_grads for the fp64 yardstick)

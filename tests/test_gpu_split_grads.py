@@ -1,0 +1,167 @@
+"""configs[2] training-step parity (systems/split_occ.py:150-237, models/split_mixed_occ.py:224-443): one
+split-mixed-occ training step at stage 1 with the full-size environment light (base_res 512), finite-difference normals
++ curvature probe, reflection bounce, every loss term -- loss parts and the gradient of EVERY parameter group
+(hash table, SDF net, the five texture nets, `variance`, `emitter.base`) against oracle/split.py evaluated in float64
+(the yardstick; oracle/split.py itself is pinned to the reference's Python by tests/test_reference_host_cpu.py).
+
+Tolerances are derived IN THE TEST from an fp32 twin of the oracle: finite-difference normals amplify the fp32 rounding
+of the SDF by 1/(2 eps) ~ 1400, so any fp32 evaluation -- the reference's own included -- sits a measurable distance
+from the fp64 value; `floor` below is that distance for the CPU fp32 oracle, and the product must stay within
+max(1e-3, 3 x floor) per quantity.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+from helpers import rel_l2, split_oracle_params  # noqa: E402
+from oracle import ref as oref  # noqa: E402
+from oracle import split as osplit  # noqa: E402
+from oracle import textures as otx  # noqa: E402
+from rise_sdf_b200 import synthetic as syn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def split_model(base_res=512, seed=0):
+    from rise_sdf_b200.split_mixed_occ import SplitMixedOCCModel, split_mixed_occ_config
+    torch.manual_seed(seed)
+    cfg = split_mixed_occ_config()
+    cfg["light"]["envlight_config"]["base_res"] = base_res
+    m = SplitMixedOCCModel(cfg).cuda()
+    with torch.no_grad():
+        m.geometry.network.layers[0].weight_v[:, 3:].normal_(0.0, 0.05)
+        m.variance.variance.fill_(0.5)
+        m.geometry.encoding.encoding.encoding.params.uniform_(-0.02, 0.02)
+    m.eval()
+    m.update_step(0, 20000)              # schedule only (eval: no occupancy update): stage 1, all levels on, progressive eps
+    assert m.stage == 1
+    m.occupancy_grid.binaries = syn.analytic_grid("ball")[None].cuda()
+    m.render_step_size = 1.732 * 2 * 1.5 / 256
+    return m
+
+
+def reference_base_grad(base, level_grads, diffuse_grad):
+    """d loss / d emitter.base from the gradients at the prefiltered levels, chained through the REFERENCE's own
+    compiled prefilter backward kernels (oracle/_ref/renderutils_plugin.so: lib/renderutils/c_src/cubemap.cu:139-169,
+    302-350) and the reference's cubemap_mip backward (lib/pbr/utils/light_utils.py:99-109, restated in oracle/split.py).
+    Returns None when the plugin was not built."""
+    P = oref.renderutils_plugin()
+    if P is None:
+        return None
+    from rise_sdf_b200 import renderutils as ru
+    inputs = [base.detach().float().cuda()]
+    while inputs[-1].shape[1] > 16:
+        x = inputs[-1].permute(0, 3, 1, 2)
+        inputs.append(torch.nn.functional.avg_pool2d(x, (2, 2)).permute(0, 2, 3, 1).contiguous())
+    n = len(inputs)
+    rough = [(i / (n - 2)) * (0.5 - 0.08) + 0.08 for i in range(n - 1)] + [1.0]
+    G = None
+    for i in range(n - 1, -1, -1):
+        N = inputs[i].shape[1]
+        cut = ru.ndf_cutoff(rough[i], 0.99)
+        bounds = P.specular_bounds(N, cut)
+        raw = P.specular_cubemap_fwd(inputs[i], bounds, rough[i], cut)
+        go = level_grads[i].float().cuda()
+        g4 = torch.cat([go / raw[..., 3:], torch.zeros(6, N, N, 1, device="cuda")], -1).contiguous()
+        g = P.specular_cubemap_bwd(inputs[i], bounds, g4, rough[i], cut)
+        if i == n - 1:
+            g = g + P.diffuse_cubemap_bwd(inputs[i], diffuse_grad.float().cuda().contiguous())
+        else:
+            g = g + osplit._CubemapMip.backward(None, G.cpu().double()).float().cuda()
+        G = g
+    return G.cpu()
+
+
+def test_split_train_step_grads():
+    from rise_sdf_b200.train import split_loss
+    m = split_model(512).train()
+    m.randomized = False
+    rays, rgb, fg, bg = syn.training_rays(256, seed=4)
+    m.background_color = bg.cuda()
+    grid = syn.analytic_grid("ball")
+    dirs, real = [], torch.rand_like
+    torch.rand_like = lambda x, *a, **k: (dirs.append(real(x, *a, **k)), dirs[-1])[1]
+    try:
+        m.emitter.build_mips()
+        for t in m.emitter.specular + [m.emitter.diffuse]:
+            t.retain_grad()
+        out = m(rays.cuda())
+    finally:
+        torch.rand_like = real
+    loss, parts = split_loss(m, out, rgb.cuda(), fg.cuda())
+    loss.backward()
+    S = int(out["num_samples"])
+    assert len(dirs) == 1 and dirs[0].shape == (S, 3) and S > 1000
+    # the product's own sample set (deterministic: no stratified jitter), so that both sides differentiate the same samples
+    with torch.no_grad():
+        ro, rd = rays[:, :3].contiguous().cuda(), rays[:, 3:].contiguous().cuda()
+        ri, ts, te = m.occupancy_grid.sampling(ro, rd, alpha_fn=m._alpha_fn(ro, rd), render_step_size=m.render_step_size,
+                                               stratified=False)
+    assert torch.equal(ri, out["ray_indices"])
+    samples = (ri.cpu(), ts.cpu(), te.cpu())
+
+    def oracle(dtype):
+        P = split_oracle_params(m).to(dtype)
+        P.specular = [t.detach().cpu().to(dtype).clone() for t in m.emitter.specular]
+        P.diffuse = m.emitter.diffuse.detach().cpu().to(dtype).clone()
+        leaves = dict(P.named_tensors())
+        del leaves["emitter.base"]                          # the levels are the leaves here; base is chained below
+        leaves.update({f"specular.{i}": t for i, t in enumerate(P.specular)}, diffuse=P.diffuse)
+        for t in leaves.values():
+            t.requires_grad_(True)
+        ref = osplit.forward_train(P, rays, grid.numpy(), m.render_step_size, dirs[0].cpu(), stage=1, background=bg,
+                                   dtype=dtype, samples=samples)
+        rl, rp = osplit.loss(ref, rgb, fg, stage=1)
+        rl.backward()
+        return ref, rl, rp, {k: t.grad for k, t in leaves.items()}
+
+    ref, rloss, rparts, g64 = oracle(torch.float64)
+    _, loss32, parts32, g32 = oracle(torch.float32)
+    named = dict(m.named_parameters())
+    got = {k: named[k].grad for k in g64 if k in named}
+    got.update({f"specular.{i}": t.grad for i, t in enumerate(m.emitter.specular)}, diffuse=m.emitter.diffuse.grad)
+    assert set(got) == set(g64)
+
+    report, bad = [], []
+    for k in sorted(rparts):
+        floor = abs(float(parts32[k]) - float(rparts[k]))
+        err = abs(float(parts[k]) - float(rparts[k]))
+        tol = max(2e-4 * max(abs(float(rparts[k])), 1e-3), 3 * floor)
+        report.append(f"loss.{k}: {float(parts[k]):.6e} err {err:.2e} (fp32-oracle floor {floor:.2e})")
+        if err > tol:
+            bad.append(report[-1])
+    for k in sorted(g64):
+        r = g64[k].numpy()
+        if np.abs(r).sum() == 0:           # e.g. the fine pyramid levels: random-init roughness ~ 0.5 only touches levels 3-5
+            assert got[k] is None or float(got[k].abs().sum()) == 0, k
+            report.append(f"grad {k}: zero on both sides")
+            continue
+        assert got[k] is not None, k
+        floor = rel_l2(g32[k].numpy(), r)
+        err = rel_l2(got[k].cpu().numpy(), r)
+        report.append(f"grad {k}: rel-L2 {err:.2e} (fp32-oracle floor {floor:.2e})")
+        if err > max(1e-3, 3 * floor):
+            bad.append(report[-1])
+    print("\n".join(report))
+    assert not bad, bad
+
+    # emitter.base = the level gradients (checked above against the fp64 yardstick, at its fp32 noise floor) chained
+    # through build_mips.  The chain itself is checked tightly: the product's OWN level gradients pushed through the
+    # reference's compiled prefilter backward kernels + the reference's cubemap_mip backward must give the product's
+    # base gradient; with the fp64 oracle's level gradients it must agree within that same noise floor.
+    lv = [t.grad if t.grad is not None else torch.zeros_like(t) for t in m.emitter.specular]
+    gb = reference_base_grad(m.emitter.base, [t.detach().cpu().double() for t in lv], m.emitter.diffuse.grad.cpu().double())
+    if gb is None:
+        pytest.skip("oracle/_ref/renderutils_plugin.so not built: emitter.base chain not checked (level grads were)")
+    err = rel_l2(m.emitter.base.grad.cpu().numpy(), gb.numpy())
+    print(f"grad emitter.base, chain only (512^2, product level grads through the reference's prefilter backward): rel-L2 {err:.2e}")
+    assert err <= 1e-3, err
+    gb64 = reference_base_grad(m.emitter.base, [g64[f"specular.{i}"] for i in range(len(m.emitter.specular))], g64["diffuse"])
+    err64 = rel_l2(m.emitter.base.grad.cpu().numpy(), gb64.numpy())
+    floor = max(rel_l2(g32[k].numpy(), g64[k].numpy()) for k in ("specular.3", "specular.4", "specular.5", "diffuse"))
+    print(f"grad emitter.base vs fp64 level grads: rel-L2 {err64:.2e} (level-gradient floor {floor:.2e})")
+    assert err64 <= max(1e-3, 3 * floor), (err64, floor)

@@ -169,7 +169,7 @@ def test_specular_cubemap_vs_reference(N, roughness):
 
 
 # ------------------------------------------------------------------ end-to-end split-sum render
-def _split_model(base_res=64):
+def _split_model(base_res=64, seed=0):
     from rise_sdf_b200.split_mixed_occ import SplitMixedOCCModel, split_mixed_occ_config
     torch.manual_seed(0)
     cfg = split_mixed_occ_config()
@@ -182,19 +182,37 @@ def _split_model(base_res=64):
     return m
 
 
+def _sample_set_difference(m, rays, ref, keep):
+    """Samples the product keeps and the fp64 oracle drops (or vice versa), with the oracle's transmittance at each."""
+    from oracle import fields as ofields
+    ro, rd = rays[:, :3].contiguous().cuda(), rays[:, 3:].contiguous().cuda()
+    with torch.no_grad():
+        ri, ts, te = m.occupancy_grid.sampling(ro, rd, alpha_fn=m._alpha_fn(ro, rd), render_step_size=m.render_step_size,
+                                               stratified=False)
+    ours = set(zip(ri.cpu().tolist(), ts.cpu().numpy().view(np.uint32).tolist()))
+    theirs = set(zip(ref["ray_indices"].tolist(), ref["t_starts"].numpy().view(np.uint32).tolist()))
+    _, T = ofields.render_weight_from_alpha(keep["alphas"].double(), keep["ri"], rays.shape[0])
+    cand = {(int(r), int(b)): float(t) for r, b, t in zip(keep["ri"].tolist(), keep["ts"].numpy().view(np.uint32).tolist(),
+                                                            T.tolist())}
+    return ours, theirs, cand
+
+
 @pytest.mark.parametrize("relighting", [False, True])
 def test_split_sum_render_vs_oracle(relighting):
-    """configs[2]/[3] shape at 192 rays, stage 1 (+ third bounce when relighting), eval mode
-    (fused tcgen05 MLPs).  Finite-difference normals amplify every rounding of the SDF MLP by
-    1/(2 eps) ~ 1400x and the reflection bounce starts AT the surface, so the tolerances are the
-    measured fp32-vs-fp32 noise floor of this configuration (scripts/diag_split2.py), not 1e-4:
-    geometry/material channels <= 1e-3, colour channels 99% of rays <= 1e-2 and mean <= 1e-3."""
+    """configs[2]/[3] shape at 192 rays, stage 1 (+ third bounce when relighting), eval mode (fused tcgen05 MLPs), full
+    512^2 environment light, against oracle/split.py evaluated in float64.
+    The north-star's 1e-4 is not reachable by ANY fp32 evaluation of this configuration: finite-difference normals
+    amplify the fp32 rounding of the SDF by 1/(2 eps) ~ 1400 and the reflection bounce starts at the surface.  The
+    bounds are therefore derived here, per channel, from an fp32 twin of the oracle (same code, float32):
+    `floor` = |oracle32 - oracle64|; the product must stay within 1e-4 or 3x floor (mean / p99), 5x floor (max).
+    Sample set: identical to the fp64 oracle's except for candidates whose transmittance sits at the early-stop
+    threshold (checked: every differing sample has T within a factor 2 of 1e-4)."""
     import sys, os
     sys.path.insert(0, os.path.dirname(__file__))
     from helpers import split_oracle_params
     from oracle import split as osplit
     from rise_sdf_b200 import synthetic as syn
-    m = _split_model().eval()
+    m = _split_model(base_res=512).eval()
     m.update_step(0, 20000)
     assert m.stage == 1
     with torch.no_grad():
@@ -206,20 +224,34 @@ def test_split_sum_render_vs_oracle(relighting):
     m.render_step_size = 1.732 * 2 * 1.5 / 256
     with torch.no_grad():
         out = m(rays.cuda(), relighting=relighting)
-    P = split_oracle_params(m)
-    osplit.build_mips(P)
-    for a, b, tol in zip(m.emitter.specular, P.specular, (2e-3, 1e-5, 1e-5)):
-        assert float((a.detach().cpu() - b).abs().max()) <= tol     # level 0: fp32 NDF cancellation (see oracle test)
-    assert float((m.emitter.diffuse.detach().cpu() - P.diffuse).abs().max()) <= 1e-5
-    P.specular = [t.detach().cpu() for t in m.emitter.specular]
-    ref = osplit.forward(P, rays, grid.numpy(), m.render_step_size, stage=1, relighting=relighting, background=bg)
-    assert abs(int(out["num_samples"].sum()) - ref["num_samples"]) <= 2
-    for k in ("comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic"):
-        e = (out[k].cpu() - ref[k]).abs()
-        assert float(e.max()) <= 1e-3 * max(float(ref[k].abs().max()), 1.0), (k, float(e.max()))
-    for k in ("comp_rgb", "comp_rgb_phys", "comp_rgb_full", "comp_rgb_phys_full"):
-        e = (out[k].cpu() - ref[k]).abs().max(-1).values
-        assert float(e.mean()) <= 1e-3 and float(torch.quantile(e, 0.99)) <= 2e-2, (k, float(e.mean()), float(e.max()))
+
+    def oracle(dtype, keep=None):
+        P = split_oracle_params(m).to(dtype)
+        # prefiltered levels from the product (pinned to the reference's compiled kernels by the prefilter tests; the
+        # dense CPU prefilter cannot run at 512^2)
+        P.specular = [t.detach().cpu().to(dtype) for t in m.emitter.specular]
+        P.diffuse = m.emitter.diffuse.detach().cpu().to(dtype)
+        return osplit.forward(P, rays, grid.numpy(), m.render_step_size, stage=1, relighting=relighting, background=bg,
+                              dtype=dtype, keep=keep)
+
+    keep = {}
+    ref = oracle(torch.float64, keep)
+    ref32 = oracle(torch.float32)
+    ours, theirs, cand = _sample_set_difference(m, rays, ref, keep)
+    diff = ours ^ theirs
+    assert int(out["num_samples"].sum()) == len(ours)
+    assert len(diff) <= 8 and all(0.5e-4 <= cand[k] <= 2e-4 for k in diff), sorted(cand[k] for k in diff)
+    report = []
+    for k in ("comp_normal", "opacity", "depth", "comp_albedo", "comp_roughness", "comp_metallic", "comp_rgb",
+              "comp_rgb_phys", "comp_rgb_full", "comp_rgb_phys_full"):
+        scale = max(float(ref[k].abs().max()), 1.0)
+        e = (out[k].cpu().double() - ref[k]).abs().max(-1).values / scale
+        f = (ref32[k].double() - ref[k]).abs().max(-1).values / scale
+        q = lambda x: (float(x.mean()), float(torch.quantile(x, 0.99)), float(x.max()))
+        (em, e99, ex), (fm, f99, fx) = q(e), q(f)
+        report.append(f"{k}: product mean/p99/max {em:.1e}/{e99:.1e}/{ex:.1e}   fp32-oracle floor {fm:.1e}/{f99:.1e}/{fx:.1e}")
+        assert em <= max(1e-4, 3 * fm) and e99 <= max(1e-4, 3 * f99) and ex <= max(1e-4, 5 * fx), report[-1]
+    print("\n".join(report))
     assert out["comp_rgb_phys"].shape == (192, 3) and out["comp_rgb_full"].min() >= 0 and out["comp_rgb_full"].max() <= 1
 
 
