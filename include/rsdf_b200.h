@@ -112,8 +112,12 @@ int rsdf_normalize3_bwd(const float *g, const float *grad_out, int n, float eps,
 
 /* Eikonal and sparsity regularisers of the loss block (systems/neus.py:117-131, systems/split_occ.py:186-204) as
  * sums over the samples: out2[0] = sum (|sdf_grad_i| - 1)^2, out2[1] = sum exp(-scale |sdf_i|) (the caller divides
- * by n); backward from the two scalar cotangents cot2 (device). */
-int rsdf_sdf_reg_fwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, float *out2, void *stream);
+ * by n); backward from the two scalar cotangents cot2 (device).  `partials`: caller-owned scratch of
+ * 2 * RSDF_SDF_REG_BLOCKS floats -- per-block sums, added by a second one-block launch in a fixed order, so the two
+ * loss terms are bit-reproducible (no float atomics). */
+#define RSDF_SDF_REG_BLOCKS 1184
+int rsdf_sdf_reg_fwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, float *out2,
+                     float *partials, void *stream);
 int rsdf_sdf_reg_bwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, const float *cot2,
                      float *grad_sdf_grad, float *grad_sdf, void *stream);
 
@@ -354,6 +358,8 @@ typedef struct rsdf_adam_groups {
     float eps[RSDF_ADAM_MAX_GROUPS];
     float bias2_sqrt[RSDF_ADAM_MAX_GROUPS];
     float weight_decay[RSDF_ADAM_MAX_GROUPS];
+    int32_t skip[RSDF_ADAM_MAX_GROUPS];            /* != 0: leave the group's p / m / v untouched (torch.optim.Adam skips
+                                                      parameters whose .grad is None; gradients here are never None) */
 } rsdf_adam_groups;
 int rsdf_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, long long n,
                    const rsdf_adam_groups *groups_host, int zero_grad, void *stream);

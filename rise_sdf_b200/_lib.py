@@ -51,7 +51,8 @@ class AdamGroupsC(ctypes.Structure):
                 ("step_size", ctypes.c_float * ADAM_MAX_GROUPS), ("one_minus_beta1", ctypes.c_float * ADAM_MAX_GROUPS),
                 ("beta2", ctypes.c_float * ADAM_MAX_GROUPS), ("one_minus_beta2", ctypes.c_float * ADAM_MAX_GROUPS),
                 ("eps", ctypes.c_float * ADAM_MAX_GROUPS),
-                ("bias2_sqrt", ctypes.c_float * ADAM_MAX_GROUPS), ("weight_decay", ctypes.c_float * ADAM_MAX_GROUPS)]
+                ("bias2_sqrt", ctypes.c_float * ADAM_MAX_GROUPS), ("weight_decay", ctypes.c_float * ADAM_MAX_GROUPS),
+                ("skip", ctypes.c_int32 * ADAM_MAX_GROUPS)]
 
 
 # name -> argtypes (restype is int for all but the two string getters)
@@ -71,7 +72,7 @@ _SIGS = {
     "rsdf_neus_render_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_p, c_p, c_p, c_p],
     "rsdf_neus_render_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i,
                              c_p, c_p, c_p, c_p, c_p],
-    "rsdf_sdf_reg_fwd": [c_p, c_p, c_i, c_f, c_p, c_p],
+    "rsdf_sdf_reg_fwd": [c_p, c_p, c_i, c_f, c_p, c_p, c_p],
     "rsdf_sdf_reg_bwd": [c_p, c_p, c_i, c_f, c_p, c_p, c_p, c_p],
     "rsdf_sample_setup": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p],
     "rsdf_normalize3_fwd": [c_p, c_i, c_f, c_p, c_p],
@@ -137,6 +138,11 @@ def ptr(t):
     if t is None:
         return None
     assert t.is_contiguous(), "rsdf ops need contiguous tensors"
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        # launches go to torch.cuda.current_stream() of the CURRENT device: a tensor living elsewhere would be an
+        # illegal access, not an error (one process per GPU sets the device once: bench.py, tests)
+        raise RuntimeError(f"tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: "
+                           "call torch.cuda.set_device() (one process per GPU) before using rise_sdf_b200")
     return t.data_ptr()
 
 
@@ -145,7 +151,8 @@ def stream():
 
 
 # kernels launched per C-ABI entry point (for bench.py's gpu_launches count)
-LAUNCHES = {"rsdf_march_count": 4, "rsdf_march_count_keep": 4}
+LAUNCHES = {"rsdf_march_count": 4, "rsdf_march_count_keep": 4, "rsdf_sdf_reg_fwd": 2}
+SDF_REG_BLOCKS = 1184
 STATS = {"enabled": False, "launches": 0, "timed": set(), "events": {}}
 
 

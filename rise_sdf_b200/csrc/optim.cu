@@ -10,6 +10,7 @@ namespace {
 
 struct AdamElem {
     float step_size, omb1, b2, omb2, eps, bc2_sqrt, wd;
+    bool skip;
 };
 
 __device__ __forceinline__ int find_seg(const rsdf_adam_groups &G, long long i) {
@@ -28,12 +29,14 @@ __device__ __forceinline__ AdamElem load_seg(const rsdf_adam_groups &G, int s) {
     e.eps = G.eps[s];
     e.bc2_sqrt = G.bias2_sqrt[s];
     e.wd = G.weight_decay[s];
+    e.skip = G.skip[s] != 0;
     return e;
 }
 
 // torch/optim/adam.py `_single_tensor_adam` (amsgrad off, maximize off): the operation order of
 // lerp_ / mul_.addcmul_ / sqrt / div / add / addcdiv_ kept, every product rounded on its own.
 __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, const AdamElem &e) {
+    if (e.skip) return;                                                // a group that is off the graph this step
     if (e.wd != 0.0f) g = __fmaf_rn(e.wd, p, g);                       // grad.add(param, alpha=wd)
     m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), e.omb1));            // exp_avg.lerp_(grad, 1-b1)
     v = __fadd_rn(__fmul_rn(v, e.b2), __fmul_rn(__fmul_rn(e.omb2, g), g));  // mul_(b2).addcmul_(g,g,1-b2)

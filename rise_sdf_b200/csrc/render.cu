@@ -381,7 +381,22 @@ __global__ void sdf_reg_fwd_kernel(const float *__restrict__ g, const float *__r
     if (w == 0) {
         e = l < (blockDim.x >> 5) ? se[l] : 0.f; sp = l < (blockDim.x >> 5) ? ss[l] : 0.f;
         e = warp_sum(e); sp = warp_sum(sp);
-        if (l == 0) { atomicAdd(out, e); atomicAdd(out + 1, sp); }
+        if (l == 0) { out[2 * blockIdx.x] = e; out[2 * blockIdx.x + 1] = sp; }     // per-block partials, no atomics
+    }
+}
+// second stage: one block adds the per-block partials in a fixed order -> bit-reproducible loss terms
+__global__ void sdf_reg_finish_kernel(const float *__restrict__ partials, int n_blocks, float *__restrict__ out) {
+    float e = 0.f, sp = 0.f;
+    for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) { e += partials[2 * i]; sp += partials[2 * i + 1]; }
+    e = warp_sum(e); sp = warp_sum(sp);
+    __shared__ float se[32], ss[32];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { se[w] = e; ss[w] = sp; }
+    __syncthreads();
+    if (w == 0) {
+        e = l < (blockDim.x >> 5) ? se[l] : 0.f; sp = l < (blockDim.x >> 5) ? ss[l] : 0.f;
+        e = warp_sum(e); sp = warp_sum(sp);
+        if (l == 0) { out[0] = e; out[1] = sp; }
     }
 }
 // cotangents ce, cs (device scalars, already divided by n by the caller's mean):
@@ -402,14 +417,17 @@ __global__ void sdf_reg_bwd_kernel(const float *__restrict__ g, const float *__r
 
 extern "C" {
 
-int rsdf_sdf_reg_fwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, float *out2, void *stream) {
-    if (!out2) return RSDF_EBADARG;
-    cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
-    if (n == 0) return 0;
+int rsdf_sdf_reg_fwd(const float *sdf_grad, const float *sdf, int n, float sparsity_scale, float *out2,
+                     float *partials, void *stream) {
+    if (!out2 || !partials) return RSDF_EBADARG;
+    if (n == 0) {
+        cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(float), (cudaStream_t)stream);
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     if (!sdf_grad || !sdf) return RSDF_EBADARG;
-    const int blocks = rsdf_div_up(n, 256) < 8 * RSDF_NUM_SMS ? rsdf_div_up(n, 256) : 8 * RSDF_NUM_SMS;
-    sdf_reg_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sdf_grad, sdf, n, sparsity_scale, out2);
+    const int blocks = rsdf_div_up(n, 256) < RSDF_SDF_REG_BLOCKS ? rsdf_div_up(n, 256) : RSDF_SDF_REG_BLOCKS;
+    sdf_reg_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sdf_grad, sdf, n, sparsity_scale, partials);
+    sdf_reg_finish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(partials, blocks, out2);
     RSDF_LAUNCH_CHECK();
     return 0;
 }

@@ -40,6 +40,10 @@ class VolumeSDF(nn.Module):
         self.grad_type = config.grad_type
         self._finite_difference_eps = None
         self.finite_difference_eps = config.get("finite_difference_eps", 1e-3)
+        # models/geometry.py:218-221 applies `sdf_activation(sdf + sdf_bias)` / `feature_activation(feature)` when the
+        # keys are present.  Neither shipped config sets them; they are honoured on the op-by-op path and switch the
+        # fused kernels (which return the raw network outputs) off.
+        self._post_activations = "sdf_activation" in config or "feature_activation" in config
 
     fused_analytic = True       # class-wide switch (tests compare the fused and the op-by-op paths)
 
@@ -50,7 +54,8 @@ class VolumeSDF(nn.Module):
         from .network_utils import CompositeEncoding, ProgressiveBandHashGrid, VanillaMLP
         comp = self.encoding
         if not (VolumeSDF.fused_analytic and isinstance(comp, CompositeEncoding) and comp.include_xyz
-                and isinstance(self.network, VanillaMLP) and sdf_field.supports(self.network, comp.n_output_dims)):
+                and isinstance(self.network, VanillaMLP) and sdf_field.supports(self.network, comp.n_output_dims)
+                and self.network.config_output_activation_is_identity and not self._post_activations):
             return None
         inner, mask = comp.encoding, None
         if isinstance(inner, ProgressiveBandHashGrid):
@@ -66,7 +71,9 @@ class VolumeSDF(nn.Module):
         inner, mask = parts
         comp = self.encoding
         shape = points.shape[:-1]
-        x01 = contract_to_unisphere(points.reshape(-1, 3), self.radius, self.contraction_type)
+        # (differentiable w.r.t. `points` as well: every node below returns its position leg when asked to -- the
+        # curvature probe needs it, the render path proper does not)
+        x01 = contract_to_unisphere(points.reshape(-1, 3), self.radius, self.contraction_type).contiguous().float()
         y, dy_dx, link = tcnn.hashgrid_with_jacobian(inner, x01)
         enc = y if mask is None else y * mask
         out, sdf, g0_xyz, g0_enc = sdf_field.fused_sdf_parts(self.network, x01, comp.xyz_scale, comp.xyz_offset, enc)
@@ -161,6 +168,12 @@ class VolumeSDF(nn.Module):
             points = contract_to_unisphere(points, self.radius, self.contraction_type)
             out = self._field(points.view(-1, 3)).view(*points.shape[:-1], self.n_output_dims).float()
             sdf, feature = out[..., 0], out
+            if "sdf_activation" in self.config:
+                from .network_utils import get_activation
+                sdf = get_activation(self.config.sdf_activation)(sdf + float(self.config.sdf_bias))
+            if "feature_activation" in self.config:
+                from .network_utils import get_activation
+                feature = get_activation(self.config.feature_activation)(feature)
             if with_grad:
                 if self.grad_type == "analytic":
                     grad = torch.autograd.grad(sdf, points_, grad_outputs=torch.ones_like(sdf),
@@ -184,10 +197,17 @@ class VolumeSDF(nn.Module):
                         points_t_ = points_ + eps_c * tangent
                         if not points_t_.requires_grad:
                             points_t_ = points_t_.requires_grad_(True)
-                        points_t = contract_to_unisphere(points_t_, self.radius, self.contraction_type)
-                        sdf_t = self.network(self.encoding(points_t.view(-1, 3)))[..., 0].view(*points.shape[:-1]).float()
-                        grad_t = torch.autograd.grad(sdf_t, points_t_, grad_outputs=torch.ones_like(sdf_t),
-                                                     create_graph=True, retain_graph=True, only_inputs=True)[0]
+                        probe = self._fused_parts() if points_t_.is_cuda else None
+                        if probe is not None:
+                            # d sdf / d points_t with its full second-order graph (weights, table AND the probe
+                            # position, which depends on the parameters through `tangent`) on the fused kernels:
+                            # hash grid + Jacobian -> one fused MLP node -> dy_dx^T g0, exactly the analytic-normal path
+                            _, grad_t, _ = self._forward_fused_analytic(points_t_, probe)
+                        else:
+                            points_t = contract_to_unisphere(points_t_, self.radius, self.contraction_type)
+                            sdf_t = self.network(self.encoding(points_t.view(-1, 3)))[..., 0].view(*points.shape[:-1]).float()
+                            grad_t = torch.autograd.grad(sdf_t, points_t_, grad_outputs=torch.ones_like(sdf_t),
+                                                         create_graph=True, retain_graph=True, only_inputs=True)[0]
                         dot = torch.sum(F.normalize(grad, dim=-1, eps=1e-6) * F.normalize(grad_t, dim=-1, eps=1e-6), dim=-1)
                         laplace = torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / np.pi
         rv = [sdf]

@@ -158,7 +158,9 @@ class _HashGridForwardJ(torch.autograd.Function):
 class _HashGridInputGrad(torch.autograd.Function):
     """(g2, dy_dx; x, table) -> dy_dx^T g2 [S,3] for the fused path.  Backward (the second-order pass):
     d/d g2 = dy_dx . v from the stored Jacobian; the table leg is deferred to the linked first-order
-    node (see _Link).  x is not differentiated on this path (sample positions are data)."""
+    node (see _Link).  When x requires grad (the curvature probe of models/geometry.py:246-282 sits at
+    x + 1e-4 tangent(theta)) its leg -- d/dx of (dy_dx^T g2) . v, the mixed second derivatives of the trilinear
+    interpolation -- comes from rsdf_hashgrid_bwd_bwd; on the render path proper sample positions are data."""
 
     @staticmethod
     def forward(ctx, g2, dy_dx, x, table, meta, link):
@@ -180,22 +182,27 @@ class _HashGridInputGrad(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             g_g2 = torch.empty_like(g2)
             L.call("rsdf_hashgrid_jvp", L.ptr(dy_dx), L.ptr(v), S, n_out, L.ptr(g_g2), L.stream())
+        g_x = None
+        if ctx.needs_input_grad[2]:
+            g_x = torch.empty_like(x)
+            L.call("rsdf_hashgrid_bwd_bwd", L.ptr(x), L.ptr(table), L.ptr(v), L.ptr(g2), ctx.meta.ref, S,
+                   None, None, L.ptr(g_x), L.stream())
         if table.requires_grad:
             ctx.link.v, ctx.link.g2 = v, g2
-        return g_g2, None, None, None, None, None
+        return g_g2, None, g_x, None, None, None
 
 
 def hashgrid_with_jacobian(enc, x):
     """enc: a HashGrid `Encoding`; x [S,3] in [0,1] -> (y [S,n_out], dy_dx [S,n_out,3], link)."""
     L.require_cuda(x)
     link = _Link()
-    y, dy_dx = _HashGridForwardJ.apply(x.contiguous().float(), enc.params, enc.meta, link)
+    y, dy_dx = _HashGridForwardJ.apply(x, enc.params, enc.meta, link)
     return y, dy_dx, link
 
 
 def hashgrid_input_grad(enc, g2, x, dy_dx, link):
     """dy_dx^T g2 -> [S,3]; differentiable w.r.t. g2 and (through the linked forward node) the table."""
-    return _HashGridInputGrad.apply(g2, dy_dx, x.contiguous().float(), enc.params, enc.meta, link)
+    return _HashGridInputGrad.apply(g2, dy_dx, x, enc.params, enc.meta, link)
 
 
 @torch.no_grad()

@@ -41,7 +41,8 @@ class _SdfRegularisers(torch.autograd.Function):
         sdf_grad, sdf = sdf_grad.contiguous().float(), sdf.contiguous().float()
         n = sdf.shape[0]
         out = torch.empty(2, device=sdf.device, dtype=torch.float32)
-        L.call("rsdf_sdf_reg_fwd", L.ptr(sdf_grad), L.ptr(sdf), n, float(scale), L.ptr(out), L.stream())
+        partials = torch.empty(2 * L.SDF_REG_BLOCKS, device=sdf.device, dtype=torch.float32)
+        L.call("rsdf_sdf_reg_fwd", L.ptr(sdf_grad), L.ptr(sdf), n, float(scale), L.ptr(out), L.ptr(partials), L.stream())
         ctx.save_for_backward(sdf_grad, sdf)
         ctx.scale = float(scale)
         out = out / max(n, 1)
@@ -151,59 +152,93 @@ class FlatGradBucket:
             self.flat.mul_(1.0 / dist.get_world_size())
 
 
-class NeusTrainer:
-    def __init__(self, model, lr=0.01, lr_variance=0.001):
+class _Trainer:
+    """The per-batch sequence of the reference's Lightning loop, without Lightning:
+        on_train_batch_start  -> update_module_step(model, epoch, global_step)   (systems/base.py:100-103): occupancy
+                                 refresh every 16 steps, cos-anneal ratio, progressive hash-level mask + FD eps, stage
+        training_step         -> render, losses (systems/neus.py:98-135, systems/split_occ.py:150-237)
+        backward, (DDP all-reduce), optimizer.step(), scheduler.step() [interval: step]
+    `step(..., update=False)` leaves the schedule to the caller (parity tests pin the state by hand)."""
+
+    max_steps, warmup_steps = 30000, 500
+
+    def _setup(self, groups, lr, betas, eps, scheduler):
+        from .optim import warmup_exponential_scheduler
+        self.opt = FlatAdam(groups, lr=lr, betas=betas, eps=eps)
+        self.bucket = self.opt.bucket
+        self.sched = warmup_exponential_scheduler(self.opt, self.warmup_steps, self.max_steps) if scheduler else None
+        self.global_step = 0
+
+    def _inactive_groups(self):
+        return ()
+
+    def _finish(self, loss, optimize):
+        loss.backward()
+        self.bucket.all_reduce_mean()
+        if optimize:
+            self.opt.step(inactive_groups=self._inactive_groups())
+            if self.sched is not None:
+                self.sched.step()
+        self.global_step += 1
+
+
+class NeusTrainer(_Trainer):
+    """configs/neus-blender.yaml:92-119: Adam(betas 0.9/0.99, eps 1e-15), lr 0.01 (variance 0.001), 500-step linear
+    warm-up then exponential decay to 0.1x at trainer.max_steps = 30000."""
+
+    def __init__(self, model, lr=0.01, lr_variance=0.001, scheduler=True):
         self.model = model
         groups = [
             {"params": list(model.geometry.parameters()), "lr": lr},
-            {"params": [p for p in model.texture.parameters() if p.numel() > 0], "lr": lr},
+            {"params": list(model.texture.parameters()), "lr": lr},
             {"params": list(model.variance.parameters()), "lr": lr_variance},
         ]
-        self.opt = FlatAdam(groups, lr=lr, betas=(0.9, 0.99), eps=1e-15)
-        self.bucket = self.opt.bucket
-        self.global_step = 0
+        self._setup(groups, lr, (0.9, 0.99), 1e-15, scheduler)
 
-    def step(self, rays, rgb, fg_mask, background, optimize=True):
+    def step(self, rays, rgb, fg_mask, background, optimize=True, update=True):
         m = self.model
+        if update:
+            m.update_step(0, self.global_step)
         m.background_color = background
         self.bucket.zero()
         out = m(rays)
         loss, parts = neus_loss(out, rgb, fg_mask)
-        loss.backward()
-        self.bucket.all_reduce_mean()
-        if optimize:
-            self.opt.step()
-        self.global_step += 1
+        self._finish(loss, optimize)
         return loss, out
 
 
-class SplitTrainer:
+class SplitTrainer(_Trainer):
     """One split-mixed-occ training step (systems/split_occ.py:150-237): rebuild the env-light mip pyramid
     (`emitter.build_mips()`, the `base` cube map is learnable), render, loss, backward, gradient exchange,
-    Adam with the per-group learning rates of configs/split-mixed-occ-tensoir.yaml:153-166."""
+    Adam with the per-group learning rates of configs/split-mixed-occ-tensoir.yaml:153-166 and its schedule
+    (:167-182, trainer.max_steps = 80000)."""
 
-    def __init__(self, model, lr=0.005, lr_variance=0.001, lr_emitter=0.01):
+    max_steps = 80000
+    EMITTER_GROUP = 3
+
+    def __init__(self, model, lr=0.005, lr_variance=0.001, lr_emitter=0.01, scheduler=True):
         self.model = model
         groups = [
             {"params": list(model.geometry.parameters()), "lr": lr},
-            {"params": [p for p in model.texture.parameters() if p.numel() > 0], "lr": lr},
+            {"params": list(model.texture.parameters()), "lr": lr},
             {"params": list(model.variance.parameters()), "lr": lr_variance},
             {"params": list(model.emitter.parameters()), "lr": lr_emitter},
         ]
-        self.opt = FlatAdam(groups, lr=lr, betas=(0.9, 0.999), eps=1e-12)
-        self.bucket = self.opt.bucket
-        self.global_step = 0
+        self._setup(groups, lr, (0.9, 0.999), 1e-12, scheduler)
 
-    def step(self, rays, rgb, fg_mask, background, optimize=True):
+    def _inactive_groups(self):
+        # stage 0 (models/texture.py:323-324 returns before any emitter lookup): `emitter.base.grad` stays None in the
+        # reference and torch.optim.Adam skips it -- no moment decay, its step count starts at the stage switch
+        return (self.EMITTER_GROUP,) if self.model.stage == 0 else ()
+
+    def step(self, rays, rgb, fg_mask, background, optimize=True, update=True):
         m = self.model
+        if update:
+            m.update_step(0, self.global_step)
         m.background_color = background
         self.bucket.zero()
         m.emitter.build_mips()
         out = m(rays)
         loss, parts = split_loss(m, out, rgb, fg_mask)
-        loss.backward()
-        self.bucket.all_reduce_mean()
-        if optimize:
-            self.opt.step()
-        self.global_step += 1
+        self._finish(loss, optimize)
         return loss, out

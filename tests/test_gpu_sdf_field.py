@@ -127,3 +127,36 @@ def test_inference_kernel_out_and_sdf_only(S, ts):
     assert out.shape == (S, 48) and sdf.shape == (S,)
     assert rel(out, ro.detach()) <= 2e-6 and rel(out1, ro.detach()) <= 2e-6
     assert float((sdf.double().cpu() - ro[:, 0].detach().cpu()).abs().max()) <= 2e-6 * max(float(ro[:, 0].abs().max()), 1.0)
+
+
+@pytest.mark.parametrize("want_g0", [False, True])
+def test_double_backward_through_the_fused_node(want_g0):
+    """The curvature probe of models/geometry.py:246-282: `autograd.grad(sdf, h0, create_graph=True)` THROUGH the fused
+    node, then a backward through that gradient to the inputs and every weight (the node's create_graph path:
+    sdf_field._FusedSDF._backward_twice_differentiable).  Before round 2 the node was `once_differentiable`, which
+    hands back constants for a cotangent that does not require grad: the second-order terms were silently lost."""
+    m = make_mlp(seed=4)
+    S = 700
+    g = torch.Generator().manual_seed(9)
+    h0 = (torch.randn(S, 35, generator=g) * 0.3).cuda().requires_grad_(True)
+    c = torch.randn(S, 35, generator=g).cuda()
+    params = list(m.parameters())
+
+    def probe(out, h):
+        (gh,) = torch.autograd.grad(out[:, 0], h, torch.ones_like(out[:, 0]), create_graph=True)
+        return (gh * c.to(gh)).sum() + ((gh[:, :3].norm(dim=-1) - 1.0) ** 2).mean() + (out ** 2).mean()
+
+    if want_g0:          # the analytic-normal node, double-differentiated on top of its own g0 output
+        out, g0 = sdf_field.fused_sdf(m, h0, want_g0=True)
+        l = probe(out, h0) + (g0 ** 2).mean()
+    else:
+        out, _ = sdf_field.fused_sdf(m, h0, want_g0=False)
+        l = probe(out, h0)
+    got = torch.autograd.grad(l, [h0] + params)
+    h64 = h0.detach().double().requires_grad_(True)
+    ro, rg = ref64(m, h64, None, want_g0=want_g0)
+    lr = probe(ro, h64) + ((rg ** 2).mean() if want_g0 else 0.0)
+    want = torch.autograd.grad(lr, [h64] + params)
+    assert abs(float(l) - float(lr)) <= 1e-5 * abs(float(lr))
+    for n, a, b in zip(["h0"] + [n for n, _ in m.named_parameters()], got, want):
+        assert rel(a, b) <= 5e-5, (n, rel(a, b))

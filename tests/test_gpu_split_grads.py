@@ -165,3 +165,52 @@ def test_split_train_step_grads():
     floor = max(rel_l2(g32[k].numpy(), g64[k].numpy()) for k in ("specular.3", "specular.4", "specular.5", "diffuse"))
     print(f"grad emitter.base vs fp64 level grads: rel-L2 {err64:.2e} (level-gradient floor {floor:.2e})")
     assert err64 <= max(1e-3, 3 * floor), (err64, floor)
+
+
+def test_fused_analytic_field_is_differentiable_wrt_the_points():
+    """The curvature probe evaluates d sdf / d x at x_t = x + 1e-4 tangent(theta) and differentiates it again w.r.t.
+    the weights, the table AND x_t (models/geometry.py:246-282).  The fused analytic path (hash grid + Jacobian ->
+    one fused MLP node -> dy_dx^T g0) must give the same first and second-order gradients as the op-by-op autograd
+    path (tcnn.Encoding double backward + the MLP's twice-differentiable GEMM primitives) and as float64 torch."""
+    from oracle import fields as ofields
+    from rise_sdf_b200.geometry import VolumeSDF
+    m = split_model(64).train()
+    geo = m.geometry
+    g = torch.Generator().manual_seed(3)
+    pts = ((torch.rand(3000, 3, generator=g) * 2 - 1) * 1.2).cuda()
+    c = torch.randn(3000, 3, generator=g).cuda()
+    params = [p for p in geo.parameters() if p.requires_grad]
+
+    def run(fused):
+        p = pts.clone().requires_grad_(True)
+        VolumeSDF.fused_analytic = fused
+        try:
+            if fused:
+                sdf, grad, feat = geo._forward_fused_analytic(p, geo._fused_parts())
+            else:
+                x01 = (p + 1.5) * float(np.float32(1.0) / np.float32(3.0))
+                sdf = geo.network(geo.encoding(x01))[..., 0]
+                (grad,) = torch.autograd.grad(sdf, p, torch.ones_like(sdf), create_graph=True)
+        finally:
+            VolumeSDF.fused_analytic = True
+        loss = (grad * c).sum() + ((grad.norm(dim=-1) - 1.0) ** 2).mean() + sdf.mean()
+        return [sdf, grad] + list(torch.autograd.grad(loss, [p] + params))
+
+    a, b = run(True), run(False)
+    # float64 yardstick (oracle hash grid + torch MLP)
+    P = split_oracle_params(m).to(torch.float64)
+    p64 = pts.cpu().clone().requires_grad_(True)
+    leaves = [P.table] + [t for l in P.geo_mlp for t in l.values()]
+    for t in leaves:
+        t.requires_grad_(True)
+    sdf64 = osplit._field(P, p64, torch.float64)[:, 0]
+    (g64,) = torch.autograd.grad(sdf64, p64, torch.ones_like(sdf64), create_graph=True)
+    l64 = (g64 * c.cpu().double()).sum() + ((g64.norm(dim=-1) - 1.0) ** 2).mean() + sdf64.mean()
+    r = [sdf64, g64] + list(torch.autograd.grad(l64, [p64] + leaves))
+    names = ["sdf", "grad", "d/d points"] + [n for n, p_ in geo.named_parameters() if p_.requires_grad]
+    by_name = dict(zip(["sdf", "grad", "d/d points", "encoding.encoding.encoding.params"]
+                       + [f"network.layers.{2 * i}.{k}" for i, l in enumerate(P.geo_mlp) for k in l], r))
+    for n, x, y in zip(names, a, b):
+        ref = by_name[n].detach().float()
+        ea, eb = rel_l2(x.detach().cpu().numpy(), ref.numpy()), rel_l2(y.detach().cpu().numpy(), ref.numpy())
+        assert ea <= 2e-4 and eb <= 2e-4, (n, ea, eb)

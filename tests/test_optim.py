@@ -86,6 +86,80 @@ def test_flat_adam_state_dict_round_trip_and_external_grads():
         assert float((pa - pc).abs().max()) <= 2e-6 * (float(pa.abs().max()) + 1e-12)
 
 
+@pytest.mark.gpu
+def test_flat_adam_keeps_empty_and_frozen_parameters_in_its_groups():
+    """The reference's groups come from `module.parameters()` (systems/utils.py:309-320) and carry the empty tcnn
+    SphericalHarmonics `params` (texture group) -- and may carry frozen tensors.  FlatAdam must keep them in
+    `param_groups` so that group sizes and state-dict indices are torch.optim.Adam's: a Lightning `optimizer_states`
+    entry loads, and what FlatAdam saves loads into torch.optim.Adam."""
+    from rise_sdf_b200.optim import FlatAdam
+
+    def make():
+        ps = _params("cuda", seed=5)
+        empty = torch.nn.Parameter(torch.zeros(0, device="cuda"))
+        frozen = torch.nn.Parameter(torch.randn(7, device="cuda"), requires_grad=False)
+        groups = [{"params": ps[:2] + [empty] + ps[2:4], "lr": 0.01}, {"params": [frozen] + ps[4:], "lr": 0.002}]
+        return ps, groups
+
+    (a, ga), (b, gb), (c, gc) = make(), make(), make()
+    ref = torch.optim.Adam(ga, lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+    opt = FlatAdam(gb, lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+    assert [len(g["params"]) for g in opt.param_groups] == [len(g["params"]) for g in ref.param_groups] == [5, 4]
+    g = torch.Generator().manual_seed(2)
+    grads = [[torch.randn(p.shape, generator=g).cuda() for p in a] for _ in range(4)]
+    for it in range(2):
+        for pa, pb, gr in zip(a, b, grads[it]):
+            pa.grad = gr.clone()
+            pb.grad.copy_(gr)
+        ref.step(); opt.step()
+    sd_ref, sd_opt = ref.state_dict(), opt.state_dict()
+    assert [g_["params"] for g_ in sd_ref["param_groups"]] == [g_["params"] for g_ in sd_opt["param_groups"]]
+    assert sd_ref["state"].keys() == sd_opt["state"].keys() and 2 not in sd_opt["state"] and 5 not in sd_opt["state"]
+    # torch's state dict -> FlatAdam, FlatAdam's -> torch: both continue identically
+    with torch.no_grad():
+        for pc, pa in zip(c, a):
+            pc.copy_(pa)
+    o2 = FlatAdam(gc, lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+    o2.load_state_dict(sd_ref)
+    r2 = torch.optim.Adam(make()[1], lr=0.01, betas=(0.9, 0.99), eps=1e-15)
+    r2.load_state_dict(sd_opt)                              # must not raise "doesn't match the size"
+    for it in range(2, 4):
+        for pa, pc, gr in zip(a, c, grads[it]):
+            pa.grad = gr.clone()
+            pc.grad.copy_(gr)
+        ref.step(); o2.step()
+    for pa, pc in zip(a, c):
+        assert float((pa - pc).abs().max()) <= 2e-6 * (float(pa.abs().max()) + 1e-12)
+
+
+@pytest.mark.gpu
+def test_flat_adam_late_activated_group_matches_torch():
+    """`emitter.base` gets no gradient during stage 0 (10 000 steps): torch.optim.Adam skips it (grad None) and its
+    first real update runs with step = 1 bias correction.  `step(inactive_groups=...)` reproduces that; the saved
+    per-parameter `step` counts match torch's."""
+    from rise_sdf_b200.optim import FlatAdam
+    a, b = _params("cuda", seed=7), _params("cuda", seed=7)
+    ref = torch.optim.Adam(_groups(a), lr=0.01, betas=(0.9, 0.999), eps=1e-12, foreach=False)
+    opt = FlatAdam(_groups(b), lr=0.01, betas=(0.9, 0.999), eps=1e-12)
+    g = torch.Generator().manual_seed(4)
+    late = {id(p) for p in a[5:]}
+    for it in range(7):
+        off = it < 4                                           # group 2 is off the graph for the first four steps
+        ref.zero_grad(set_to_none=True); opt.zero_grad()
+        for pa, pb in zip(a, b):
+            if off and id(pa) in late:
+                continue
+            gr = torch.randn(pa.shape, generator=g).cuda()
+            pa.grad = gr.clone()
+            pb.grad.copy_(gr)
+        ref.step(); opt.step(inactive_groups=(2,) if off else ())
+        for pa, pb in zip(a, b):
+            assert float((pa - pb).abs().max()) <= 2e-6 * (float(pa.abs().max()) + 1e-12), it
+    sd_a, sd_b = ref.state_dict(), opt.state_dict()
+    assert {k: float(v["step"]) for k, v in sd_a["state"].items()} == {k: float(v["step"]) for k, v in sd_b["state"].items()}
+    assert float(sd_b["state"][5]["step"]) == 3.0 and float(sd_b["state"][0]["step"]) == 7.0
+
+
 def test_flat_adam_refuses_cpu_parameters():
     from rise_sdf_b200.optim import FlatAdam
     with pytest.raises(NotImplementedError):
