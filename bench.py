@@ -391,7 +391,7 @@ def run_split_train(args, dev, world, rank, n_rays=4096):
 
 SPLIT_TIMED = ["rsdf_hashgrid_fwd", "rsdf_hashgrid_bwd_table", "rsdf_hashgrid_bwd_input", "rsdf_hashgrid_bwd_bwd",
                "rsdf_hashgrid_fd6", "rsdf_sdf_mlp_fwd", "rsdf_sdf_mlp_bwd", "rsdf_sdf_mlp_eval", "rsdf_relu_layer_fwd",
-               "rsdf_relu_layer_bwd", "rsdf_mlp_fwd", "rsdf_mm_stream", "rsdf_mm_tn", "rsdf_specular_cubemap",
+               "rsdf_relu_layer_bwd", "rsdf_mlp_fwd", "rsdf_mm_stream", "rsdf_mm_tn", "rsdf_specular_cubemap", "rsdf_specular_apply",
                "rsdf_diffuse_cubemap", "rsdf_cube_sample_fwd", "rsdf_cube_sample_bwd", "rsdf_tex2d_fwd", "rsdf_tex2d_bwd",
                "rsdf_weight_from_alpha_fwd", "rsdf_weight_from_alpha_bwd", "rsdf_accumulate_fwd", "rsdf_accumulate_bwd",
                "rsdf_march_count_keep", "rsdf_march_compact", "rsdf_adam_step", "rsdf_sh_fwd", "rsdf_sh_bwd"]

@@ -216,6 +216,23 @@ int rsdf_specular_bounds(const float *table, int res, float costheta_cutoff, flo
 int rsdf_specular_cubemap(const float *table, const float *bounds, const float *src, int res, float roughness,
                           float costheta_cutoff, int transposed, float *dst, void *stream);
 
+/* The same GGX prefilter as a CACHED SPARSE OPERATOR: the pair weights depend on (res, roughness, cutoff) only, the
+ * map is what changes from step to step.  rsdf_specular_build evaluates every (output texel, lobe-box texel) weight
+ * once -- the arithmetic of rsdf_specular_cubemap, IEEE sqrt / divisions -- into `weights` (dense run per output texel
+ * at offset[p]: faces in order, each face's box row-major; 0 outside the cutoff circle; offset = exclusive prefix sum
+ * of the per-texel box areas, int64 [6 res^2 + 1]) and the constant normaliser wsum[6 res^2] (channel 3 of the
+ * reference's specular_cubemap_fwd).  rsdf_specular_apply streams them (src: [6 res^2, 4], rgb padded to 16 bytes;
+ * dst: [6 res^2, 3]): forward dst[p] = sum_x w(p,x) src[x] with
+ * src = cubemap * area / 4; transposed != 0: dst[x] = area(x)/4 * sum_p w(x,p) src[p] (src = d loss / d out[..., :3]).
+ * The weight of a pair is evaluated from the side of the forward pass's OUTPUT texel (V in V.H), as the reference's
+ * scatter backward does: `transposed` selects the operator (forward: runs owned by the output texel; transposed: runs
+ * owned by the source texel, same box structure, wsum not written) -- two arrays, one per direction. */
+int rsdf_specular_build(const float *texel_table, const float *bounds, const long long *offset, int res,
+                        float roughness, float costheta_cutoff, int transposed, float *weights, float *wsum,
+                        void *stream);
+int rsdf_specular_apply(const float *texel_table, const float *bounds, const long long *offset, const float *weights,
+                        const float *src, int res, int transposed, float *dst, void *stream);
+
 /* ---------------------------------------------------------------- K3: tensor-core MLPs */
 /* nn.Linear weight W[N][K] fp32 (models/network_utils.py:127) -> bf16 hi/lo "tile image" blob
  * (UMMA canonical no-swizzle layout, N_pad x K_pad, multiples of 16); blob bytes = 4*N_pad*K_pad. */

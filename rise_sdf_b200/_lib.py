@@ -94,6 +94,8 @@ _SIGS = {
     "rsdf_diffuse_cubemap": [c_p, c_p, c_i, c_i, c_p, c_p],
     "rsdf_specular_bounds": [c_p, c_i, c_f, c_p, c_p, c_p],
     "rsdf_specular_cubemap": [c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p],
+    "rsdf_specular_build": [c_p, c_p, c_p, c_i, c_f, c_f, c_i, c_p, c_p, c_p],
+    "rsdf_specular_apply": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p],
     "rsdf_mlp_pack_weight": [c_p, c_i, c_i, c_i, c_i, c_p, c_p],
     "rsdf_mlp_fwd": [c_p, c_p],
     "rsdf_mm_stream": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

@@ -169,7 +169,11 @@ __global__ void specular_kernel(int N, float roughness, float cutoff, const floa
                     const float hl = sqrtf(hx * hx + hy * hy + hz * hz);
                     if (hl > 0.0f) { hx /= hl; hy /= hl; hz /= hl; } else { hx = hy = hz = 0.f; }
                     const float wiDotN = fmaxf(dp, 0.0f);
-                    const float vDotH = fmaxf(me.x * hx + me.y * hy + me.z * hz, 0.0f);
+                    // V = the direction of the OUTPUT texel of the forward pass: `me` forward, `o` in the gather
+                    // backward (the reference's scatter evaluates the weight from the output texel's side; at
+                    // roughness 0.08 the two sides differ by 5e-3 through the fp32 cancellation in D_ggx)
+                    const float vDotH = TRANSPOSED ? fmaxf(o.x * hx + o.y * hy + o.z * hz, 0.0f)
+                                                   : fmaxf(me.x * hx + me.y * hy + me.z * hz, 0.0f);
                     const float w = wiDotN * ndf_ggx(alphaSqr, vDotH) * (TRANSPOSED ? me.w : o.w) / 4.0f;
                     cx += src[3 * q] * w; cy += src[3 * q + 1] * w; cz += src[3 * q + 2] * w;
                     wsum += w;
@@ -184,9 +188,153 @@ __global__ void specular_kernel(int N, float roughness, float cutoff, const floa
     }
 }
 
+// ---- specular prefilter as a CACHED SPARSE OPERATOR ---------------------------------------------------------------
+// The pair weight s(p,x) = (L_x.N_p) D_ggx(N_p.H) / 4 depends on (resolution, roughness, cutoff) only -- not on the
+// cube map -- and the prefilter runs every training step (forward + backward) on a map that is the only thing that
+// changes.  With 180 GB of HBM per GPU the whole operator fits: the weights of every (output texel, lobe-box texel)
+// pair are evaluated ONCE, with exactly the arithmetic of specular_kernel above (IEEE sqrt / divisions: the GGX lobe of
+// the finest level is sharp enough that one ulp in N.H moves D by 1e-3), and stored as a dense run per output texel:
+//     weights[offset[p] + sum of the box areas of faces < s + (y - ymin) * box_w + (x - xmin)]
+// (0 outside the cutoff circle).  4.9 GB for the 512 ... 16 pyramid of the config.  A training step then streams them:
+// one warp per output texel, lanes over the run (coalesced 128-byte reads), the source texel gathered from L2,
+// three FMAs per pair and a shuffle reduction.  The backward is the same gather with the roles of the two texels
+// swapped (the lobe box is symmetric), scaled by the receiving texel's solid angle -- the semantics of
+// specular_kernel<true>.  HBM-bound: ~1 ms per pass instead of ~12 ms of fp32 divisions.
+// `me` = the texel that owns the run, `o` = the other one; V (in V.H) is the forward pass's OUTPUT texel: `me` for the
+// forward operator, `o` for the transposed one (see specular_kernel)
+template <bool TRANSPOSED>
+__device__ __forceinline__ float pair_weight(const float4 me, const float4 o, float alphaSqr, float cutoff) {
+    const float dp = o.x * me.x + o.y * me.y + o.z * me.z;
+    if (!(dp >= cutoff)) return 0.0f;
+    float hx = o.x + me.x, hy = o.y + me.y, hz = o.z + me.z;
+    const float hl = sqrtf(hx * hx + hy * hy + hz * hz);
+    if (hl > 0.0f) { hx /= hl; hy /= hl; hz /= hl; } else { hx = hy = hz = 0.f; }
+    const float wiDotN = fmaxf(dp, 0.0f);
+    const float vDotH = TRANSPOSED ? fmaxf(o.x * hx + o.y * hy + o.z * hz, 0.0f)
+                                   : fmaxf(me.x * hx + me.y * hy + me.z * hz, 0.0f);
+    return wiDotN * ndf_ggx(alphaSqr, vDotH);          // x area / 4 when applied (as in specular_kernel)
+}
+
+// warp per output texel p: writes its run of pair weights and (forward operator) wsum[p] = sum_x s(p,x) area(x) / 4
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256)
+specular_build_kernel(int N, float roughness, float cutoff, const float4 *__restrict__ table,
+                      const float *__restrict__ bounds, const long long *__restrict__ offset,
+                      float *__restrict__ weights, float *__restrict__ wsum) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= 6 * N * N) return;
+    const float4 me = table[p];
+    const float alpha = roughness * roughness, alphaSqr = alpha * alpha;
+    float *run = weights + offset[p];
+    float acc = 0.f;
+    for (int s = 0; s < 6; ++s) {
+        const float *b = bounds + (size_t)p * 24 + s * 4;
+        const int xmin = (int)b[0], xmax = (int)b[1], ymin = (int)b[2], ymax = (int)b[3];
+        if (xmin > xmax || ymin > ymax) continue;
+        const int bw = xmax - xmin + 1, n = bw * (ymax - ymin + 1);
+        const float inv_bw = 1.0f / (float)bw;
+        for (int k = lane; k < n; k += 32) {
+            int dy = (int)(((float)k + 0.5f) * inv_bw);
+            int dx = k - dy * bw;
+            if (dx < 0) { --dy; dx += bw; } else if (dx >= bw) { ++dy; dx -= bw; }
+            const float4 o = table[(s * N + ymin + dy) * N + xmin + dx];
+            const float w = pair_weight<TRANSPOSED>(me, o, alphaSqr, cutoff);
+            run[k] = w;
+            acc += w * o.w / 4.0f;
+        }
+        run += n;
+    }
+    if (!TRANSPOSED) {
+        acc = warp_sum(acc);
+        if (lane == 0) wsum[p] = acc;
+    }
+}
+
+// out[p] = scale_p * sum over p's run of weights * src[q]     (src: [6N^2, 4] -- rgb padded to 16 bytes)
+//   forward : src = cubemap * area / 4 (pre-multiplied by the caller), scale_p = 1
+//   backward: src = grad_out (already divided by wsum through autograd), scale_p = area(p) / 4
+// Branch-free inner loop, four pairs per lane and trip: the weight loads (coalesced, streaming) and the 16-byte
+// gathers of one trip are all in flight before the first FMA.
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256)
+specular_apply_kernel(int N, const float4 *__restrict__ table, const float4 *__restrict__ bounds,
+                      const long long *__restrict__ offset, const float *__restrict__ weights,
+                      const float4 *__restrict__ src, float *__restrict__ dst) {
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= 6 * N * N) return;
+    const float *run = weights + offset[p];
+    // lane s < 6 fetches the box of face s; everybody reads it back with a shuffle
+    float4 mine = make_float4(1.f, 0.f, 1.f, 0.f);
+    if (lane < 6) mine = __ldg(bounds + (size_t)p * 6 + lane);
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll 1
+    for (int s = 0; s < 6; ++s) {
+        const int xmin = (int)__shfl_sync(0xffffffffu, mine.x, s), xmax = (int)__shfl_sync(0xffffffffu, mine.y, s);
+        const int ymin = (int)__shfl_sync(0xffffffffu, mine.z, s), ymax = (int)__shfl_sync(0xffffffffu, mine.w, s);
+        if (xmin > xmax || ymin > ymax) continue;
+        const int bw = xmax - xmin + 1, n = bw * (ymax - ymin + 1);
+        const float inv_bw = 1.0f / (float)bw;
+        const float4 *face = src + (size_t)(s * N + ymin) * N + xmin;
+        for (int k0 = lane; k0 < n; k0 += 128) {
+            float w[4];
+            int q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + 32 * u;
+                const bool in = k < n;
+                w[u] = in ? __ldcs(run + k) : 0.0f;
+                const int kk = in ? k : 0;
+                int dy = (int)(((float)kk + 0.5f) * inv_bw);
+                int dx = kk - dy * bw;
+                if (dx < 0) { --dy; dx += bw; } else if (dx >= bw) { ++dy; dx -= bw; }
+                q[u] = dy * N + dx;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 v = __ldg(face + q[u]);
+                cx = fmaf(v.x, w[u], cx); cy = fmaf(v.y, w[u], cy); cz = fmaf(v.z, w[u], cz);
+            }
+        }
+        run += n;
+    }
+    cx = warp_sum(cx); cy = warp_sum(cy); cz = warp_sum(cz);
+    if (lane == 0) {
+        const float sc = TRANSPOSED ? table[p].w / 4.0f : 1.0f;
+        dst[3 * p] = cx * sc; dst[3 * p + 1] = cy * sc; dst[3 * p + 2] = cz * sc;
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int rsdf_specular_build(const float *table, const float *bounds, const long long *offset, int res, float roughness,
+                        float costheta_cutoff, int transposed, float *weights, float *wsum, void *stream) {
+    if (!table || !bounds || !offset || !weights || (!transposed && !wsum) || res < 1) return RSDF_EBADARG;
+    const long long threads = 6LL * res * res * 32;
+    if (transposed)
+        specular_build_kernel<true><<<rsdf_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+            res, roughness, costheta_cutoff, (const float4 *)table, bounds, offset, weights, wsum);
+    else
+        specular_build_kernel<false><<<rsdf_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+            res, roughness, costheta_cutoff, (const float4 *)table, bounds, offset, weights, wsum);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_specular_apply(const float *table, const float *bounds, const long long *offset, const float *weights,
+                        const float *src, int res, int transposed, float *dst, void *stream) {
+    if (!table || !bounds || !offset || !weights || !src || !dst || res < 1) return RSDF_EBADARG;
+    const long long threads = 6LL * res * res * 32;
+    if (transposed)
+        specular_apply_kernel<true><<<rsdf_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+            res, (const float4 *)table, (const float4 *)bounds, offset, weights, (const float4 *)src, dst);
+    else
+        specular_apply_kernel<false><<<rsdf_div_up(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+            res, (const float4 *)table, (const float4 *)bounds, offset, weights, (const float4 *)src, dst);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
 
 int rsdf_cubemap_texel_table(int res, float *table, void *stream) {
     if (!table || res < 1) return RSDF_EBADARG;

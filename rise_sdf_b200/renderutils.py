@@ -81,6 +81,65 @@ def _ndf_bounds(res, roughness, cutoff, device):
     return _bounds[key]
 
 
+# ---- the prefilter as a cached sparse operator (csrc/cubemap.cu: specular_build / specular_apply) ------------------
+# Training rebuilds the pyramid every step (systems/split_occ.py:151-152) from a map that is the only thing that
+# changes: the 1.2 G pair weights of the six levels (4.9 GB per direction) are evaluated once per (res, roughness, cutoff) and
+# streamed from HBM afterwards.  Used when autograd is recording (training); a one-off no-grad build (relighting's
+# EnvSet) runs the direct kernel and allocates nothing.
+OPERATOR_CACHE = True
+OPERATOR_CACHE_MIN_RES = 32
+_operators = {}
+
+
+class _Operator:
+    def __init__(self, res, roughness, cutoff, device):
+        self.c, self.bounds = _ndf_bounds(res, roughness, cutoff, device)
+        b = self.bounds.view(-1, 6, 4)
+        area = ((b[..., 1] - b[..., 0] + 1).clamp(min=0) * (b[..., 3] - b[..., 2] + 1).clamp(min=0)).sum(-1)
+        self.offset = torch.zeros(area.numel() + 1, device=device, dtype=torch.int64)
+        torch.cumsum(area.to(torch.int64), 0, out=self.offset[1:])
+        self.n_pairs = int(self.offset[-1])
+        self.table = texel_table(res, device)
+        # one array per direction: a pair's weight is evaluated from the forward OUTPUT texel's side either way
+        self.weights = torch.empty(max(self.n_pairs, 1), device=device, dtype=torch.float32)
+        self.weights_t = torch.empty(max(self.n_pairs, 1), device=device, dtype=torch.float32)
+        self.wsum = torch.empty(6, res, res, 1, device=device, dtype=torch.float32)
+        for tr, w in ((0, self.weights), (1, self.weights_t)):
+            L.call("rsdf_specular_build", L.ptr(self.table), L.ptr(self.bounds), L.ptr(self.offset), res, float(roughness),
+                   float(self.c), tr, L.ptr(w), L.ptr(self.wsum), L.stream())
+        self.area4 = (self.table[:, 3] / 4.0).view(6, res, res, 1)
+        self.res = res
+
+    def apply(self, src, transposed):
+        """src [6,res,res,3] -> [6,res,res,3]; the kernel gathers 16-byte texels, so the rgb is padded here"""
+        src = torch.nn.functional.pad(src, (0, 1)).contiguous()
+        dst = torch.empty(6, self.res, self.res, 3, device=src.device, dtype=torch.float32)
+        L.call("rsdf_specular_apply", L.ptr(self.table), L.ptr(self.bounds), L.ptr(self.offset),
+               L.ptr(self.weights_t if transposed else self.weights), L.ptr(src), self.res, int(transposed), L.ptr(dst),
+               L.stream())
+        return dst
+
+
+def _operator(res, roughness, cutoff, device):
+    key = (res, roughness, cutoff, str(device))
+    if key not in _operators:
+        _operators[key] = _Operator(res, roughness, cutoff, device)
+    return _operators[key]
+
+
+class _SpecularOperator(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cubemap, op):
+        ctx.op = op
+        rgb = op.apply(cubemap * op.area4, False)
+        return torch.cat([rgb, op.wsum], -1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        return ctx.op.apply(dout[..., 0:3], True), None
+
+
 class _SpecularCubemap(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cubemap, roughness, costheta_cutoff, bounds):
@@ -110,6 +169,10 @@ def specular_cubemap(cubemap, roughness, cutoff=0.99, use_python=False):
     L.require_cuda(cubemap)
     assert cubemap.shape[0] == 6 and cubemap.shape[1] == cubemap.shape[2], \
         "Bad shape for cubemap tensor: %s" % str(cubemap.shape)
-    c, bounds = _ndf_bounds(cubemap.shape[1], roughness, cutoff, cubemap.device)
-    out = _SpecularCubemap.apply(cubemap.float(), roughness, c, bounds)
+    res = cubemap.shape[1]
+    if OPERATOR_CACHE and res >= OPERATOR_CACHE_MIN_RES and torch.is_grad_enabled() and cubemap.requires_grad:
+        out = _SpecularOperator.apply(cubemap.float().contiguous(), _operator(res, roughness, cutoff, cubemap.device))
+    else:
+        c, bounds = _ndf_bounds(res, roughness, cutoff, cubemap.device)
+        out = _SpecularCubemap.apply(cubemap.float(), roughness, c, bounds)
     return out[..., 0:3] / out[..., 3:]

@@ -1,0 +1,61 @@
+"""The CUDA product against outputs of the REFERENCE's own Python (models/neus.py & co., run unmodified on the CPU over
+the oracle's third-party stand-ins by tests/golden/make_ref_host_golden.py): forward images, per-sample fields, loss
+terms and parameter gradients of a configs[1]-shaped training step.  The reference tree does not exist on the GPU box;
+this fixture is how its Python travels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+from helpers import rel_l2  # noqa: E402
+from rise_sdf_b200 import synthetic as syn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_host_neus.npz")
+
+
+def test_neus_training_step_vs_reference_python_golden():
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_ref_host_golden as mk
+    from rise_sdf_b200.neus import NeuSModel, neus_blender_config
+    from rise_sdf_b200.train import neus_loss
+    z = np.load(GOLD)
+    torch.manual_seed(0)
+    m = NeuSModel(neus_blender_config()).cuda()
+    sd = {k[len("state."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("state.")}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(("occupancy_grid" in k or "encoding.params" in k) for k in missing), (missing, unexpected)
+    with torch.no_grad():
+        p = m.geometry.encoding.encoding.params
+        p.copy_(mk.table(p.numel()))
+    m.train()
+    m.randomized = False
+    m.cos_anneal_ratio = mk.RATIO
+    m.occupancy_grid.binaries = syn.analytic_grid("ball")[None].cuda()
+    m.render_step_size = mk.STEP
+    rays, rgb, fg, bg = (t.cuda() for t in syn.training_rays(mk.N_RAYS, seed=6))
+    m.background_color = bg
+    out = m(rays)
+    loss, parts = neus_loss(out, rgb, fg)
+    loss.backward()
+    assert np.array_equal(out["ray_indices"].cpu().numpy(), z["out.ray_indices"])          # bit-exact sample set
+    for k in ("comp_rgb", "opacity", "depth", "comp_rgb_full", "sdf_samples", "sdf_grad_samples", "weights"):
+        a, b = out[k].detach().cpu().numpy(), z["out." + k]
+        assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1.0), (k, np.abs(a - b).max())
+    cond = np.minimum(z["out.opacity"] / 1e-2, 1.0)       # normalised normals: see tests/test_gpu_neus.py
+    assert (np.abs(out["comp_normal"].detach().cpu().numpy() - z["out.comp_normal"]) * cond).max() <= 1e-4
+    assert abs(float(loss) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+    for k, v in parts.items():
+        assert abs(float(v) - float(z["loss." + k])) <= 2e-4 * max(abs(float(z["loss." + k])), 1e-3), k
+    for k, v in m.named_parameters():
+        if v.numel() == 0:
+            continue
+        g = v.grad.detach().cpu()
+        if "encoding.encoding.params" in k:
+            assert abs(float(g.double().norm()) - float(z["grad_norm." + k])) <= 1e-3 * float(z["grad_norm." + k])
+            assert rel_l2(g[::997].numpy(), z["grad_sub." + k]) <= 1e-3, k
+        else:
+            assert rel_l2(g.numpy(), z["grad." + k]) <= 1e-3, (k, rel_l2(g.numpy(), z["grad." + k]))

@@ -135,8 +135,13 @@ def test_diffuse_cubemap_vs_reference(N):
         assert float((cc.grad - r_g).abs().max()) <= 3e-4 * float(r_g.abs().max())  # fp32 atomics (order varies) vs gather
 
 
-@pytest.mark.parametrize("N,roughness", [(16, 1.0), (32, 0.5), (32, 0.08), (64, 0.185)])
-def test_specular_cubemap_vs_reference(N, roughness):
+@pytest.mark.parametrize("cached", [False, True])
+@pytest.mark.parametrize("N,roughness", [(16, 1.0), (32, 0.5), (32, 0.08), (64, 0.185), (128, 0.29), (256, 0.08)])
+def test_specular_cubemap_vs_reference(N, roughness, cached, monkeypatch):
+    """`cached`: the prefilter as a cached sparse operator (pair weights evaluated once, streamed every step) against
+    the direct kernel: both must match the reference's compiled kernels."""
+    monkeypatch.setattr(ru, "OPERATOR_CACHE", cached)
+    monkeypatch.setattr(ru, "OPERATOR_CACHE_MIN_RES", 16)
     g = torch.Generator().manual_seed(N)
     cube = (torch.rand(6, N, N, 3, generator=g) * 0.5 + 0.25)
     cutoff = ru.ndf_cutoff(roughness, 0.99)
