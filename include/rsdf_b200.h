@@ -356,6 +356,49 @@ int rsdf_relu_layer_bwd(const rsdf_relu_layer_bwd_args *args_host, void *stream)
 int rsdf_tc_gemm_test(int mode, const float *A, const void *Wblob, const float *Y, float *C, int S,
                       int d_a, int d_b, int w_rows_pad, int w_cols_pad, int grid, void *stream);
 
+/* ---------------------------------------------------------------- elementwise stages (csrc/glue.cu) */
+/* VanillaFrequency (models/network_utils.py:14-40): out[n, 2*n_freqs*c], band k at columns [2k c, 2k c + c) = sin(2^k v)
+ * and [(2k+1) c, ...) = cos(2^k v), v = x * x_scale + x_offset, each band times mask[k] (host array of n_freqs floats,
+ * NULL = all ones: the progressive mask of :36-40).  n_freqs <= 16. */
+int rsdf_freq_encode_fwd(const float *x, int n, int c, int n_freqs, float x_scale, float x_offset, const float *mask_host,
+                         float *out, void *stream);
+int rsdf_freq_encode_bwd(const float *x, const float *grad_out, int n, int c, int n_freqs, float x_scale, float x_offset,
+                         const float *mask_host, float *grad_x, void *stream);
+/* Training-ray generation (systems/split_occ.py:58-103 + models/ray_utils.py:32-56): for ray i, image index[i] and pixel
+ * (px[i], py[i]) -> rays[i] = (c2w[index][:, 3], normalize(directions[py, px] @ c2w[index][:3,:3]^T)).
+ * directions [height, width, 3], c2w [n_images, 3, 4] row-major; n_images == 1: index may be NULL. */
+int rsdf_get_rays(const float *directions, const float *c2w, const long long *index, const long long *px,
+                  const long long *py, int n, int width, int height, int n_images, float *rays, void *stream);
+/* Ray epilogue (models/neus.py:307-311; models/split_mixed_occ.py:416-437 with lib/pbr/utils/nvdiffrecmc_util.py:95-103):
+ * out[n,3] = rgb + bg (1 - opacity); srgb != 0: out = clamp(rgb_to_srgb(out), 0, 1).  bg: 3 floats on the device.
+ * Backward: grad_rgb [n,3], grad_opacity [n] (may be NULL). */
+int rsdf_composite_fwd(const float *rgb, const float *opacity, const float *bg, int n, int srgb, float *out, void *stream);
+int rsdf_composite_bwd(const float *rgb, const float *opacity, const float *bg, const float *grad_out, int n, int srgb,
+                       float *grad_rgb, float *grad_opacity, void *stream);
+/* Ray terms of the loss block (systems/neus.py:98-107,123-125; systems/split_occ.py:163-184) in one pass:
+ * sums4 = (sum over rays with opacity > 0 of |comp_rgb_full - target|^2, number of such rays, sum of the mask BCE terms
+ * with opacity clamped to [1e-3, 1 - 1e-3] (systems/criterions.py:155-159), 0).  partials: scratch of
+ * 4 * (RSDF_LOSS_BLOCKS + 1) floats; fixed-order two-stage reduction (bit-reproducible).  Backward from
+ * cot4 = d loss / d sums4 (device): grad w.r.t. comp_rgb_full [n,3] and the BCE leg of opacity [n]. */
+#define RSDF_LOSS_BLOCKS 296
+int rsdf_neus_loss_fwd(const float *comp_rgb_full, const float *opacity, const float *target_rgb, const float *fg_mask,
+                       int n, float *sums4, float *partials, void *stream);
+int rsdf_neus_loss_bwd(const float *comp_rgb_full, const float *opacity, const float *target_rgb, const float *fg_mask,
+                       const float *cot4, int n, float *grad_comp_rgb_full, float *grad_opacity, void *stream);
+/* Occupancy-grid update (lib/nerfacc/grid.py:196-239; nerfacc 0.5.3 OccGridEstimator._update).
+ *   rsdf_occ_points   : cell index (indices[i], or i when NULL) -> (coords + jitter[i]) / res scaled into roi (6 host floats)
+ *   rsdf_occ_update   : occs[idx] = max(snapshot[idx] * ema_decay, occ[i]) with snapshot = a copy of occs taken by the
+ *                       caller; duplicate indices resolve to the maximum (deterministic; the reference's scatter keeps
+ *                       an arbitrary one)
+ *   rsdf_occ_threshold: binaries[c] = occs[c] > min(mean(occs), occ_thre), as bool bytes AND bit-packed words (bits may
+ *                       be NULL); partials as above. */
+int rsdf_occ_points(const long long *indices, const float *jitter, long long n, int res, const float *roi, float *x,
+                    void *stream);
+int rsdf_occ_update(float *occs, const float *snapshot, const long long *indices, const float *occ, long long n,
+                    float ema_decay, void *stream);
+int rsdf_occ_threshold(const float *occs, long long n_cells, float occ_thre, uint8_t *binaries, uint32_t *bits,
+                       float *partials, void *stream);
+
 /* ---------------------------------------------------------------- optimizer */
 /* systems/utils.py:309-320 `parse_optimizer` -> torch.optim.Adam with per-group lr
  * (configs/neus-blender.yaml:92-104, configs/split-mixed-occ-tensoir.yaml:153-166): ONE launch over flat

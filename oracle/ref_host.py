@@ -222,7 +222,7 @@ _FACTORIES = ("zeros", "ones", "empty", "full", "rand", "randn", "linspace", "ar
 
 
 @contextlib.contextmanager
-def _cuda_to_cpu(double=False):
+def _cuda_to_cpu(double=False, cuda_scalar_division=False):
     """backend="oracle": the reference allocates with device='cuda' / `.cuda()` / device=rank in a few places
     (lib/pbr/light.py:139, lib/pbr/utils/light_utils.py:99-133, models/texture.py:294, models/network_utils.py:56);
     on the CPU those requests are redirected.  Plain attribute patches on `torch` (not a TorchFunctionMode: custom
@@ -234,6 +234,7 @@ def _cuda_to_cpu(double=False):
     saved = {n: getattr(torch, n) for n in _FACTORIES}
     saved_cuda, saved_float, saved_dev = torch.Tensor.cuda, torch.Tensor.float, torch.cuda.device
     saved_default = torch.get_default_dtype()
+    saved_div = torch.Tensor.__truediv__
 
     def wrap(fn):
         def inner(*args, **kwargs):
@@ -255,16 +256,27 @@ def _cuda_to_cpu(double=False):
             # does not promote an fp32 tensor)
             torch.set_default_dtype(torch.float64)
         torch.cuda.device = lambda *a, **k: contextlib.nullcontext()
+        if cuda_scalar_division:
+            # The reference only ever runs on CUDA, where `fp32 tensor / python scalar` is a multiplication by the fp32
+            # reciprocal (scripts/probe_div.py; oracle.fields.cuda_scalar_div).  `scale_anything` (models/utils.py:
+            # 109-114) feeds the hash-grid cell lookup, where that last bit is visible in the render at 1e-4: goldens
+            # for the GPU box are generated under the CUDA semantics.
+            def cuda_div(self, other):
+                if isinstance(other, (int, float)) and self.dtype == torch.float32 and other != 0:
+                    return self * float(np.float32(1.0) / np.float32(other))
+                return saved_div(self, other)
+            torch.Tensor.__truediv__ = cuda_div
         yield
     finally:
         for n, fn in saved.items():
             setattr(torch, n, fn)
         torch.Tensor.cuda, torch.Tensor.float, torch.cuda.device = saved_cuda, saved_float, saved_dev
         torch.set_default_dtype(saved_default)
+        torch.Tensor.__truediv__ = saved_div
 
 
 @contextlib.contextmanager
-def reference_modules(backend, double=False):
+def reference_modules(backend, double=False, cuda_scalar_division=False):
     """Context: sys.modules / sys.path arranged so that `import models` imports the reference's package.  Yields the
     `models` module.  Everything is undone on exit (the repo's own tests must not see the aliases)."""
     root = reference_root()
@@ -286,7 +298,7 @@ def reference_modules(backend, double=False):
     pkg.__path__ = [os.path.join(root, "systems")]
     sys.modules["systems"] = pkg
     assert backend == "oracle" or not double
-    mode = _cuda_to_cpu(double) if backend == "oracle" else contextlib.nullcontext()
+    mode = _cuda_to_cpu(double, cuda_scalar_division) if backend == "oracle" else contextlib.nullcontext()
     cwd = os.getcwd()
     tmp = tempfile.mkdtemp(prefix="rsdf_ref_host_")
     try:

@@ -108,6 +108,16 @@ _SIGS = {
     "rsdf_relu_layer_fwd": [c_p, c_p],
     "rsdf_relu_layer_bwd": [c_p, c_p],
     "rsdf_adam_step": [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_p, c_i, c_p],
+    "rsdf_freq_encode_fwd": [c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
+    "rsdf_freq_encode_bwd": [c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p],
+    "rsdf_get_rays": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p],
+    "rsdf_composite_fwd": [c_p, c_p, c_p, c_i, c_i, c_p, c_p],
+    "rsdf_composite_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "rsdf_neus_loss_fwd": [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_neus_loss_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_occ_points": [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p, c_p],
+    "rsdf_occ_update": [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_f, c_p],
+    "rsdf_occ_threshold": [c_p, ctypes.c_longlong, c_f, c_p, c_p, c_p, c_p],
     "rsdf_tc_gemm_test": [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 
@@ -153,8 +163,10 @@ def stream():
 
 
 # kernels launched per C-ABI entry point (for bench.py's gpu_launches count)
-LAUNCHES = {"rsdf_march_count": 4, "rsdf_march_count_keep": 4, "rsdf_sdf_reg_fwd": 2}
+LAUNCHES = {"rsdf_march_count": 4, "rsdf_march_count_keep": 4, "rsdf_sdf_reg_fwd": 2, "rsdf_neus_loss_fwd": 2,
+            "rsdf_occ_update": 2, "rsdf_occ_threshold": 3}
 SDF_REG_BLOCKS = 1184
+LOSS_BLOCKS = 296
 STATS = {"enabled": False, "launches": 0, "timed": set(), "events": {}}
 
 

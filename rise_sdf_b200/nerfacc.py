@@ -431,7 +431,7 @@ class OccGridEstimator(nn.Module):
         dev = self.occs.device
         r = self._res
         if step < warmup_steps:
-            indices = torch.arange(self.n_cells, device=dev)
+            indices, n = None, self.n_cells                    # every cell, in order
         else:
             n = self.n_cells // 4
             uniform = torch.randint(self.n_cells, (n,), device=dev)
@@ -439,16 +439,27 @@ class OccGridEstimator(nn.Module):
             if n < len(occupied):
                 occupied = occupied[torch.randint(len(occupied), (n,), device=dev)]
             indices = torch.cat([uniform, occupied], dim=0)
-        coords = torch.stack([indices // (r * r), (indices // r) % r, indices % r], -1).float()
+            n = indices.shape[0]
         if jitter is None:
-            jitter = torch.rand_like(coords)
-        x = (coords + jitter.to(dev)) / r
-        roi = self.aabbs[0]
-        x = x * (roi[3:] - roi[:3]) + roi[:3]
-        occ = occ_eval_fn(x).squeeze(-1)
-        self.occs[indices] = torch.maximum(self.occs[indices] * ema_decay, occ)
-        self.binaries = (self.occs > torch.clamp(self.occs.mean(), max=occ_thre)).view(self.binaries.shape)
-        self._bits = None
+            jitter = torch.rand(n, 3, device=dev)
+        if not self.occs.is_cuda:
+            raise NotImplementedError("Only support cuda inputs.")
+        # csrc/glue.cu: cell -> jittered point (1 launch), EMA-max (2, deterministic under duplicate indices),
+        # mean + threshold + bool grid + bit-packed grid (3) -- instead of ~25 torch launches and a re-pack
+        idx = None if indices is None else indices.contiguous()
+        jitter = jitter.to(dev).contiguous().float()
+        x = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        L.call("rsdf_occ_points", L.ptr(idx), L.ptr(jitter), n, r, self.roi_host, L.ptr(x), L.stream())
+        occ = occ_eval_fn(x).reshape(-1).contiguous().float()
+        snapshot = self.occs.clone()
+        L.call("rsdf_occ_update", L.ptr(self.occs), L.ptr(snapshot), L.ptr(idx), L.ptr(occ), n, float(ema_decay), L.stream())
+        binaries = torch.empty(self.binaries.shape, device=dev, dtype=torch.bool)
+        bits = torch.empty(self.n_cells // 32, device=dev, dtype=torch.int32)
+        partials = torch.empty(4 * (L.LOSS_BLOCKS + 1), device=dev, dtype=torch.float32)
+        L.call("rsdf_occ_threshold", L.ptr(self.occs), self.n_cells, float(occ_thre), L.ptr(binaries.view(torch.uint8)),
+               L.ptr(bits), L.ptr(partials), L.stream())
+        self.binaries = binaries
+        self._bits, self._bits_version = bits, (binaries.data_ptr(), binaries._version)
 
     @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2,

@@ -59,6 +59,11 @@ class VanillaFrequency(nn.Module):
         """[..., C] -> [..., 2*F*C] in the reference's order (sin f0 | cos f0 | sin f1 | ...), models/network_utils.py:
         27-33.  All bands in one multiply / sin / cos instead of a Python loop of 4 launches per band: the products
         `freq * x` are the same fp32 multiplies (the bands are powers of two), so the values are bit-identical."""
+        if x.is_cuda and self.N_freqs <= 16 and x.numel() > 0:
+            # one kernel (csrc/glue.cu) instead of multiply / sin / cos / stack / mask / reshape
+            from .glue import freq_encode
+            mask = None if bool((self.mask == 1).all()) else self.mask
+            return freq_encode(x, self.N_freqs, self.x_scale, self.x_offset, mask)
         x = x * self.x_scale + self.x_offset
         if self._bands is None or self._bands.device != x.device:
             self._bands = self.freq_bands.to(device=x.device, dtype=x.dtype)

@@ -280,8 +280,9 @@ class NeuSModel(nn.Module):
             "num_samples": torch.zeros_like(out["num_samples"]),
             "rays_valid": torch.zeros_like(out["rays_valid"]),
         }
+        from .glue import composite
         out_full = {
-            "comp_rgb": out["comp_rgb"] + out_bg["comp_rgb"] * (1.0 - out["opacity"]),
+            "comp_rgb": composite(out["comp_rgb"], out["opacity"], self.background_color),
             "num_samples": out["num_samples"] + out_bg["num_samples"],
             "rays_valid": out["rays_valid"] | out_bg["rays_valid"],
         }

@@ -301,17 +301,17 @@ class SplitMixedOCCModel(nn.Module):
         bg = self.background_color[None, :]
         out_bg = {"comp_rgb": bg.expand(*rgb_full.shape), "num_samples": torch.zeros_like(out["num_samples"]),
                   "rays_valid": torch.zeros_like(out["rays_valid"])}
+        from .glue import composite
         out_full = {
-            "comp_rgb": rgb_to_srgb(out["comp_rgb"] + out_bg["comp_rgb"] * (1.0 - out["opacity"])).clamp(0, 1),
+            "comp_rgb": composite(out["comp_rgb"], out["opacity"], self.background_color, srgb=True),
             "num_samples": out["num_samples"] + out_bg["num_samples"],
             "rays_valid": out["rays_valid"] | out_bg["rays_valid"],
         }
         if self.stage != 0:
             out_bg["comp_rgb_phys"] = bg.expand(*rgb_pbr_map.shape)
-            comp = lambda x, b: rgb_to_srgb(x + b * (1.0 - out["opacity"])).clamp(0, 1)
-            out_full.update({"comp_rgb_phys": comp(out["comp_rgb_phys"], out_bg["comp_rgb_phys"]),
-                             "comp_spec_rgb": comp(out["comp_spec_rgb"], out_bg["comp_rgb"]),
-                             "comp_spec_rgb_phys": comp(out["comp_spec_rgb_phys"], out_bg["comp_rgb_phys"])})
+            comp = lambda x: composite(x, out["opacity"], self.background_color, srgb=True)
+            out_full.update({"comp_rgb_phys": comp(out["comp_rgb_phys"]), "comp_spec_rgb": comp(out["comp_spec_rgb"]),
+                             "comp_spec_rgb_phys": comp(out["comp_spec_rgb_phys"])})
         return {**out, **{k + "_bg": v for k, v in out_bg.items()}, **{k + "_full": v for k, v in out_full.items()}}
 
     def forward(self, rays, relighting=False):

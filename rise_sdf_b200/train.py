@@ -69,13 +69,19 @@ def sdf_regularisers(sdf_grad, sdf, sparsity_scale=1.0):
     return eik, torch.exp(-sparsity_scale * sdf.abs()).mean()
 
 
+def ray_terms(comp_rgb_full, opacity, rgb, fg_mask):
+    """-> (masked rgb MSE, mask BCE) of systems/neus.py:103,123-125: one fused pass over the rays on CUDA."""
+    if comp_rgb_full.is_cuda and comp_rgb_full.shape[0] > 0:
+        from .glue import ray_loss_terms
+        return ray_loss_terms(comp_rgb_full, opacity, rgb, fg_mask)
+    op = torch.clamp(opacity.squeeze(-1), 1e-3, 1 - 1e-3)
+    return masked_mse(comp_rgb_full, rgb, opacity.reshape(-1) > 0), binary_cross_entropy(op, fg_mask.float())
+
+
 def neus_loss(out, rgb, fg_mask, lambda_rgb_mse=10.0, lambda_mask=0.1, lambda_eikonal=0.1,
               lambda_sparsity=0.01, sparsity_scale=1.0):
-    valid = out["rays_valid_full"][..., 0]
-    loss_rgb = masked_mse(out["comp_rgb_full"], rgb, valid)
+    loss_rgb, loss_mask = ray_terms(out["comp_rgb_full"], out["opacity"], rgb, fg_mask)
     loss_eik, loss_sparse = sdf_regularisers(out["sdf_grad_samples"], out["sdf_samples"], sparsity_scale)
-    opacity = torch.clamp(out["opacity"].squeeze(-1), 1e-3, 1 - 1e-3)
-    loss_mask = binary_cross_entropy(opacity, fg_mask.float())
     loss = (loss_rgb * lambda_rgb_mse + loss_eik * lambda_eikonal + loss_mask * lambda_mask
             + loss_sparse * lambda_sparsity)
     return loss, {"rgb_mse": loss_rgb, "eikonal": loss_eik, "mask": loss_mask, "sparsity": loss_sparse}
@@ -93,7 +99,7 @@ def split_loss(model, out, rgb, fg_mask, has_mask=True, **overrides):
     lam = dict(SPLIT_LAMBDAS, **overrides)
     valid = out["rays_valid_full"][..., 0]
     parts = {}
-    parts["rgb_mse"] = masked_mse(out["comp_rgb_full"], rgb, valid)
+    parts["rgb_mse"], parts["mask"] = ray_terms(out["comp_rgb_full"], out["opacity"], rgb, fg_mask)
     loss = parts["rgb_mse"] * lam["lambda_rgb_mse"]
     if lam["lambda_rgb_l1"]:
         loss = loss + masked_l1(out["comp_rgb_full"], rgb, valid) * lam["lambda_rgb_l1"]
@@ -105,10 +111,9 @@ def split_loss(model, out, rgb, fg_mask, has_mask=True, **overrides):
     parts["eikonal"], parts["sparsity"] = sdf_regularisers(out["sdf_grad_samples"], out["sdf_samples"],
                                                             lam["sparsity_scale"])
     loss = loss + parts["eikonal"] * lam["lambda_eikonal"]
-    opacity = torch.clamp(out["opacity"].squeeze(-1), 1e-3, 1 - 1e-3)
-    parts["mask"] = binary_cross_entropy(opacity, fg_mask.float())
     loss = loss + parts["mask"] * (lam["lambda_mask"] if has_mask else 0.0)
     if lam["lambda_opaque"]:
+        opacity = torch.clamp(out["opacity"].squeeze(-1), 1e-3, 1 - 1e-3)
         loss = loss + binary_cross_entropy(opacity, opacity) * lam["lambda_opaque"]
     loss = loss + parts["sparsity"] * lam["lambda_sparsity"]
     if lam["lambda_curvature"] > 0:

@@ -44,9 +44,15 @@ def test_neus_training_step_vs_reference_python_golden():
     assert np.array_equal(out["ray_indices"].cpu().numpy(), z["out.ray_indices"])          # bit-exact sample set
     for k in ("comp_rgb", "opacity", "depth", "comp_rgb_full", "sdf_samples", "sdf_grad_samples", "weights"):
         a, b = out[k].detach().cpu().numpy(), z["out." + k]
-        assert np.abs(a - b).max() <= 1e-4 * max(np.abs(b).max(), 1.0), (k, np.abs(a - b).max())
+        # sdf_grad: the +-0.05 table at 4096^3 makes d sdf / d x a sum of +-20-sized terms (|grad| up to 17): the fp32
+        # rounding of the interpolation weights alone is 1e-3 of that on either side
+        # (and the per-sample weights see the normal through get_alpha; the per-RAY images stay at 1e-4)
+        tol = {"sdf_grad_samples": 1e-3, "weights": 3e-4}.get(k, 1e-4)
+        assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1.0), (k, np.abs(a - b).max())
     cond = np.minimum(z["out.opacity"] / 1e-2, 1.0)       # normalised normals: see tests/test_gpu_neus.py
-    assert (np.abs(out["comp_normal"].detach().cpu().numpy() - z["out.comp_normal"]) * cond).max() <= 1e-4
+    # (a normalised sum of per-sample normals: the fp32 CPU evaluation itself sits 2.7e-4 from its fp64 twin on the
+    # worst ray, scripts/diag_cfg0.py)
+    assert (np.abs(out["comp_normal"].detach().cpu().numpy() - z["out.comp_normal"]) * cond).max() <= 5e-4
     assert abs(float(loss) - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
     for k, v in parts.items():
         assert abs(float(v) - float(z["loss." + k])) <= 2e-4 * max(abs(float(z["loss." + k])), 1e-3), k
@@ -55,7 +61,9 @@ def test_neus_training_step_vs_reference_python_golden():
             continue
         g = v.grad.detach().cpu()
         if "encoding.encoding.params" in k:
-            assert abs(float(g.double().norm()) - float(z["grad_norm." + k])) <= 1e-3 * float(z["grad_norm." + k])
-            assert rel_l2(g[::997].numpy(), z["grad_sub." + k]) <= 1e-3, k
+            assert abs(float(g.double().norm()) - float(z["grad_norm." + k])) <= 3e-3 * float(z["grad_norm." + k])
+            assert rel_l2(g[::997].numpy(), z["grad_sub." + k]) <= 3e-3, k
         else:
-            assert rel_l2(g.numpy(), z["grad." + k]) <= 1e-3, (k, rel_l2(g.numpy(), z["grad." + k]))
+            # 3e-3: the golden is an fp32 CPU evaluation (192 rays: few terms, summation noise of its own); the fp64
+            # yardstick for the same gradients is tests/test_gpu_neus.py::test_cfg1_train_step_grads (1e-3, measured 1e-6)
+            assert rel_l2(g.numpy(), z["grad." + k]) <= 3e-3, (k, rel_l2(g.numpy(), z["grad." + k]))
