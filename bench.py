@@ -690,6 +690,29 @@ def run_ours(args):
     L.stats_reset(False)
     n_samples = int(out["num_samples"].item())
 
+    # ---- the reduced-precision MLP variant (single fp16 plane, one product per GEMM; tests/test_gpu_mlp_fp16.py) ----
+    variant = None
+    if not args.no_variant:
+        from rise_sdf_b200.network_utils import VanillaMLP
+        VanillaMLP.mlp_precision = "fp16"
+        try:
+            for i in range(3):
+                step_resident(i)
+            ms_v, _ = timed(step_resident, args.steps)
+            L.stats_reset(True, TRAIN_TIMED)
+            timed(step_resident, n_prof)
+            kv = L.stats_times_ms()
+            L.stats_reset(False)
+        finally:
+            VanillaMLP.mlp_precision = "fp32"
+        (ms_v,) = _max_over_ranks([ms_v], dev, world)
+        variant = {"mlp_precision": "fp16 single plane, one tcgen05 product per GEMM, fp32 TMEM accumulation",
+                   "value": world * N_RAYS / (ms_v / args.steps / 1e3), "unit": "rays/s", "ms_per_step": ms_v / args.steps,
+                   "stated_tolerance": "rendered rgb/opacity/depth 5e-3, loss 1e-3, parameter gradients 3e-2 rel-L2 vs "
+                                       "float64 (tests/test_gpu_mlp_fp16.py); NOT the parity path, not the headline",
+                   "kernel_ms_per_step": {k: round(v[1] / n_prof, 4) for k, v in sorted(kv.items())
+                                          if k in ("rsdf_sdf_mlp_fwd", "rsdf_sdf_mlp_bwd", "rsdf_relu_layer_fwd",
+                                                   "rsdf_relu_layer_bwd")}}
     # ---- the reference's GPU build, as far as it can be had on this box (rank 0 of a 1-GPU run) ----
     gref = None
     if world == 1 and not args.no_gpu_reference:
@@ -763,6 +786,8 @@ def run_ours(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if variant:
+        line["mlp_variant_fp16"] = variant
     if gref:
         line["gpu_reference"] = gref
     if split_train:
@@ -793,6 +818,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variant", action="store_true", help="skip the fp16 single-plane MLP variant timing")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip the reference-GPU-kernel comparison and the PyTorch-CUDA stand-in step (1-GPU runs only)")
     ap.add_argument("--no-relight", action="store_true",

@@ -286,6 +286,9 @@ typedef struct rsdf_sdf_mlp {
     const void *w1_blob, *w2_blob, *w3_blob;
     const float *b1, *b2, *b3, *w3_row0;
     int32_t n_in, n_out;
+    int32_t precision;      /* 0: fp32-class (fp16 hi|lo operands, three products per GEMM) -- the parity path;
+                               1: the reduced-precision VARIANT, single fp16 plane / one product (rsdf_sdf_mlp_fwd/bwd only;
+                               tolerance: tests/test_gpu_mlp_fp16.py) */
 } rsdf_sdf_mlp;
 int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float scale0, float shift0,
                      const float *in1, int w1, int n_samples, float *out, float *sdf, float *g0a, float *g0b,
@@ -331,6 +334,7 @@ typedef struct rsdf_relu_layer_fwd_args {
     void *a0_save;
     void *a_out;
     float *rows_out;
+    int32_t fp16;            /* != 0: reduced-precision variant -- streams carry ONE fp16 plane per tile, one product */
 } rsdf_relu_layer_fwd_args;
 typedef struct rsdf_relu_layer_bwd_args {
     const void *w;
@@ -347,6 +351,7 @@ typedef struct rsdf_relu_layer_bwd_args {
     float *gW;
     float *gb_prev;
     float *gb_self;
+    int32_t fp16;
 } rsdf_relu_layer_bwd_args;
 int rsdf_relu_layer_fwd(const rsdf_relu_layer_fwd_args *args_host, void *stream);
 int rsdf_relu_layer_bwd(const rsdf_relu_layer_bwd_args *args_host, void *stream);

@@ -25,14 +25,14 @@ class HashGridMetaC(ctypes.Structure):
 
 class SdfMlpC(ctypes.Structure):
     _fields_ = [("w1_blob", c_p), ("w2_blob", c_p), ("w3_blob", c_p), ("b1", c_p), ("b2", c_p), ("b3", c_p),
-                ("w3_row0", c_p), ("n_in", ctypes.c_int32), ("n_out", ctypes.c_int32)]
+                ("w3_row0", c_p), ("n_in", ctypes.c_int32), ("n_out", ctypes.c_int32), ("precision", ctypes.c_int32)]
 
 
 class ReluFwdC(ctypes.Structure):
     _fields_ = [("w", c_p), ("bias", c_p), ("r_pad", ctypes.c_int32), ("r_real", ctypes.c_int32),
                 ("k_pad", ctypes.c_int32), ("n_samples", ctypes.c_int32), ("inp", c_p * 3), ("in_w", ctypes.c_int32 * 3),
                 ("in_scale", ctypes.c_float * 3), ("in_shift", ctypes.c_float * 3), ("n_in", ctypes.c_int32),
-                ("a_in", c_p), ("a0_save", c_p), ("a_out", c_p), ("rows_out", c_p)]
+                ("a_in", c_p), ("a0_save", c_p), ("a_out", c_p), ("rows_out", c_p), ("fp16", ctypes.c_int32)]
 
 
 class ReluBwdC(ctypes.Structure):
@@ -40,7 +40,7 @@ class ReluBwdC(ctypes.Structure):
                 ("k_real", ctypes.c_int32), ("n_samples", ctypes.c_int32), ("zb_in", c_p), ("g_rows", c_p),
                 ("amax", c_p), ("a_in", c_p), ("zb_out", c_p), ("rows_out", c_p * 3), ("seg_w", ctypes.c_int32 * 3),
                 ("seg_scale", ctypes.c_float * 3), ("first_layer", ctypes.c_int32), ("gW", c_p), ("gb_prev", c_p),
-                ("gb_self", c_p)]
+                ("gb_self", c_p), ("fp16", ctypes.c_int32)]
 
 
 ADAM_MAX_GROUPS = 8

@@ -46,23 +46,36 @@ __device__ __forceinline__ void ld16(const Tid &t, int col, float *v) {
     tc::tmem_ld16(t.tl + (uint32_t)(col + t.col0), v);
     tc::tmem_ld_wait();
 }
-__device__ __forceinline__ void st16(uint8_t *img, const Tid &t, const float *v) {
+// fp16 != 0: the reduced-precision VARIANT -- image streams carry the hi plane only (half the HBM bytes), one product
+// per GEMM.  Default: fp16 hi|lo planes, three products (fp32-class).
+__device__ __forceinline__ void st16(uint8_t *img, const Tid &t, const float *v, int fp16) {
     const int c = t.col0 >> 3;
-    tc::store_chunk(img, 128 * 128, 128, t.f, c, v);
-    tc::store_chunk(img, 128 * 128, 128, t.f, c + 1, v + 8);
+    if (fp16) {
+        tc::store_chunk_hi(img, 128, t.f, c, v);
+        tc::store_chunk_hi(img, 128, t.f, c + 1, v + 8);
+    } else {
+        tc::store_chunk(img, 128 * 128, 128, t.f, c, v);
+        tc::store_chunk(img, 128 * 128, 128, t.f, c + 1, v + 8);
+    }
 }
-// 3-product split GEMM with a run-time k-step count
+__device__ __forceinline__ void store_in_chunk(uint8_t *img, uint32_t plane, int rows, int r, int c, const float *v, int fp16) {
+    if (fp16) tc::store_chunk_hi(img, rows, r, c, v);
+    else tc::store_chunk(img, plane, rows, r, c, v);
+}
+// split GEMM with a run-time k-step count
 __device__ __forceinline__ void gemm3(uint32_t d, const tc::Operand &A, const tc::Operand &B, int ksteps,
-                                      uint32_t idesc, bool accumulate) {
+                                      uint32_t idesc, bool accumulate, int fp16) {
     const uint64_t a_hi = tc::smem_desc(A.addr, A.lbo, A.sbo), a_lo = tc::smem_desc(A.addr + A.plane, A.lbo, A.sbo);
     const uint64_t b_hi = tc::smem_desc(B.addr, B.lbo, B.sbo), b_lo = tc::smem_desc(B.addr + B.plane, B.lbo, B.sbo);
     const uint64_t ak = A.kstep >> 4, bk = B.kstep >> 4;
+    if (!fp16) {
 #pragma unroll 1
-    for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_lo + k * ak, b_hi + k * bk, idesc, accumulate || k > 0);
+        for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_lo + k * ak, b_hi + k * bk, idesc, accumulate || k > 0);
 #pragma unroll 1
-    for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_hi + k * ak, b_lo + k * bk, idesc, true);
+        for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_hi + k * ak, b_lo + k * bk, idesc, true);
+    }
 #pragma unroll 1
-    for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_hi + k * ak, b_hi + k * bk, idesc, true);
+    for (int k = 0; k < ksteps; ++k) tc::mma_f16(d, a_hi + k * ak, b_hi + k * bk, idesc, !fp16 || accumulate || k > 0);
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
@@ -92,6 +105,7 @@ struct FwdArgs {
     uint8_t *a0_save;                // rows mode: keep the staged input as an image stream (may be NULL)
     uint8_t *a_out;                  // hidden layer: stream of relu(W a + b) images [128 x 64]
     float *rows_out;                 // head: [S, r_real] = W a + b
+    int fp16;                        // != 0: single-plane streams, one product
 };
 constexpr uint32_t F_W = 0, F_IN = 65536, F_OUT = F_IN + 2 * IMG128, F_CTRL = F_OUT + 2 * IMG128,
                    F_SMEM = F_CTRL + 64;
@@ -114,7 +128,9 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
     const uint32_t tmem = ct->tmem_slot;
     t.tl = tmem + ((uint32_t)(t.q * 32) << 16);
     const bool rows_in = p.in[0] != nullptr;
-    const uint32_t in_bytes = 2u * (uint32_t)p.k_pad * 128u, in_plane = (uint32_t)p.k_pad * 128u;
+    const uint32_t planes = p.fp16 ? 1u : 2u;
+    const uint32_t in_bytes = planes * (uint32_t)p.k_pad * 128u, in_plane = (uint32_t)p.k_pad * 128u;
+    const uint32_t out_bytes = planes * 128u * 128u;
     const uint32_t w_bytes = 4u * (uint32_t)p.r_pad * (uint32_t)p.k_pad;
     const int n_tiles = (p.S + NS - 1) / NS;
     if (t.tid == 0) {
@@ -169,8 +185,8 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
         __syncthreads();
         if (rows_in) {
             if (fr < p.k_pad) {
-                tc::store_chunk(in_img, in_plane, p.k_pad, fr, cr, rv[0]);
-                tc::store_chunk(in_img, in_plane, p.k_pad, fr, cr + 4, rv[1]);
+                store_in_chunk(in_img, in_plane, p.k_pad, fr, cr, rv[0], p.fp16);
+                store_in_chunk(in_img, in_plane, p.k_pad, fr, cr + 4, rv[1], p.fp16);
             }
         } else {
             if (t.tid == 0 && tile + (int)gridDim.x < n_tiles) {   // prefetch: the other slot's reader has drained
@@ -182,7 +198,7 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
         }
         PHASE_BEGIN()
             gemm3(tmem, tc::op_kmajor(sW, (uint32_t)p.r_pad * p.k_pad * 2, p.r_pad),
-                  tc::op_mnmajor(tc::smem_u32(in_img), in_plane, p.k_pad), p.k_pad / 16, idesc, false);
+                  tc::op_mnmajor(tc::smem_u32(in_img), in_plane, p.k_pad), p.k_pad / 16, idesc, false, p.fp16);
         PHASE_END()
         if (rows_in && tile + (int)gridDim.x < n_tiles) load_rows((tile + gridDim.x) * NS);
         if (p.a_out) {
@@ -190,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
             ld16(t, 0, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + bf, 0.0f);
-            st16(out_img, t, v);
+            st16(out_img, t, v, p.fp16);
         } else if (t.q * 32 < p.r_real) {
             float v[16];
             ld16(t, 0, v);
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
         tc::tc_fence_before();
         __syncthreads();
         if (t.tid == 0) {
-            if (p.a_out) tc::bulk_s2g(p.a_out + (size_t)tile * IMG128, out_img, IMG128);
+            if (p.a_out) tc::bulk_s2g(p.a_out + (size_t)tile * out_bytes, out_img, out_bytes);
             if (rows_in && p.a0_save) tc::bulk_s2g(p.a0_save + (size_t)tile * in_bytes, in_img, in_bytes);
             tc::bulk_commit();
         }
@@ -238,6 +254,7 @@ struct BwdArgs {
     float *gW;                       // [r_real, k_real], atomically accumulated
     float *gb_prev;                  // [k_real] bias gradient of the previous layer (with zb_out)
     float *gb_self;                  // [r_real] bias gradient of this layer (with g_rows)
+    int fp16;                        // != 0: single-plane streams, one product
 };
 constexpr uint32_t B_W = 0, B_RING = 65536, B_OUT = B_RING + 4 * IMG128, B_CTRL = B_OUT + IMG128,
                    B_SMEM = B_CTRL + 64;
@@ -260,8 +277,10 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
     const uint32_t tmem = ct->tmem_slot;
     t.tl = tmem + ((uint32_t)(t.q * 32) << 16);
     const bool rows_in = p.g_rows != nullptr;
-    const uint32_t zb_bytes = 2u * (uint32_t)p.r_pad * 128u, zb_plane = (uint32_t)p.r_pad * 128u;
-    const uint32_t a_bytes = 2u * (uint32_t)p.k_pad * 128u, a_plane = (uint32_t)p.k_pad * 128u;
+    const uint32_t planes = p.fp16 ? 1u : 2u;
+    const uint32_t zb_bytes = planes * (uint32_t)p.r_pad * 128u, zb_plane = (uint32_t)p.r_pad * 128u;
+    const uint32_t a_bytes = planes * (uint32_t)p.k_pad * 128u, a_plane = (uint32_t)p.k_pad * 128u;
+    const uint32_t out_bytes = planes * 128u * 128u;
     const uint32_t w_bytes = 4u * (uint32_t)p.r_pad * (uint32_t)p.k_pad;
     const int n_tiles = (p.S + NS - 1) / NS;
     auto issue_loads = [&](int tile, int st) {       // thread 0
@@ -322,14 +341,14 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
         if (rows_in && t.tid < 128) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { bself += gv[j]; gv[j] *= gsc; }
-            tc::store_chunk(zb_img, zb_plane, p.r_pad, fr, cr, gv);
+            store_in_chunk(zb_img, zb_plane, p.r_pad, fr, cr, gv, p.fp16);
         }
         tc::mbar_wait(&ct->bar_in[st], (uint32_t)(it >> 1) & 1u);
         PHASE_BEGIN()
             gemm3(tmem + ACC, tc::op_kmajor(tc::smem_u32(a_img), a_plane, p.k_pad),
-                  tc::op_kmajor(tc::smem_u32(zb_img), zb_plane, p.r_pad), NS / 16, id_g, it > 0);
+                  tc::op_kmajor(tc::smem_u32(zb_img), zb_plane, p.r_pad), NS / 16, id_g, it > 0, p.fp16);
             gemm3(tmem + T0, tc::op_mnmajor(sW, (uint32_t)p.r_pad * p.k_pad * 2, p.r_pad),
-                  tc::op_mnmajor(tc::smem_u32(zb_img), zb_plane, p.r_pad), p.r_pad / 16, id_d, false);
+                  tc::op_mnmajor(tc::smem_u32(zb_img), zb_plane, p.r_pad), p.r_pad / 16, id_d, false, p.fp16);
         PHASE_END()
         if (rows_in && tile + (int)gridDim.x < n_tiles) load_g((tile + gridDim.x) * NS);
         if (p.zb_out) {
@@ -337,14 +356,19 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
             __syncthreads();
             float v[16], a[16];
             ld16(t, T0, v);
-            tc::load_chunk(a_img, a_plane, p.k_pad, t.f, t.col0 >> 3, a);
-            tc::load_chunk(a_img, a_plane, p.k_pad, t.f, (t.col0 >> 3) + 1, a + 8);
+            if (p.fp16) {
+                tc::load_chunk_hi(a_img, p.k_pad, t.f, t.col0 >> 3, a);
+                tc::load_chunk_hi(a_img, p.k_pad, t.f, (t.col0 >> 3) + 1, a + 8);
+            } else {
+                tc::load_chunk(a_img, a_plane, p.k_pad, t.f, t.col0 >> 3, a);
+                tc::load_chunk(a_img, a_plane, p.k_pad, t.f, (t.col0 >> 3) + 1, a + 8);
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 v[j] = a[j] > 0.0f ? v[j] : 0.0f;
                 bprev += v[j];
             }
-            st16(out_img, t, v);
+            st16(out_img, t, v, p.fp16);
         } else if (t.q * 32 < p.k_real) {
             float v[16];
             ld16(t, T0, v);
@@ -366,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
         tc::tc_fence_before();
         __syncthreads();
         if (t.tid == 0 && p.zb_out) {
-            tc::bulk_s2g(p.zb_out + (size_t)tile * IMG128, out_img, IMG128);
+            tc::bulk_s2g(p.zb_out + (size_t)tile * out_bytes, out_img, out_bytes);
             tc::bulk_commit();
         }
     }

@@ -51,6 +51,7 @@ struct Net {
     const uint8_t *w1, *w2, *w3;          // blobs: [128 x 48], [128 x 128], [48 x 128] (rows x cols, padded)
     const float *b1, *b2, *b3, *w3r0;     // fp32 biases and row 0 of W3 (the sdf head)
     int n_in, n_out;
+    int fp16;                             // != 0: the single-plane fp16 variant
 };
 struct Inputs {
     const float *in0, *in1;               // h0 = cat(in0 * sc0 + sh0, in1)
@@ -74,26 +75,37 @@ __device__ __forceinline__ void ld16(const Tid &t, int col, float *v) {
     tc::tmem_ld16(t.tl + (uint32_t)(col + t.col0), v);
     tc::tmem_ld_wait();
 }
+// SPLIT = true : fp32-class arithmetic, every operand an fp16 hi|lo pair and every GEMM three products (tc.cuh)
+// SPLIT = false: the reduced-precision VARIANT -- single fp16 plane, one product per GEMM (a third of the tensor work,
+//                no lo-plane conversion / stores in the epilogues); tolerance stated in tests/test_gpu_mlp_fp16.py
 // this thread's 16 samples of feature row f -> two 16-byte chunks per plane of a [128 x 64] image
+template <bool SPLIT = true>
 __device__ __forceinline__ void st16(uint8_t *img, const Tid &t, const float *v) {
     const int c = t.col0 >> 3;
-    tc::store_chunk(img, IMG_B_PLANE, HID, t.f, c, v);
-    tc::store_chunk(img, IMG_B_PLANE, HID, t.f, c + 1, v + 8);
+    if (SPLIT) {
+        tc::store_chunk(img, IMG_B_PLANE, HID, t.f, c, v);
+        tc::store_chunk(img, IMG_B_PLANE, HID, t.f, c + 1, v + 8);
+    } else {
+        tc::store_chunk_hi(img, HID, t.f, c, v);
+        tc::store_chunk_hi(img, HID, t.f, c + 1, v + 8);
+    }
 }
 
 // 3-product split GEMM, fully unrolled; descriptors advance by adding to the 14-bit address field
-template <int KSTEPS>
+template <int KSTEPS, bool SPLIT = true>
 __device__ __forceinline__ void gemm3(uint32_t d, const tc::Operand &A, const tc::Operand &B, uint32_t idesc,
                                       bool accumulate) {
     const uint64_t a_hi = tc::smem_desc(A.addr, A.lbo, A.sbo), a_lo = tc::smem_desc(A.addr + A.plane, A.lbo, A.sbo);
     const uint64_t b_hi = tc::smem_desc(B.addr, B.lbo, B.sbo), b_lo = tc::smem_desc(B.addr + B.plane, B.lbo, B.sbo);
     const uint64_t ak = A.kstep >> 4, bk = B.kstep >> 4;
+    if (SPLIT) {
 #pragma unroll
-    for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_lo + k * ak, b_hi + k * bk, idesc, accumulate || k > 0);
+        for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_lo + k * ak, b_hi + k * bk, idesc, accumulate || k > 0);
 #pragma unroll
-    for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_hi + k * ak, b_lo + k * bk, idesc, true);
+        for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_hi + k * ak, b_lo + k * bk, idesc, true);
+    }
 #pragma unroll
-    for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_hi + k * ak, b_hi + k * bk, idesc, true);
+    for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_hi + k * ak, b_hi + k * bk, idesc, SPLIT || accumulate || k > 0);
 }
 
 __device__ __forceinline__ float exp2f_fast(float x) {
@@ -173,9 +185,13 @@ __device__ __forceinline__ void load_chunk8(const RowSrc &r, int tid, int s0, in
             }
     }
 }
+template <bool SPLIT = true>
 __device__ __forceinline__ void store_chunk8(uint8_t *img, const Tid &t, const float *v) {
     const int f = t.tid & 63, c = t.tid >> 6;
-    if (f < KP) tc::store_chunk(img, IMG_S_PLANE, KP, f, c, v);
+    if (f < KP) {
+        if (SPLIT) tc::store_chunk(img, IMG_S_PLANE, KP, f, c, v);
+        else tc::store_chunk_hi(img, KP, f, c, v);
+    }
 }
 
 // TMEM [feature lanes < wa + wb][64 samples] -> two row-major arrays split at feature wa:
@@ -266,7 +282,7 @@ __device__ unsigned long long g_prof[8];
 constexpr uint32_t F_H0 = W_END, F_BIGA = F_H0 + IMG_S_BYTES, F_BIGB = F_BIGA + IMG_B_BYTES,
                    F_CTRL = F_BIGB + IMG_B_BYTES, F_SMEM = F_CTRL + 64;
 
-template <bool WITH_GRAD>
+template <bool WITH_GRAD, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *__restrict__ sdf,
                float *__restrict__ g0a, float *__restrict__ g0b) {
@@ -304,10 +320,10 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
     if ((int)blockIdx.x < n_tiles) load_chunk8(src_h, t.tid, blockIdx.x * NS, in.S, hv);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int s0 = tile * NS;
-        store_chunk8(h0_img, t, hv);
+        store_chunk8<SPLIT>(h0_img, t, hv);
         // P1: Z1 = W1 h0
         PHASE_BEGIN()
-            gemm3<KP / 16>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
+            gemm3<KP / 16, SPLIT>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
         PHASE_END()
         // prefetch the next tile's inputs; they land while this tile computes
         if (tile + (int)gridDim.x < n_tiles) load_chunk8(src_h, t.tid, (tile + gridDim.x) * NS, in.S, hv);
@@ -316,11 +332,11 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
             ld16(t, Z1, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
-            st16(big_a, t, v);
+            st16<SPLIT>(big_a, t, v);
         }
         // P2: Z2 = W2 a1
         PHASE_BEGIN()
-            gemm3<HID / 16>(tmem + Z2, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+            gemm3<HID / 16, SPLIT>(tmem + Z2, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
         PHASE_END()
         {
             float v[16], u[16];
@@ -332,14 +348,14 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
                 v[j] = a;
                 u[j] = sg * w30f;
             }
-            st16(big_a, t, v);                            // a2 (a1's MMA has drained)
-            if (WITH_GRAD) st16(big_b, t, u);             // u2 = s2 . W3[0,:]
+            st16<SPLIT>(big_a, t, v);                            // a2 (a1's MMA has drained)
+            if (WITH_GRAD) st16<SPLIT>(big_b, t, u);             // u2 = s2 . W3[0,:]
         }
         // P3: out = W3 a2 (lanes >= 48 are don't-care);  v1 = W2^T u2
         PHASE_BEGIN()
-            gemm3<HID / 16>(tmem + T0, tc::op_kmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+            gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_kmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
             if (WITH_GRAD)
-                gemm3<HID / 16>(tmem + T1, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
+                gemm3<HID / 16, SPLIT>(tmem + T1, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
         PHASE_END()
         store_rows(out, net.n_out, 1.0f, nullptr, 0, s0, in.S, t, T0, b3f, nullptr);
         if (sdf && t.q == 0) {            // the sdf head (feature row 0) once more as its own [S] array
@@ -365,10 +381,10 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
             ld16(t, Z1, z);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] *= sp_sig(z[j] + b1f);
-            st16(big_a, t, v);                            // u1 = s1 . v1
+            st16<SPLIT>(big_a, t, v);                            // u1 = s1 . v1
             // P4: g0 = W1^T u1 (lanes >= 48 don't-care)
             PHASE_BEGIN()
-                gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
+                gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
             PHASE_END()
             store_rows(g0a, in.w0, 1.0f, g0b, in.w1, s0, in.S, t, T0, 0.0f, nullptr);
         }
@@ -395,7 +411,7 @@ struct Grads {
 
 // CHAIN = false: no cotangent reaches g0 (plain first-order backward, e.g. the finite-difference evaluations
 // of the split-sum config): the gradient-chain GEMMs and three of the seven epilogue passes drop out.
-template <bool CHAIN>
+template <bool CHAIN, bool SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -494,14 +510,14 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
                 gov[j] *= sc; ggv[j] *= sc;
                 hw[j] = hv[j] * swsc[8 * cs + j];
             }
-            store_chunk8(h0_img, t, hv);
-            store_chunk8(h0w_img, t, hw);
-            store_chunk8(go_img, t, gov);
-            store_chunk8(gg_img, t, ggv);
+            store_chunk8<SPLIT>(h0_img, t, hv);
+            store_chunk8<SPLIT>(h0w_img, t, hw);
+            store_chunk8<SPLIT>(go_img, t, gov);
+            store_chunk8<SPLIT>(gg_img, t, ggv);
         }
         // P1: Z1 = W1 h0
         PHASE_BEGIN()
-            gemm3<KP / 16>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
+            gemm3<KP / 16, SPLIT>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
         PHASE_END()
         if (tile + (int)gridDim.x < n_tiles) load_tile((tile + gridDim.x) * NS);      // prefetch the next tile's rows
         const float *wsc = swsc + t.col0, *inv = sinv + t.col0;    // per-sample factors (smem broadcasts)
@@ -510,11 +526,11 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
             ld16(t, Z1, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
-            st16(big_a, t, v);                            // a1
+            st16<SPLIT>(big_a, t, v);                            // a1
         }
         // P2: Z2 = W2 a1
         PHASE_BEGIN()
-            gemm3<HID / 16>(tmem + Z2, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+            gemm3<HID / 16, SPLIT>(tmem + Z2, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
         PHASE_END()
         {
             float v[16], u[16];
@@ -526,17 +542,17 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
                 v[j] = a * wsc[j];
                 u[j] = sg * w30f;
             }
-            st16(big_a, t, v);                            // a2 * 2^(K-k_s)  (weight-gradient operand only)
-            if (CHAIN) st16(big_b, t, u);                 // u2
+            st16<SPLIT>(big_a, t, v);                            // a2 * 2^(K-k_s)  (weight-gradient operand only)
+            if (CHAIN) st16<SPLIT>(big_b, t, u);                 // u2
         }
         // P3: gW3^T += a2 g_out^T ; v1 = W2^T u2 ; ub1 = W1 g_g0   (no chain: ab2 = W3^T g_out right away)
         PHASE_BEGIN()
-            gemm3<KS>(tmem + AW3, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGO, IMG_S_PLANE, KP), id_g48, acc);
+            gemm3<KS, SPLIT>(tmem + AW3, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGO, IMG_S_PLANE, KP), id_g48, acc);
             if (CHAIN) {
-                gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
-                gemm3<KP / 16>(tmem + T1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sGG, IMG_S_PLANE, KP), id_kn, false);
+                gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
+                gemm3<KP / 16, SPLIT>(tmem + T1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sGG, IMG_S_PLANE, KP), id_kn, false);
             } else {
-                gemm3<KP / 16>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
+                gemm3<KP / 16, SPLIT>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
             }
         PHASE_END()
         float zp[16], vb[16];                             // z1-bar (chain part) and v1-bar, kept in registers
@@ -553,23 +569,23 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
                 zp[j] = v[j] * ub[j] * ds;
                 v[j] *= sg * wsc[j];
             }
-            st16(big_a, t, v);                            // u1 * 2^(K-k_s) = s1 . v1  (weight-gradient operand)
+            st16<SPLIT>(big_a, t, v);                            // u1 * 2^(K-k_s) = s1 . v1  (weight-gradient operand)
             ld16(t, Z2, z);
 #pragma unroll
             for (int j = 0; j < 16; ++j) z[j] = sp_sig(z[j] + b2f) * w30f * wsc[j];
-            st16(big_b, t, z);                            // u2 * 2^(K-k_s)  (v1's MMA has drained)
+            st16<SPLIT>(big_b, t, z);                            // u2 * 2^(K-k_s)  (v1's MMA has drained)
         }
         if (CHAIN) {
             // P4: gW1 += u1 g_g0^T
             PHASE_BEGIN()
-                gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGG, IMG_S_PLANE, KP), id_g48, acc);
+                gemm3<KS, SPLIT>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGG, IMG_S_PLANE, KP), id_g48, acc);
             PHASE_END()
-            st16(big_a, t, vb);                           // v1-bar
+            st16<SPLIT>(big_a, t, vb);                           // v1-bar
             // P5: gW2 += u2 vb1^T ; ub2 = W2 vb1 ; ab2 = W3^T g_out
             PHASE_BEGIN()
-                gemm3<KS>(tmem + AW2, tc::op_kmajor(sB, IMG_B_PLANE, HID), tc::op_kmajor(sA, IMG_B_PLANE, HID), id_g128, acc);
-                gemm3<HID / 16>(tmem + T0, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
-                gemm3<KP / 16>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
+                gemm3<KS, SPLIT>(tmem + AW2, tc::op_kmajor(sB, IMG_B_PLANE, HID), tc::op_kmajor(sA, IMG_B_PLANE, HID), id_g128, acc);
+                gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
+                gemm3<KP / 16, SPLIT>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
             PHASE_END()
         }
         {
@@ -591,16 +607,16 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
                 b2acc = fmaf(zb, inv[j], b2acc);
                 z[j] = zb;
             }
-            st16(big_a, t, z);                            // z2-bar
+            st16<SPLIT>(big_a, t, z);                            // z2-bar
             ld16(t, Z1, z);
 #pragma unroll
             for (int j = 0; j < 16; ++j) z[j] = sp_act(z[j] + b1f) * wsc[j];
-            st16(big_b, t, z);                            // a1 * 2^(K-k_s)
+            st16<SPLIT>(big_b, t, z);                            // a1 * 2^(K-k_s)
         }
         // P6: gW2 += zb2 a1^T ; ab1 = W2^T zb2
         PHASE_BEGIN()
-            gemm3<KS>(tmem + AW2, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sB, IMG_B_PLANE, HID), id_g128, CHAIN || acc);
-            gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
+            gemm3<KS, SPLIT>(tmem + AW2, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sB, IMG_B_PLANE, HID), id_g128, CHAIN || acc);
+            gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
         PHASE_END()
         {
             float ab[16], z[16];
@@ -612,12 +628,12 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
                 b1acc = fmaf(zb, inv[j], b1acc);
                 z[j] = zb;
             }
-            st16(big_a, t, z);                            // z1-bar
+            st16<SPLIT>(big_a, t, z);                            // z1-bar
         }
         // P7: gW1 += zb1 h0^T ; d/d h0 = W1^T zb1
         PHASE_BEGIN()
-            gemm3<KS>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sH0W, IMG_S_PLANE, KP), id_g48, CHAIN || acc);
-            gemm3<HID / 16>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
+            gemm3<KS, SPLIT>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sH0W, IMG_S_PLANE, KP), id_g48, CHAIN || acc);
+            gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
         PHASE_END()
         if (g.g_in0 || g.g_in1) store_rows(g.g_in0, in.w0, in.sc0, g.g_in1, in.w1, s0, in.S, t, T0, 0.0f, sinv);
         __syncthreads();                                  // sinv/swsc are rewritten by the next tile
@@ -867,7 +883,7 @@ bool check_net(const rsdf_sdf_mlp *n) {
 }
 Net to_net(const rsdf_sdf_mlp *n) {
     return Net{(const uint8_t *)n->w1_blob, (const uint8_t *)n->w2_blob, (const uint8_t *)n->w3_blob,
-               n->b1, n->b2, n->b3, n->w3_row0, n->n_in, n->n_out};
+               n->b1, n->b2, n->b3, n->w3_row0, n->n_in, n->n_out, n->precision};
 }
 
 }  // namespace
@@ -905,10 +921,16 @@ int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
     const int n_tiles = (n_samples + NS - 1) / NS;
     const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
     cudaError_t e;
+#define RSDF_FWD(G, SP)                                                                                          \
+    {                                                                                                            \
+        e = cudaFuncSetAttribute(sdf_fwd_kernel<G, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM); \
+        if (e != cudaSuccess) return (int)e;                                                                     \
+        sdf_fwd_kernel<G, SP><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, g0a, g0b); \
+    }
     if (g0a) {
-        e = cudaFuncSetAttribute(sdf_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        sdf_fwd_kernel<true><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, g0a, g0b);
+        if (net->precision) RSDF_FWD(true, false) else RSDF_FWD(true, true)
+    } else if (net->precision) {
+        RSDF_FWD(false, false)          // (the two-group inference kernels below are fp32-class only)
     } else {
         const int pairs = (n_tiles + 1) / 2;
         const int eg = pairs < RSDF_NUM_SMS ? pairs : RSDF_NUM_SMS;
@@ -939,14 +961,16 @@ int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
     const int n_tiles = (n_samples + NS - 1) / NS;
     const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
     cudaError_t e;
+#define RSDF_BWD(C, SP)                                                                                          \
+    {                                                                                                            \
+        e = cudaFuncSetAttribute(sdf_bwd_kernel<C, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM); \
+        if (e != cudaSuccess) return (int)e;                                                                     \
+        sdf_bwd_kernel<C, SP><<<grid, THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);               \
+    }
     if (g_g0a || g_g0b) {
-        e = cudaFuncSetAttribute(sdf_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        sdf_bwd_kernel<true><<<grid, THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);
+        if (net->precision) RSDF_BWD(true, false) else RSDF_BWD(true, true)
     } else {
-        e = cudaFuncSetAttribute(sdf_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        sdf_bwd_kernel<false><<<grid, THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);
+        if (net->precision) RSDF_BWD(false, false) else RSDF_BWD(false, true)
     }
     RSDF_LAUNCH_CHECK();
     return 0;

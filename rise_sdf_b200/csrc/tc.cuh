@@ -197,6 +197,16 @@ __device__ __forceinline__ void store_chunk(uint8_t *img, uint32_t plane_bytes, 
     *reinterpret_cast<uint4 *>(img + off) = h;
     *reinterpret_cast<uint4 *>(img + plane_bytes + off) = l;
 }
+// single-plane variant: 8 consecutive columns of row r as fp16 (round to nearest, saturating)
+__device__ __forceinline__ void store_chunk_hi(uint8_t *img, int rows, int r, int c, const float *v) {
+    uint4 h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(v[3]), "f"(v[2]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.z) : "f"(v[5]), "f"(v[4]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.w) : "f"(v[7]), "f"(v[6]));
+    const uint32_t off = (uint32_t)c * (uint32_t)(rows * 16) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    *reinterpret_cast<uint4 *>(img + off) = h;
+}
 // read back 8 columns of row r as fp32 (hi + lo)
 __device__ __forceinline__ void load_chunk(const uint8_t *img, uint32_t plane_bytes, int rows, int r, int c,
                                            float *v) {
@@ -210,6 +220,17 @@ __device__ __forceinline__ void load_chunk(const uint8_t *img, uint32_t plane_by
                    __half2float(__ushort_as_half((unsigned short)(ll[k] & 0xFFFFu)));
         v[2 * k + 1] = __half2float(__ushort_as_half((unsigned short)(hh[k] >> 16))) +
                        __half2float(__ushort_as_half((unsigned short)(ll[k] >> 16)));
+    }
+}
+
+__device__ __forceinline__ void load_chunk_hi(const uint8_t *img, int rows, int r, int c, float *v) {
+    const uint32_t off = (uint32_t)c * (uint32_t)(rows * 16) + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    const uint4 h = *reinterpret_cast<const uint4 *>(img + off);
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[2 * k] = __half2float(__ushort_as_half((unsigned short)(hh[k] & 0xFFFFu)));
+        v[2 * k + 1] = __half2float(__ushort_as_half((unsigned short)(hh[k] >> 16)));
     }
 }
 

@@ -246,6 +246,11 @@ class VanillaMLP(nn.Module):
         return self.forward(torch.cat(segs, dim=-1))
 
     _packed = None
+    # "fp32": every GEMM as three fp16 products of hi|lo operands with fp32 accumulation -- fp32-class, the parity path.
+    # "fp16": the reduced-precision VARIANT named by the north star -- single fp16 plane, one product per GEMM, half
+    #         the activation-stream bytes (fused SDF field fwd/bwd and the ReLU training nets).  Stated tolerance:
+    #         tests/test_gpu_mlp_fp16.py (outputs 2e-3 of their scale; end to end: images 5e-3, gradients 3e-2 rel-L2).
+    mlp_precision = "fp32"
     fused_inference = True      # class-wide switches (tests compare the kernel and the torch paths)
     tc_training = True
     fused_training = True

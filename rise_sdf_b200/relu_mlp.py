@@ -24,8 +24,14 @@ def supports(mlp, n_in=None):
             and (n_in or mlp.dim_in) <= 128 and mlp.dim_out <= 16)
 
 
-def _stream(n_tiles, rows, device):
-    return torch.empty(n_tiles, 2 * rows * 128, dtype=torch.uint8, device=device)
+def _fp16():
+    from .network_utils import VanillaMLP
+    return 1 if VanillaMLP.mlp_precision == "fp16" else 0
+
+
+def _stream(n_tiles, rows, device, fp16=0):
+    """operand-image stream: per 64-sample tile an fp16 hi|lo pair of [rows x 64] planes (one plane in the fp16 variant)"""
+    return torch.empty(n_tiles, (1 if fp16 else 2) * rows * 128, dtype=torch.uint8, device=device)
 
 
 class _ReluMLP(torch.autograd.Function):
@@ -44,14 +50,15 @@ class _ReluMLP(torch.autograd.Function):
         out = torch.empty(S, n_out, device=dev, dtype=torch.float32)
         blobs = [pack_weight(W, HID if i + 1 < len(Ws) else 16, k0 if i == 0 else HID) for i, W in enumerate(Ws)]
         acts = []                                                        # a_0 (input image stream), a_1, ..., a_L
+        fp16 = ctx.fp16 = _fp16()
         if S:
-            a0 = _stream(n_tiles, k0, dev)
+            a0 = _stream(n_tiles, k0, dev, fp16)
             acts.append(a0)
             for i in range(len(Ws) - 1):
                 p = L.ReluFwdC()
                 p.w, p.bias = blobs[i].data_ptr(), bs[i].data_ptr()
-                p.r_pad, p.r_real, p.k_pad, p.n_samples = HID, HID, (k0 if i == 0 else HID), S
-                a_out = _stream(n_tiles, HID, dev)
+                p.r_pad, p.r_real, p.k_pad, p.n_samples, p.fp16 = HID, HID, (k0 if i == 0 else HID), S, fp16
+                a_out = _stream(n_tiles, HID, dev, fp16)
                 if i == 0:
                     for g, sg in enumerate(segs):
                         p.inp[g], p.in_w[g] = sg.data_ptr(), sg.shape[1]
@@ -64,7 +71,7 @@ class _ReluMLP(torch.autograd.Function):
                 acts.append(a_out)
             p = L.ReluFwdC()
             p.w, p.bias = blobs[-1].data_ptr(), bs[-1].data_ptr()
-            p.r_pad, p.r_real, p.k_pad, p.n_samples = 16, n_out, HID, S
+            p.r_pad, p.r_real, p.k_pad, p.n_samples, p.fp16 = 16, n_out, HID, S, fp16
             p.a_in, p.rows_out = acts[-1].data_ptr(), out.data_ptr()
             L.call("rsdf_relu_layer_fwd", ctypes.byref(p), L.stream())
         ctx.n_seg, ctx.scales, ctx.seg_w = n_seg, [float(s) for s in scales], [s.shape[1] for s in segs]
@@ -100,7 +107,7 @@ class _ReluMLP(torch.autograd.Function):
                 p.w = ctx.blobs[i].data_ptr()
                 p.r_pad, p.r_real = (16, n_out) if head else (HID, HID)
                 p.k_pad, p.k_real = (ctx.k0, ctx.n_in) if first else (HID, HID)
-                p.n_samples, p.amax, p.a_in = S, amax.data_ptr(), ctx.acts[i].data_ptr()
+                p.n_samples, p.amax, p.a_in, p.fp16 = S, amax.data_ptr(), ctx.acts[i].data_ptr(), ctx.fp16
                 if head:
                     p.g_rows, p.gb_self = g_out.data_ptr(), gbs[i].data_ptr()
                 else:
@@ -111,7 +118,7 @@ class _ReluMLP(torch.autograd.Function):
                         p.seg_w[g], p.seg_scale[g] = w, ctx.scales[g]
                         p.rows_out[g] = None if g_segs[g] is None else g_segs[g].data_ptr()
                 else:
-                    zb_next = _stream(n_tiles, HID, dev)
+                    zb_next = _stream(n_tiles, HID, dev, ctx.fp16)
                     p.zb_out, p.gb_prev = zb_next.data_ptr(), gbs[i - 1].data_ptr()
                 p.gW = gWs[i].data_ptr()
                 L.call("rsdf_relu_layer_bwd", ctypes.byref(p), L.stream())

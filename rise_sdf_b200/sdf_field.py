@@ -20,6 +20,12 @@ from .fused_mlp import pack_weight
 HID, KP = 128, 48
 
 
+def _fp16():
+    """The reduced-precision MLP variant (VanillaMLP.mlp_precision = "fp16"): single fp16 plane, one product."""
+    from .network_utils import VanillaMLP
+    return 1 if VanillaMLP.mlp_precision == "fp16" else 0
+
+
 def supports(mlp, dim_in=None):
     """True when `mlp` is the SDF-shaped VanillaMLP the fused kernels are built for."""
     return (getattr(mlp, "sphere_init", False) and mlp.n_hidden_layers == 2 and mlp.n_neurons == HID
@@ -34,6 +40,7 @@ def _net_struct(W1, b1, W2, b2, W3, b3):
     c.w1_blob, c.w2_blob, c.w3_blob = (k.data_ptr() for k in keep[:3])
     c.b1, c.b2, c.b3, c.w3_row0 = (k.data_ptr() for k in keep[3:])
     c.n_in, c.n_out = W1.shape[1], W3.shape[0]
+    c.precision = _fp16()
     return c, keep
 
 
@@ -181,7 +188,7 @@ class PackedSDF:
         self.mlp, self._key, self._net, self._keep = mlp, None, None, None
 
     def _struct(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.mlp.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in self.mlp.parameters()) + (_fp16(),)
         if key != self._key:
             with torch.no_grad():
                 (W1, b1), (W2, b2), (W3, b3) = self.mlp.effective_weights()
@@ -201,7 +208,7 @@ class PackedSDF:
         if S:
             # measured (3.34 M evaluations): sdf-only 0.79 ms on the TMEM-operand kernel vs 1.14 ms on the smem-operand
             # one; full 48-wide output 1.50 vs 1.38 ms (row-per-thread output stores) -> each variant on its faster kernel
-            if PackedSDF.tensor_memory_operands and (sdf_only or PackedSDF.tensor_memory_full_output):
+            if PackedSDF.tensor_memory_operands and (sdf_only or PackedSDF.tensor_memory_full_output) and not _fp16():
                 L.call("rsdf_sdf_mlp_eval", ctypes.byref(self._struct()), L.ptr(in0), in0.shape[1], float(scale0),
                        float(shift0), L.ptr(in1), 0 if in1 is None else in1.shape[1], S, L.ptr(out), L.ptr(sdf), L.stream())
             else:
