@@ -239,3 +239,45 @@ def load_env_latlong(fn, device="cuda"):
     """Lat-long environment map as the tensor `EnvironmentLightMipCube.relight` / `EnvSet` take
     (`lib/pbr/light.py:155-158`)."""
     return torch.tensor(load_image(fn).copy(), dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------------------- image writers
+def save_png(path, img):
+    """utils/mixins.py `save_image_grid` / `save_rgb_image` write 8-bit PNGs through cv2; this is a dependency-free
+    writer (zlib from the standard library) for rendered frames: img [H, W, 3|1] float in [0, 1] (torch or numpy)."""
+    import struct
+    import zlib
+    import numpy as np
+    a = img.detach().cpu().numpy() if hasattr(img, "detach") else np.asarray(img)
+    if a.ndim == 2:
+        a = a[..., None]
+    a = (np.clip(a, 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)
+    h, w, c = a.shape
+    assert c in (1, 3)
+    raw = b"".join(b"\x00" + a[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    png = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2 if c == 3 else 0, 0, 0, 0))
+           + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+    with open(path, "wb") as f:
+        f.write(png)
+
+
+def save_exr_or_hdr(path, img):
+    """Float frames (utils/mixins.py writes .exr through pyexr): `.hdr` through this module's own Radiance codec, `.exr`
+    through OpenCV when its EXR codec is enabled."""
+    a = img.detach().cpu().numpy() if hasattr(img, "detach") else img
+    if path.lower().endswith(".hdr"):
+        return write_hdr(path, a)
+    import os
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    import cv2
+    if not cv2.imwrite(path, a[..., ::-1].astype("float32")):
+        raise RuntimeError(f"OpenCV could not write {path}")
+
+
+def save_level_grid(path, level):
+    """The isosurface level grid (VolumeSDF.isosurface_level) as a raw .npy volume for an external marching-cubes tool."""
+    import numpy as np
+    np.save(path, level.detach().cpu().numpy() if hasattr(level, "detach") else level)

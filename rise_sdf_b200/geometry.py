@@ -222,6 +222,61 @@ class VolumeSDF(nn.Module):
         rv = [v if self.training else v.detach() for v in rv]
         return rv[0] if len(rv) == 1 else rv
 
+    # ------------------------------------------------------------------ isosurface query (models/geometry.py:76-112)
+    @torch.no_grad()
+    def forward_level(self, points):
+        """models/geometry.py:294-299: sdf at world-space points, no gradients (sdf-only inference kernel)."""
+        x01 = contract_to_unisphere(points.reshape(-1, 3), self.radius, self.contraction_type)
+        sdf = self._field(x01.contiguous().float(), sdf_only=True).view(*points.shape[:-1])
+        if "sdf_activation" in self.config:
+            from .network_utils import get_activation
+            sdf = get_activation(self.config.sdf_activation)(sdf + float(self.config.sdf_bias))
+        return sdf
+
+    @torch.no_grad()
+    def isosurface_level(self, resolution=512, vmin=None, vmax=None, chunk=1 << 22, out=None):
+        """The level grid `BaseImplicitGeometry.isosurface_` evaluates before marching cubes (models/geometry.py:76-91):
+        sdf at the resolution^3 vertices of linspace(0, 1, resolution)^3 scaled into [vmin, vmax] (default: the whole
+        [-radius, radius]^3 box), x-major like `MarchingCubeHelper.grid_vertices` (:43-49).  The reference moves 2 M-point
+        chunks to the GPU and back (`.cpu()` per chunk); here the vertices are generated on the device chunk by chunk
+        (nothing but the [resolution^3] result is ever materialised: 512 MB at 512^3) and each chunk is one hash-grid
+        launch + one sdf-only tcgen05 inference launch.  Returns a float32 tensor [resolution, resolution, resolution]."""
+        r = int(resolution)
+        dev = next(self.parameters()).device
+        lo = torch.as_tensor([-self.radius] * 3 if vmin is None else vmin, dtype=torch.float32, device=dev)
+        hi = torch.as_tensor([self.radius] * 3 if vmax is None else vmax, dtype=torch.float32, device=dev)
+        level = out if out is not None else torch.empty(r ** 3, device=dev, dtype=torch.float32)
+        lin = torch.linspace(0.0, 1.0, r, device=dev)
+        for s in range(0, r ** 3, chunk):
+            idx = torch.arange(s, min(s + chunk, r ** 3), device=dev)
+            v = torch.stack([lin[idx // (r * r)], lin[(idx // r) % r], lin[idx % r]], -1)
+            level[s:s + idx.numel()] = self.forward_level(v * (hi - lo) + lo)       # scale_anything((0,1) -> (vmin, vmax))
+        return level.view(r, r, r)
+
+    @torch.no_grad()
+    def isosurface_bounds(self, level, vmin=None, vmax=None, threshold=0.0):
+        """World-space bounding box of the level set: the cells whose corner values straddle `threshold`.  The reference
+        takes it from the coarse marching-cubes mesh (models/geometry.py:104-110) to place the fine grid; marching cubes
+        itself (PyMCubes, a CPU third-party dependency) is not part of the path."""
+        r = level.shape[0]
+        dev = level.device
+        lo = torch.as_tensor([-self.radius] * 3 if vmin is None else vmin, dtype=torch.float32, device=dev)
+        hi = torch.as_tensor([self.radius] * 3 if vmax is None else vmax, dtype=torch.float32, device=dev)
+        inside = level > threshold
+        cross = torch.zeros(r, r, r, dtype=torch.bool, device=dev)
+        for d in range(3):
+            a, b = inside.narrow(d, 0, r - 1), inside.narrow(d, 1, r - 1)
+            c = a != b
+            cross.narrow(d, 0, r - 1).logical_or_(c)
+            cross.narrow(d, 1, r - 1).logical_or_(c)
+        nz = torch.nonzero(cross)
+        if nz.numel() == 0:
+            return None
+        mn, mx = nz.min(0).values.float() / (r - 1), nz.max(0).values.float() / (r - 1)
+        bmin, bmax = mn * (hi - lo) + lo, mx * (hi - lo) + lo
+        pad = (bmax - bmin) * 0.1                                                  # :106-107
+        return (bmin - pad).clamp(-self.radius, self.radius), (bmax + pad).clamp(-self.radius, self.radius)
+
     def update_step(self, epoch, global_step):
         update_module_step(self.encoding, epoch, global_step)
         update_module_step(self.network, epoch, global_step)

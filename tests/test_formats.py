@@ -131,3 +131,19 @@ def test_reference_state_dict_quirks():
     sd["model.geometry.network.layers.0.bias"] = torch.zeros(7)
     with pytest.raises(RuntimeError):
         fm.load_reference_state_dict(b, sd)
+
+
+def test_png_writer_round_trips_through_opencv(tmp_path):
+    """formats.save_png (stdlib zlib) is decoded by cv2.imread to the same 8-bit pixels."""
+    import cv2
+    import numpy as np
+    from rise_sdf_b200 import formats
+    g = np.random.default_rng(0)
+    img = g.random((37, 53, 3)).astype(np.float32)
+    p = str(tmp_path / "frame.png")
+    formats.save_png(p, img)
+    back = cv2.imread(p, cv2.IMREAD_COLOR)[..., ::-1]
+    assert back.shape == (37, 53, 3)
+    assert np.array_equal(back, (np.clip(img, 0, 1) * 255.0 + 0.5).astype(np.uint8))
+    formats.save_png(str(tmp_path / "depth.png"), img[..., 0])
+    assert cv2.imread(str(tmp_path / "depth.png"), cv2.IMREAD_GRAYSCALE).shape == (37, 53)

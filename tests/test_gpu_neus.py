@@ -113,3 +113,36 @@ def test_occupancy_update_matches_oracle():
     assert float((m.occupancy_grid.occs.cpu() - occs).abs().max()) <= 1e-7
     assert int((m.occupancy_grid.binaries[0].cpu() != binary).sum()) <= 4
     assert 0.05 < float(binary.float().mean()) < 0.9
+
+
+def test_isosurface_level_grid_and_bounds():
+    """models/geometry.py:76-112: the level grid behind `isosurface()` (chunked vertices -> forward_level) and the bounding
+    box that places the fine grid, at 96^3 against the CPU oracle on a subset and at 512^3 for size / time."""
+    from oracle import fields as ofields
+    m = build(table_scale=0.002).eval()
+    geo = m.geometry
+    level = geo.isosurface_level(96, chunk=200000)                      # ragged last chunk
+    assert level.shape == (96, 96, 96)
+    P = oracle_params_from_model(m)
+    lin = torch.linspace(0.0, 1.0, 96)
+    ijk = torch.randint(0, 96, (4000, 3), generator=torch.Generator().manual_seed(0))
+    pts = torch.stack([lin[ijk[:, 0]], lin[ijk[:, 1]], lin[ijk[:, 2]]], -1) * 3.0 - 1.5
+    ref, _, _ = ofields.sdf_field(pts, P.table, P.meta, P.geo_mlp, P.radius, with_grad=False)
+    got = level[ijk[:, 0], ijk[:, 1], ijk[:, 2]].cpu()
+    assert float((got - ref).abs().max()) <= 5e-6
+    # every sign change of the level grid lies inside the (10 %-padded, box-clamped) bounds the fine grid is placed on
+    bmin, bmax = geo.isosurface_bounds(level)
+    assert bool((bmin < bmax).all()) and float(bmin.min()) >= -1.5 and float(bmax.max()) <= 1.5
+    ins = (level > 0).cpu()
+    cr = torch.nonzero(ins[1:, :, :] != ins[:-1, :, :]).float() / 95.0 * 3.0 - 1.5
+    assert cr.numel() > 0 and bool((cr >= bmin.cpu() - 1e-5).all()) and bool((cr <= bmax.cpu() + 3.0 / 95 + 1e-5).all())
+    fine = geo.isosurface_level(64, vmin=bmin.tolist(), vmax=bmax.tolist())
+    assert float(fine.min()) < 0 < float(fine.max())
+    torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    big = geo.isosurface_level(512)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert big.shape == (512, 512, 512) and torch.isfinite(big).all() and dt < 5.0, dt
+    print(f"512^3 isosurface query: {dt * 1e3:.0f} ms ({512 ** 3 / dt / 1e9:.2f} G points/s)")
