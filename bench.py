@@ -394,7 +394,9 @@ SPLIT_TIMED = ["rsdf_hashgrid_fwd", "rsdf_hashgrid_bwd_table", "rsdf_hashgrid_bw
                "rsdf_relu_layer_bwd", "rsdf_mlp_fwd", "rsdf_mm_stream", "rsdf_mm_tn", "rsdf_specular_cubemap", "rsdf_specular_apply",
                "rsdf_diffuse_cubemap", "rsdf_cube_sample_fwd", "rsdf_cube_sample_bwd", "rsdf_tex2d_fwd", "rsdf_tex2d_bwd",
                "rsdf_weight_from_alpha_fwd", "rsdf_weight_from_alpha_bwd", "rsdf_accumulate_fwd", "rsdf_accumulate_bwd",
-               "rsdf_march_count_keep", "rsdf_march_compact", "rsdf_adam_step", "rsdf_sh_fwd", "rsdf_sh_bwd"]
+               "rsdf_march_count_keep", "rsdf_march_compact", "rsdf_adam_step", "rsdf_sh_fwd", "rsdf_sh_bwd",
+               "rsdf_split_shade_fwd", "rsdf_split_shade_bwd", "rsdf_split_render_fwd", "rsdf_split_render_bwd",
+               "rsdf_freq_encode_fwd", "rsdf_freq_encode_bwd", "rsdf_normalize3_fwd", "rsdf_normalize3_bwd"]
 
 
 # ------------------------------------------------------------------------------------------

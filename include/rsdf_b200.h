@@ -140,6 +140,21 @@ int rsdf_neus_render_bwd(const int32_t *packed_info, const float *rays_d, const 
                          float cos_anneal_ratio, int n_rays, float *grad_sdf,
                          float *grad_sdf_grad, float *grad_rgb, float *grad_inv_s_per_ray,
                          void *stream);
+/* The same fused pass for the split-sum renderer (models/split_mixed_occ.py:151-177 get_alpha, models/volrend.py:851-885
+ * render_weight_from_alpha + 4x accumulate_along_rays, models/split_mixed_occ.py:384-394 normal-orientation map):
+ * `normals` [S,3] are the already normalised sdf gradients (the shading networks needed them earlier), `colors`
+ * [S, color_dim] the 7 (stage 0) or 24 (stage 1) shading channels of models/texture.py:345.
+ * out[n_rays, color_dim + 6] = (colours, sum w n (3), opacity, depth, sum w relu(d . n)). */
+int rsdf_split_render_fwd(const int32_t *packed_info, const float *rays_d, const float *t_starts, const float *t_ends,
+                          const float *sdf, const float *normals, const float *colors, int color_dim, const float *inv_s,
+                          float cos_anneal_ratio, int n_rays, float *alpha, float *weights, float *trans, float *out,
+                          void *stream);
+int rsdf_split_render_bwd(const int32_t *packed_info, const float *rays_d, const float *t_starts, const float *t_ends,
+                          const float *sdf, const float *normals, const float *colors, int color_dim, const float *alpha,
+                          const float *weights, const float *trans, const float *grad_out,
+                          const float *grad_weights_extra, const float *inv_s, float cos_anneal_ratio, int n_rays,
+                          float *grad_sdf, float *grad_normals, float *grad_colors, float *grad_inv_s_per_ray,
+                          void *stream);
 
 /* ---------------------------------------------------------------- K2: hash-grid encoding */
 /* tinycudann.Encoding(3, HashGrid).forward (models/network_utils.py:50,99).
@@ -203,6 +218,37 @@ int rsdf_cube_sample_fwd(const float *const *levels_host, const int *res_host, i
 int rsdf_cube_sample_bwd(const float *const *levels_host, float *const *grad_levels_host,
                          const int *res_host, int n_levels, const float *dirs, const float *mip_level_bias,
                          const float *grad_out, int n, float *grad_bias, float *grad_dirs, void *stream);
+
+/* The split-sum combine of models/texture.py:330-377 (VolumeMixedMipSplitOcc.forward after its four material
+ * networks) in one kernel: sigmoid of the raw network outputs, blend / albedo mixes, reflection direction, FG LUT
+ * lookup (models/texture.py:340), diffuse + prefiltered-specular emitter lookups with get_mip
+ * (lib/pbr/light.py:168-206), channel packing of models/texture.py:345.
+ *   stage 0: colors [n,7]  = (diff_rgb3, spec_rgb3, blend)           (lookups skipped; lut/diffuse/levels unused)
+ *   stage 1: colors [n,24] = (... , diff_pbr3, spec_pbr3, spec_ref3, spec_light3, albedo3, metallic, roughness) */
+typedef struct {
+    const float *raw_albedo;      /* [n,6] albedo_network output, pre-activation (diff_rgb | albedo) */
+    const float *raw_roughness;   /* [n,1] */
+    const float *raw_metallic;    /* [n,2] (blend | metallic) */
+    const float *raw_env;         /* [n,3] env_network output */
+    const float *normals;         /* [n,3] unit normals */
+    const float *dirs;            /* [n,3] ray directions (wi = -dirs) */
+    const float *fg_lut;          /* [lut_h, lut_w, 2] */
+    int lut_h, lut_w;
+    const float *diffuse;         /* [6, diffuse_res, diffuse_res, 3] */
+    int diffuse_res;
+    const float *const *specular_levels; /* HOST array of n_levels DEVICE pointers, [6,res_l,res_l,3] each */
+    const int *specular_res;      /* HOST array */
+    int n_levels;
+    float min_roughness, max_roughness;  /* EnvironmentLightMipCube.MIN/MAX_ROUGHNESS (lib/pbr/light.py:129-130) */
+    int stage;
+    int n;
+} rsdf_split_shade_args;
+int rsdf_split_shade_fwd(const rsdf_split_shade_args *args, float *colors, void *stream);
+/* grads of the raw outputs and the normals are written; texel grads are atomic += (each may be NULL) */
+int rsdf_split_shade_bwd(const rsdf_split_shade_args *args, const float *grad_colors, float *grad_raw_albedo,
+                         float *grad_raw_roughness, float *grad_raw_metallic, float *grad_raw_env,
+                         float *grad_normals /* may be NULL */, float *grad_fg_lut, float *grad_diffuse,
+                         float *const *grad_specular_levels /* HOST array or NULL */, void *stream);
 /* lib/renderutils cubemap prefilter (lib/renderutils/c_src/cubemap.cu:110-350, ops.py:391-458).
  * table: float4[6*res*res] (direction, solid angle) built by rsdf_cubemap_texel_table.
  * transposed=0: forward; transposed=1: backward as a deterministic gather (src = grad_out). */

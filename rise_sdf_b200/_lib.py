@@ -43,6 +43,14 @@ class ReluBwdC(ctypes.Structure):
                 ("gb_self", c_p), ("fp16", ctypes.c_int32)]
 
 
+class SplitShadeC(ctypes.Structure):
+    _fields_ = [("raw_albedo", c_p), ("raw_roughness", c_p), ("raw_metallic", c_p), ("raw_env", c_p), ("normals", c_p),
+                ("dirs", c_p), ("fg_lut", c_p), ("lut_h", ctypes.c_int32), ("lut_w", ctypes.c_int32), ("diffuse", c_p),
+                ("diffuse_res", ctypes.c_int32), ("specular_levels", c_p), ("specular_res", c_p),
+                ("n_levels", ctypes.c_int32), ("min_roughness", ctypes.c_float), ("max_roughness", ctypes.c_float),
+                ("stage", ctypes.c_int32), ("n", ctypes.c_int32)]
+
+
 ADAM_MAX_GROUPS = 8
 
 
@@ -72,6 +80,9 @@ _SIGS = {
     "rsdf_neus_render_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_p, c_p, c_p, c_p],
     "rsdf_neus_render_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i,
                              c_p, c_p, c_p, c_p, c_p],
+    "rsdf_split_render_fwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_f, c_i, c_p, c_p, c_p, c_p, c_p],
+    "rsdf_split_render_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_f, c_i,
+                              c_p, c_p, c_p, c_p, c_p],
     "rsdf_sdf_reg_fwd": [c_p, c_p, c_i, c_f, c_p, c_p, c_p],
     "rsdf_sdf_reg_bwd": [c_p, c_p, c_i, c_f, c_p, c_p, c_p, c_p],
     "rsdf_sample_setup": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p],
@@ -90,6 +101,8 @@ _SIGS = {
     "rsdf_tex2d_bwd": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p],
     "rsdf_cube_sample_fwd": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p],
     "rsdf_cube_sample_bwd": [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p],
+    "rsdf_split_shade_fwd": [c_p, c_p, c_p],
+    "rsdf_split_shade_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "rsdf_cubemap_texel_table": [c_i, c_p, c_p],
     "rsdf_diffuse_cubemap": [c_p, c_p, c_i, c_i, c_p, c_p],
     "rsdf_specular_bounds": [c_p, c_i, c_f, c_p, c_p, c_p],

@@ -166,36 +166,49 @@ __device__ __forceinline__ AlphaTerms neus_alpha(float sdf, float cosv, float di
     return t;
 }
 
+// One kernel family for both renderers:
+//   CD        colour channels accumulated per ray (3: neus radiance; 7 / 24: split-sum stage 0 / 1, models/texture.py:345)
+//   NORMALIZE true : `vec` is the raw sdf gradient, n = vec / max(|vec|, eps) inside (models/neus.py:253)
+//             false: `vec` is the normal the caller already normalised (models/split_mixed_occ.py:247, needed earlier by
+//                    the shading networks); its gradient is returned as is
+//   ORIENT    one more output column: sum_i w_i relu(d . n_i), the normal-orientation map of
+//             models/split_mixed_occ.py:384-394
+// out[n_rays, CD + 5 (+ 1)] = (colours, normal3 (un-normalised sum), opacity, depth (, orientation))
+template <int CD, bool NORMALIZE, bool ORIENT>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
-neus_render_fwd_kernel(const int32_t *__restrict__ packed, const float *__restrict__ rays_d,
-                       const float *__restrict__ t_starts, const float *__restrict__ t_ends,
-                       const float *__restrict__ sdf, const float *__restrict__ grad,
-                       const float *__restrict__ rgb, const float *__restrict__ inv_s_ptr,
-                       float ratio, int n_rays, float *__restrict__ alpha_out,
-                       float *__restrict__ w_out, float *__restrict__ T_out,
-                       float *__restrict__ out) {
+sdf_render_fwd_kernel(const int32_t *__restrict__ packed, const float *__restrict__ rays_d,
+                      const float *__restrict__ t_starts, const float *__restrict__ t_ends,
+                      const float *__restrict__ sdf, const float *__restrict__ vec,
+                      const float *__restrict__ rgb, const float *__restrict__ inv_s_ptr,
+                      float ratio, float eps, int n_rays, float *__restrict__ alpha_out,
+                      float *__restrict__ w_out, float *__restrict__ T_out,
+                      float *__restrict__ out) {
+    constexpr int NO = CD + 5 + (ORIENT ? 1 : 0);
     const int ray = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (ray >= n_rays) return;
     const int base = packed[2 * ray], steps = packed[2 * ray + 1];
     const float inv_s = fminf(fmaxf(__ldg(inv_s_ptr), 1e-6f), 1e6f);
     const float dx = rays_d[3 * ray], dy = rays_d[3 * ray + 1], dz = rays_d[3 * ray + 2];
-    float acc[8];
+    float acc[NO];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+    for (int k = 0; k < NO; ++k) acc[k] = 0.0f;
     float carry = 1.0f;
     for (int c = 0; c < steps; c += 32) {
         const int j = c + lane;
         const bool ok = j < steps;
         const int s = base + j;
-        float a = 0.0f, nx = 0.f, ny = 0.f, nz = 0.f, mid = 0.f;
+        float a = 0.0f, nx = 0.f, ny = 0.f, nz = 0.f, mid = 0.f, cosv = 0.f;
         if (ok) {
-            const float gx = grad[3 * s], gy = grad[3 * s + 1], gz = grad[3 * s + 2];
-            const float inv_n = 1.0f / fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f);
-            nx = gx * inv_n; ny = gy * inv_n; nz = gz * inv_n;
+            nx = vec[3 * s]; ny = vec[3 * s + 1]; nz = vec[3 * s + 2];
+            if (NORMALIZE) {
+                const float inv_n = 1.0f / fmaxf(sqrtf(nx * nx + ny * ny + nz * nz), eps);
+                nx *= inv_n; ny *= inv_n; nz *= inv_n;
+            }
             const float t0 = t_starts[s], t1 = t_ends[s];
             mid = (t0 + t1) / 2.0f;
-            a = neus_alpha(sdf[s], dx * nx + dy * ny + dz * nz, t1 - t0, inv_s, ratio).alpha;
+            cosv = dx * nx + dy * ny + dz * nz;
+            a = neus_alpha(sdf[s], cosv, t1 - t0, inv_s, ratio).alpha;
         }
         const float incl = warp_incl_prod(1.0f - a, lane);
         float excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -207,34 +220,36 @@ neus_render_fwd_kernel(const int32_t *__restrict__ packed, const float *__restri
             alpha_out[s] = a;
             w_out[s] = w;
             T_out[s] = T;
-            acc[0] = fmaf(w, rgb[3 * s], acc[0]);
-            acc[1] = fmaf(w, rgb[3 * s + 1], acc[1]);
-            acc[2] = fmaf(w, rgb[3 * s + 2], acc[2]);
-            acc[3] = fmaf(w, nx, acc[3]);
-            acc[4] = fmaf(w, ny, acc[4]);
-            acc[5] = fmaf(w, nz, acc[5]);
-            acc[6] += w;
-            acc[7] = fmaf(w, mid, acc[7]);
+#pragma unroll
+            for (int k = 0; k < CD; ++k) acc[k] = fmaf(w, rgb[(size_t)CD * s + k], acc[k]);
+            acc[CD] = fmaf(w, nx, acc[CD]);
+            acc[CD + 1] = fmaf(w, ny, acc[CD + 1]);
+            acc[CD + 2] = fmaf(w, nz, acc[CD + 2]);
+            acc[CD + 3] += w;
+            acc[CD + 4] = fmaf(w, mid, acc[CD + 4]);
+            if (ORIENT) acc[CD + 5] = fmaf(w, fmaxf(cosv, 0.0f), acc[CD + 5]);
         }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < NO; ++k) {
         const float s = warp_sum(acc[k]);
-        if (lane == 0) out[(size_t)ray * 8 + k] = s;
+        if (lane == 0) out[(size_t)ray * NO + k] = s;
     }
 }
 
+template <int CD, bool NORMALIZE, bool ORIENT>
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
-neus_render_bwd_kernel(const int32_t *__restrict__ packed, const float *__restrict__ rays_d,
-                       const float *__restrict__ t_starts, const float *__restrict__ t_ends,
-                       const float *__restrict__ sdf, const float *__restrict__ grad,
-                       const float *__restrict__ rgb, const float *__restrict__ alpha_in,
-                       const float *__restrict__ w_in, const float *__restrict__ T_in,
-                       const float *__restrict__ go,
-                       const float *__restrict__ gw_extra, const float *__restrict__ inv_s_ptr,
-                       float ratio, int n_rays, float *__restrict__ g_sdf,
-                       float *__restrict__ g_grad, float *__restrict__ g_rgb,
-                       float *__restrict__ g_inv_s_ray) {
+sdf_render_bwd_kernel(const int32_t *__restrict__ packed, const float *__restrict__ rays_d,
+                      const float *__restrict__ t_starts, const float *__restrict__ t_ends,
+                      const float *__restrict__ sdf, const float *__restrict__ vec,
+                      const float *__restrict__ rgb, const float *__restrict__ alpha_in,
+                      const float *__restrict__ w_in, const float *__restrict__ T_in,
+                      const float *__restrict__ go,
+                      const float *__restrict__ gw_extra, const float *__restrict__ inv_s_ptr,
+                      float ratio, float eps, int n_rays, float *__restrict__ g_sdf,
+                      float *__restrict__ g_vec, float *__restrict__ g_rgb,
+                      float *__restrict__ g_inv_s_ray) {
+    constexpr int NO = CD + 5 + (ORIENT ? 1 : 0);
     const int ray = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (ray >= n_rays) return;
@@ -243,9 +258,9 @@ neus_render_bwd_kernel(const int32_t *__restrict__ packed, const float *__restri
     const float inv_s = fminf(fmaxf(inv_s_raw, 1e-6f), 1e6f);
     const bool s_live = inv_s_raw >= 1e-6f && inv_s_raw <= 1e6f;
     const float dx = rays_d[3 * ray], dy = rays_d[3 * ray + 1], dz = rays_d[3 * ray + 2];
-    float g[8];
+    float g[NO];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] = go[(size_t)ray * 8 + k];
+    for (int k = 0; k < NO; ++k) g[k] = go[(size_t)ray * NO + k];
     float carry = 0.0f, ginv = 0.0f;
     const int nchunks = (steps + 31) >> 5;
     for (int ch = nchunks - 1; ch >= 0; --ch) {
@@ -253,19 +268,25 @@ neus_render_bwd_kernel(const int32_t *__restrict__ packed, const float *__restri
         const bool ok = j < steps;
         const int s = base + j;
         float a = 0.f, w = 0.f, gwj = 0.f, T = 0.f;
-        float nx = 0.f, ny = 0.f, nz = 0.f, inv_n = 0.f, dist = 0.f, sd = 0.f;
+        float nx = 0.f, ny = 0.f, nz = 0.f, inv_n = 1.f, dist = 0.f, sd = 0.f, cosv = 0.f, vlen = 1.f;
         if (ok) {
             a = alpha_in[s];
             w = w_in[s];
-            const float gx = grad[3 * s], gy = grad[3 * s + 1], gz = grad[3 * s + 2];
-            inv_n = 1.0f / fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f);
-            nx = gx * inv_n; ny = gy * inv_n; nz = gz * inv_n;
+            nx = vec[3 * s]; ny = vec[3 * s + 1]; nz = vec[3 * s + 2];
+            if (NORMALIZE) {
+                vlen = sqrtf(nx * nx + ny * ny + nz * nz);
+                inv_n = 1.0f / fmaxf(vlen, eps);
+                nx *= inv_n; ny *= inv_n; nz *= inv_n;
+            }
             const float t0 = t_starts[s], t1 = t_ends[s];
             dist = t1 - t0;
             sd = sdf[s];
             const float mid = (t0 + t1) / 2.0f;
-            gwj = g[0] * rgb[3 * s] + g[1] * rgb[3 * s + 1] + g[2] * rgb[3 * s + 2] + g[3] * nx +
-                  g[4] * ny + g[5] * nz + g[6] + g[7] * mid;
+            cosv = dx * nx + dy * ny + dz * nz;
+            gwj = g[CD] * nx + g[CD + 1] * ny + g[CD + 2] * nz + g[CD + 3] + g[CD + 4] * mid;
+#pragma unroll
+            for (int k = 0; k < CD; ++k) gwj = fmaf(g[k], rgb[(size_t)CD * s + k], gwj);
+            if (ORIENT) gwj = fmaf(g[CD + 5], fmaxf(cosv, 0.0f), gwj);
             if (gw_extra) gwj += gw_extra[s];
             T = T_in[s];
         }
@@ -275,12 +296,14 @@ neus_render_bwd_kernel(const int32_t *__restrict__ packed, const float *__restri
         carry += __shfl_sync(0xffffffffu, sw, 0);
         if (ok) {
             // values' own grads
-            g_rgb[3 * s] = w * g[0];
-            g_rgb[3 * s + 1] = w * g[1];
-            g_rgb[3 * s + 2] = w * g[2];
-            float gnx = w * g[3], gny = w * g[4], gnz = w * g[5];
+#pragma unroll
+            for (int k = 0; k < CD; ++k) g_rgb[(size_t)CD * s + k] = w * g[k];
+            float gnx = w * g[CD], gny = w * g[CD + 1], gnz = w * g[CD + 2];
+            if (ORIENT && cosv > 0.0f) {
+                const float go_ = w * g[CD + 5];
+                gnx = fmaf(go_, dx, gnx); gny = fmaf(go_, dy, gny); gnz = fmaf(go_, dz, gnz);
+            }
             // alpha backward (models/neus.py:133-150)
-            const float cosv = dx * nx + dy * ny + dz * nz;
             const AlphaTerms t = neus_alpha(sd, cosv, dist, inv_s, ratio);
             float gsd = 0.0f;
             if (t.praw >= 0.0f && t.praw <= 1.0f) {
@@ -299,11 +322,16 @@ neus_render_bwd_kernel(const int32_t *__restrict__ packed, const float *__restri
                 gnz = fmaf(dcos, dz, gnz);
             }
             g_sdf[s] = gsd;
-            // normalize backward: n = g / max(|g|, eps)
-            const float ndot = nx * gnx + ny * gny + nz * gnz;
-            g_grad[3 * s] = (gnx - nx * ndot) * inv_n;
-            g_grad[3 * s + 1] = (gny - ny * ndot) * inv_n;
-            g_grad[3 * s + 2] = (gnz - nz * ndot) * inv_n;
+            if (NORMALIZE) {
+                // normalize backward: n = v / max(|v|, eps)
+                if (vlen > eps) {
+                    const float ndot = nx * gnx + ny * gny + nz * gnz;
+                    gnx = (gnx - nx * ndot) * inv_n; gny = (gny - ny * ndot) * inv_n; gnz = (gnz - nz * ndot) * inv_n;
+                } else {
+                    gnx *= inv_n; gny *= inv_n; gnz *= inv_n;
+                }
+            }
+            g_vec[3 * s] = gnx; g_vec[3 * s + 1] = gny; g_vec[3 * s + 2] = gnz;
         }
     }
     ginv = warp_sum(ginv);
@@ -521,10 +549,10 @@ int rsdf_neus_render_fwd(const int32_t *packed_info, const float *rays_d, const 
     if (n_rays == 0) return 0;
     if (!packed_info || !rays_d || !inv_s || !out || !alpha || !weights || !trans)
         return RSDF_EBADARG;
-    neus_render_fwd_kernel<<<rsdf_div_up(n_rays, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0,
-                             (cudaStream_t)stream>>>(packed_info, rays_d, t_starts, t_ends, sdf,
-                                                     sdf_grad, rgb, inv_s, cos_anneal_ratio, n_rays,
-                                                     alpha, weights, trans, out);
+    sdf_render_fwd_kernel<3, true, false><<<rsdf_div_up(n_rays, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0,
+                                            (cudaStream_t)stream>>>(packed_info, rays_d, t_starts, t_ends, sdf,
+                                                                    sdf_grad, rgb, inv_s, cos_anneal_ratio, 1e-12f,
+                                                                    n_rays, alpha, weights, trans, out);
     RSDF_LAUNCH_CHECK();
     return 0;
 }
@@ -539,11 +567,53 @@ int rsdf_neus_render_bwd(const int32_t *packed_info, const float *rays_d, const 
                          void *stream) {
     if (n_rays == 0) return 0;
     if (!packed_info || !rays_d || !inv_s || !grad_out || !trans) return RSDF_EBADARG;
-    neus_render_bwd_kernel<<<rsdf_div_up(n_rays, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0,
-                             (cudaStream_t)stream>>>(
+    sdf_render_bwd_kernel<3, true, false><<<rsdf_div_up(n_rays, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0,
+                                            (cudaStream_t)stream>>>(
         packed_info, rays_d, t_starts, t_ends, sdf, sdf_grad, rgb, alpha, weights, trans, grad_out,
-        grad_weights_extra, inv_s, cos_anneal_ratio, n_rays, grad_sdf, grad_sdf_grad, grad_rgb,
+        grad_weights_extra, inv_s, cos_anneal_ratio, 1e-12f, n_rays, grad_sdf, grad_sdf_grad, grad_rgb,
         grad_inv_s_per_ray);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_split_render_fwd(const int32_t *packed_info, const float *rays_d, const float *t_starts, const float *t_ends,
+                          const float *sdf, const float *normals, const float *colors, int color_dim, const float *inv_s,
+                          float cos_anneal_ratio, int n_rays, float *alpha, float *weights, float *trans, float *out,
+                          void *stream) {
+    if (n_rays == 0) return 0;
+    if (!packed_info || !rays_d || !inv_s || !out || !alpha || !weights || !trans) return RSDF_EBADARG;
+    const int blocks = rsdf_div_up(n_rays, WARPS_PER_BLOCK), threads = 32 * WARPS_PER_BLOCK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define RSDF_SR(CD)                                                                                                   \
+    sdf_render_fwd_kernel<CD, false, true><<<blocks, threads, 0, st>>>(packed_info, rays_d, t_starts, t_ends, sdf,    \
+                                                                       normals, colors, inv_s, cos_anneal_ratio, 0.f, \
+                                                                       n_rays, alpha, weights, trans, out)
+    if (color_dim == 24) RSDF_SR(24);
+    else if (color_dim == 7) RSDF_SR(7);
+    else return RSDF_EBADARG;
+#undef RSDF_SR
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_split_render_bwd(const int32_t *packed_info, const float *rays_d, const float *t_starts, const float *t_ends,
+                          const float *sdf, const float *normals, const float *colors, int color_dim, const float *alpha,
+                          const float *weights, const float *trans, const float *grad_out,
+                          const float *grad_weights_extra, const float *inv_s, float cos_anneal_ratio, int n_rays,
+                          float *grad_sdf, float *grad_normals, float *grad_colors, float *grad_inv_s_per_ray,
+                          void *stream) {
+    if (n_rays == 0) return 0;
+    if (!packed_info || !rays_d || !inv_s || !grad_out || !trans) return RSDF_EBADARG;
+    const int blocks = rsdf_div_up(n_rays, WARPS_PER_BLOCK), threads = 32 * WARPS_PER_BLOCK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define RSDF_SR(CD)                                                                                                     \
+    sdf_render_bwd_kernel<CD, false, true><<<blocks, threads, 0, st>>>(                                                  \
+        packed_info, rays_d, t_starts, t_ends, sdf, normals, colors, alpha, weights, trans, grad_out,                  \
+        grad_weights_extra, inv_s, cos_anneal_ratio, 0.f, n_rays, grad_sdf, grad_normals, grad_colors, grad_inv_s_per_ray)
+    if (color_dim == 24) RSDF_SR(24);
+    else if (color_dim == 7) RSDF_SR(7);
+    else return RSDF_EBADARG;
+#undef RSDF_SR
     RSDF_LAUNCH_CHECK();
     return 0;
 }

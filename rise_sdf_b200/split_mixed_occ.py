@@ -12,9 +12,10 @@ import torch.nn.functional as F
 
 from .geometry import VolumeSDF
 from .light import EnvironmentLightMipCube, rgb_to_srgb
-from .nerfacc import ContractionType, OccGridEstimator, accumulate_along_rays
+from .nerfacc import ContractionType, OccGridEstimator, accumulate_along_rays, pack_info
 from .network_utils import Config, update_module_step
-from .neus import VarianceNetwork, chunk_batch
+from .neus import VarianceNetwork, chunk_batch, normalize3
+from .split_shade import split_render
 from .texture import VolumeMixedMipSplitOcc
 from .volrend import rendering_with_normals_sdf, secondary_rendering
 
@@ -115,7 +116,9 @@ class SplitMixedOCCModel(nn.Module):
         c = prev_cdf
         return ((p + 1e-5) / (c + 1e-5)).view(-1).clip(0.0, 1.0)
 
+    fused_render = True              # csrc/render.cu sdf_render_*_kernel<CD, false, true>; False: op-by-op (parity yardstick)
     reuse_sampling_pass = True       # no-grad passes only; results are bit-identical either way (test)
+    _skip_alpha = False
     _tile_cache = None               # relight.render_frame_shard: one dict per tile, shared by its env maps
 
     def _memo(self, key, fn):
@@ -147,7 +150,7 @@ class SplitMixedOCCModel(nn.Module):
                 sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
             else:
                 sdf, sdf_grad = self.geometry(positions, with_grad=True, with_feature=False)
-            normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
+            normal = normalize3(sdf_grad, eps=1e-6)
             dists = (t_ends - t_starts)[..., None]
             alphas = self.get_alpha(sdf, normal, t_dirs, dists)
             if keep is not None:
@@ -195,8 +198,8 @@ class SplitMixedOCCModel(nn.Module):
             if fd_train:
                 sdf, sdf_grad, feature, sdf_laplace = self.geometry(positions, with_grad=True, with_feature=True,
                                                                     with_laplace=True)
-                normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
-                alphas = self.get_alpha(sdf, normal, t_dirs, (t_ends - t_starts)[..., None])
+                normal = normalize3(sdf_grad, eps=1e-6)
+                alphas = None if self._skip_alpha else self.get_alpha(sdf, normal, t_dirs, (t_ends - t_starts)[..., None])
                 colors = self.texture(feature, t_dirs, normal, positions, self.emitter, self.stage)
                 return colors, normal, alphas, sdf, sdf_grad, sdf_laplace
 
@@ -207,7 +210,9 @@ class SplitMixedOCCModel(nn.Module):
                     keep.clear()
                     return got
                 sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
-                normal = F.normalize(sdf_grad, p=2, dim=-1, eps=1e-6)
+                normal = normalize3(sdf_grad, eps=1e-6)
+                if self._skip_alpha:
+                    return sdf, sdf_grad, feature, normal, None
                 return sdf, sdf_grad, feature, normal, self.get_alpha(sdf, normal, t_dirs, (t_ends - t_starts)[..., None])
 
             sdf, sdf_grad, feature, normal, alphas = self._memo("fields", fields)
@@ -223,9 +228,29 @@ class SplitMixedOCCModel(nn.Module):
             return r[:3], ([r[3]] if ok else []), keep
 
         (ray_indices, t_starts, t_ends), survivors, keep = self._memo("sampling", sample)
-        rgb_map, normal_map, acc_map, depth_map, extras = rendering_with_normals_sdf(
-            t_starts, t_ends, ray_indices=ray_indices, n_rays=n_rays, rgb_alpha_fn=rgb_normal_alpha_fn,
-            render_bkgd=None, has_laplace=fd_train, color_dim=7 if self.stage == 0 else 24)
+        color_dim = 7 if self.stage == 0 else 24
+        orientation_map = None
+        if self.fused_render and rays.is_cuda and t_starts.shape[0] > 0:
+            # get_alpha + weights + the five accumulations (colours, normals, opacity, depth, orientation) in one pass
+            self._skip_alpha = True
+            try:
+                got = rgb_normal_alpha_fn(t_starts, t_ends, ray_indices)
+            finally:
+                self._skip_alpha = False
+            colors, normals, sdf, sdf_grad = got[0], got[1], got[3], got[4]
+            packed = self._memo("packed", lambda: pack_info(ray_indices, n_rays))
+            acc, weights, _ = split_render(packed, rays_d, t_starts, t_ends, sdf, normals, colors, self.variance.inv_s,
+                                           self.cos_anneal_ratio)
+            rgb_map, normal_map = acc[:, :color_dim], acc[:, color_dim:color_dim + 3]
+            acc_map, depth_map = acc[:, color_dim + 3:color_dim + 4], acc[:, color_dim + 4:color_dim + 5]
+            orientation_map = acc[:, color_dim + 5:color_dim + 6]
+            extras = {"weights": weights, "sdf": sdf, "sdf_grad": sdf_grad, "normals": normals}
+            if fd_train:
+                extras["sdf_laplace"] = got[5]
+        else:
+            rgb_map, normal_map, acc_map, depth_map, extras = rendering_with_normals_sdf(
+                t_starts, t_ends, ray_indices=ray_indices, n_rays=n_rays, rgb_alpha_fn=rgb_normal_alpha_fn,
+                render_bkgd=None, has_laplace=fd_train, color_dim=color_dim)
 
         valid_indices = torch.nonzero(acc_map > 0.5)[..., 0]
         rgb_map = rgb_map.clone()      # the reference writes through slices of rgb_map in place
@@ -260,7 +285,7 @@ class SplitMixedOCCModel(nn.Module):
 
                     def third():
                         _, third_grad, third_feature = self.geometry(third_rays_o, with_grad=True, with_feature=True)
-                        third_normal = F.normalize(third_grad, p=2, dim=-1, eps=1e-6)
+                        third_normal = normalize3(third_grad, eps=1e-6)
                         if third_dirs.shape[0] == 0:
                             return third_normal, None
                         return third_normal, self.texture.secondary_material_pbr(third_feature, third_dirs,
@@ -291,7 +316,9 @@ class SplitMixedOCCModel(nn.Module):
                         "weights": weights.view(-1), "ray_indices": ray_indices.view(-1)})
             if self.config.geometry.grad_type == "finite_difference":
                 out["sdf_laplace_samples"] = extras["sdf_laplace"]
-            if ray_indices.numel() > 0:
+            if orientation_map is not None:
+                out["normals_orientation_loss_map"] = orientation_map
+            elif ray_indices.numel() > 0:
                 orient = torch.sum(rays_d[ray_indices] * extras["normals"], dim=-1, keepdim=True).clamp(min=0)
                 out["normals_orientation_loss_map"] = accumulate_along_rays(
                     weights, values=orient, ray_indices=ray_indices, n_rays=n_rays)

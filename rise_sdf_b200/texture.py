@@ -67,6 +67,11 @@ class VolumeMixedMipSplitOcc(nn.Module):
             fg_lut = bsdf_lut()
         self.register_buffer("FG_LUT", fg_lut.float().reshape(1, 256, 256, 2).contiguous())
 
+    fused_shade = True          # csrc/split_shade.cu; False: the op-by-op path below (kept as the parity yardstick)
+
+    def _fused(self, t):
+        return self.fused_shade and t.is_cuda and self.config.get("color_activation", None) == "sigmoid"
+
     def _act(self, x):
         if "color_activation" in self.config:
             return get_activation(self.config.color_activation)(x)
@@ -87,13 +92,17 @@ class VolumeMixedMipSplitOcc(nn.Module):
         NoV = torch.sum(normals * wi, -1, keepdim=True)
         xyz_embd = self.xyz_encoding(positions.view(-1, self.n_pos_dims))
         network_inp = [features.view(-1, features.shape[-1]), xyz_embd]
-        albedo = self.albedo_network.forward_segments(network_inp).view(*features.shape[:-1], 6).float()
-        diff_rgb, albedo = albedo[..., :3], albedo[..., 3:]
+        raw6 = self.albedo_network.forward_segments(network_inp).view(*features.shape[:-1], 6).float()
+        diff_rgb, albedo = raw6[..., :3], raw6[..., 3:]
         roughness = self.roughness_network.forward_segments(network_inp).view(*features.shape[:-1], 1).float()
-        metallic = self.metallic_network.forward_segments(network_inp).view(*features.shape[:-1], 2).float()
-        blend, metallic = metallic[..., :1], metallic[..., 1:]
+        raw2 = self.metallic_network.forward_segments(network_inp).view(*features.shape[:-1], 2).float()
+        blend, metallic = raw2[..., :1], raw2[..., 1:]
         wo_enc = self.dir_encoding(((wo + 1.0) / 2.0).view(-1, self.n_dir_dims))
         spec_rgb = self.env_network.forward_segments([features, wo_enc]).view(*features.shape[:-1], 3).float()
+        if self._fused(features):
+            # activations, mixes and lookups happen in ONE kernel in shade(); the networks' raw outputs are all it needs
+            return {"raw_albedo": raw6, "raw_roughness": roughness, "raw_metallic": raw2, "raw_env": spec_rgb,
+                    "dirs": dirs}
         albedo, diff_rgb, blend = self._act(albedo), self._act(diff_rgb), self._act(blend)
         metallic, roughness, spec_rgb = self._act(metallic), self._act(roughness), self._act(spec_rgb)
         spec_rgb = blend * spec_rgb
@@ -109,6 +118,10 @@ class VolumeMixedMipSplitOcc(nn.Module):
 
     def shade(self, m, normals, emitter, stage=0):
         """The emitter-dependent half of `forward`: split-sum lighting lookups + channel packing."""
+        if "raw_albedo" in m:
+            from .split_shade import split_shade
+            return split_shade(m["raw_albedo"], m["raw_roughness"], m["raw_metallic"], m["raw_env"], normals, m["dirs"],
+                               emitter, self.FG_LUT, stage)
         if stage == 0:
             return torch.cat([m["diff_rgb"], m["spec_rgb"], m["blend"]], dim=-1)
         diffuse_light = emitter.eval_mip(normals)
