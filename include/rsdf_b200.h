@@ -322,7 +322,7 @@ int rsdf_mm_tn(const float *A, const float *B, float *G, int S, int Fa, int Fb, 
  *   inputs: h0 = cat(in0[S,w0] * scale0 + shift0, in1[S,w1]),  w0 + w1 == n_in.
  *   fwd: out[S,n_out]; optionally sdf[S] = out[:,0] once more as its own array; g0 split at w0 into
  *        g0a[S,w0] = d out0/d h0[:, :w0] and g0b[S,w1] (g0a == NULL: plain forward).
- *   bwd: cotangents g_out[S,n_out], g_sdf[S] (added to g_out[:,0]; may be NULL), g_g0a[S,w0] / g_g0b[S,w1]
+ *   bwd: cotangents g_out[S,n_out] (NULL = zeros, when g_sdf is given), g_sdf[S] (added to g_out[:,0]; may be NULL), g_g0a[S,w0] / g_g0b[S,w1]
  *        (either may be NULL) -> g_in0[S,w0] = d/d in0 (scale0 applied), g_in1[S,w1] = d/d in1 (either may
  *        be NULL) and gW1[128,n_in], gb1[128], gW2[128,128], gb2[128], gW3[n_out,128], gb3[n_out], accumulated
  *        atomically (caller zeroes).  The forward is recomputed; nothing but the inputs is kept between passes.

@@ -59,10 +59,6 @@ struct Inputs {
     float sc0, sh0;
     int S;
 };
-struct Ctrl {
-    uint64_t bar_w, bar_mma;
-    uint32_t tmem_slot, pad;
-};
 
 // 16 warps: warp w owns TMEM lane quadrant w%4 (feature rows 32*(w%4)..+31) and the 16 sample
 // columns [16*(w/4), +16) of the tile
@@ -106,6 +102,38 @@ __device__ __forceinline__ void gemm3(uint32_t d, const tc::Operand &A, const tc
     }
 #pragma unroll
     for (int k = 0; k < KSTEPS; ++k) tc::mma_f16(d, a_hi + k * ak, b_hi + k * bk, idesc, SPLIT || accumulate || k > 0);
+}
+
+// The same GEMM for the dedicated issuer warp of the training kernels, ROLLED: the issuer runs ~40 GEMMs per tile and a
+// fully unrolled issue stream keeps hundreds of precomputed 64-bit descriptors live -- they spill, and every spill reload
+// of the single issuing lane is an L2 round trip in front of an MMA (ncu: 1500 local loads per tile, 32 % L1 hit).
+// Rolled, a descriptor is two 64-bit adds away from its base and nothing outlives the call.
+template <int KSTEPS, bool SPLIT>
+__device__ __forceinline__ void gemm3r(uint32_t d, const tc::Operand &A, const tc::Operand &B, uint32_t idesc,
+                                       bool accumulate) {
+    // the address is the low 14 bits of the descriptor's low word and never carries out of it: stepping a descriptor
+    // is ONE 32-bit add, the high word (LBO | SBO | version) is per-operand constant
+    const uint64_t a0 = tc::smem_desc(A.addr, A.lbo, A.sbo), b0 = tc::smem_desc(B.addr, B.lbo, B.sbo);
+    const uint32_t a_hi32 = (uint32_t)(a0 >> 32), b_hi32 = (uint32_t)(b0 >> 32);
+    const uint32_t a_lo32 = (uint32_t)a0, b_lo32 = (uint32_t)b0;
+    const uint32_t ak = A.kstep >> 4, bk = B.kstep >> 4, apl = A.plane >> 4, bpl = B.plane >> 4;
+    auto pass = [&](uint32_t a, uint32_t b, bool acc0) {
+#pragma unroll 1
+        for (int k = 0; k < KSTEPS; ++k, a += ak, b += bk)
+            tc::mma_f16(d, ((uint64_t)a_hi32 << 32) | a, ((uint64_t)b_hi32 << 32) | b, idesc, acc0 || k > 0);
+    };
+    if (SPLIT) {
+        pass(a_lo32 + apl, b_lo32, accumulate);
+        pass(a_lo32, b_lo32 + bpl, true);
+    }
+    pass(a_lo32, b_lo32, SPLIT || accumulate);
+}
+// a zero the compiler cannot see through: operands built from it are recomputed where they are used instead of being
+// hoisted out of the persistent tile loop (and spilled)
+__device__ __forceinline__ uint32_t opaque_zero() {
+    uint32_t z;
+    asm volatile("mov.u32 %0, 0;" : "=r"(z));
+    return z;
 }
 
 __device__ __forceinline__ float exp2f_fast(float x) {
@@ -237,44 +265,74 @@ __device__ __forceinline__ Tid make_tid() {
     return t;
 }
 
-__device__ __forceinline__ void load_weights(uint8_t *smem, const Net &net, Ctrl *ct, int tid) {
+__device__ __forceinline__ void load_weights(uint8_t *smem, const Net &net, uint64_t *bar, int tid) {
     if (tid == 0) {
-        tc::mbar_expect_tx(&ct->bar_w, W_END);
-        tc::bulk_g2s(smem + W1_OFF, net.w1, 2 * W1_PLANE, &ct->bar_w);
-        tc::bulk_g2s(smem + W2_OFF, net.w2, 2 * W2_PLANE, &ct->bar_w);
-        tc::bulk_g2s(smem + W3_OFF, net.w3, 2 * W3_PLANE, &ct->bar_w);
+        tc::mbar_expect_tx(bar, W_END);
+        tc::bulk_g2s(smem + W1_OFF, net.w1, 2 * W1_PLANE, bar);
+        tc::bulk_g2s(smem + W2_OFF, net.w2, 2 * W2_PLANE, bar);
+        tc::bulk_g2s(smem + W3_OFF, net.w3, 2 * W3_PLANE, bar);
     }
 }
 
-// publish this thread's smem image writes / TMEM reads, then let thread 0 issue the next MMA group
-#ifdef RSDF_PROFILE_PHASES
-// developer instrumentation (scripts/prof_phases.py): thread 0 of CTA 0 accumulates clock64 deltas
-//   [0] epilogue (previous PHASE_END -> PHASE_BEGIN)  [1] fences + __syncthreads  [2] MMA issue  [3] MMA wait
-__device__ unsigned long long g_prof[8];
-#define PROF_DECL() long long pt_ = clock64(); unsigned long long pa_[4] = {0, 0, 0, 0};
-#define PROF_MARK(i) { const long long n_ = clock64(); pa_[i] += (unsigned long long)(n_ - pt_); pt_ = n_; }
-#define PROF_FLUSH() if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < 4; ++i_) g_prof[i_] = pa_[i_]; }
-#else
-#define PROF_DECL()
-#define PROF_MARK(i)
-#define PROF_FLUSH()
-#endif
-#define PHASE_BEGIN()            \
-    PROF_MARK(0)                 \
-    tc::fence_async_smem();      \
-    tc::tc_fence_before();       \
-    __syncthreads();             \
-    PROF_MARK(1)                 \
-    if (t.warp == 0 && tc::elect_one()) { \
-        tc::tc_fence_after();
-#define PHASE_END()                          \
-        tc::mma_commit(&ct->bar_mma);        \
-    }                                        \
-    PROF_MARK(2)                             \
-    tc::mbar_wait(&ct->bar_mma, mma_phase);  \
-    mma_phase ^= 1;                          \
-    tc::tc_fence_after();                    \
-    PROF_MARK(3)
+// ---- half-tile ping-pong ---------------------------------------------------------------------------
+// The per-tile work is a strict chain  GEMM -> epilogue -> GEMM -> ...  (7 links in the backward), and with one tile in
+// flight the tensor pipe idles during every epilogue and all 16 epilogue warps idle during every GEMM (measured:
+// 11.8 us + 5.8 us per tile, serialised).  A second 64-sample tile does not fit next to the 112 KB of weights, so the
+// tile is processed as two independent 32-SAMPLE HALVES instead: epilogue group g (warps 8g..8g+7, named barrier
+// 1 + g) owns sample columns [32g, 32g+32) of every image and of every TMEM region, and a dedicated issuer warp (16)
+// serves the two groups in strict alternation with N = 32 instructions.  Group g announces "operands in place" on
+// ready[g]; the issuer issues that half's GEMMs and commits to done[g]; while the pipe works on one half, the other
+// group's epilogue runs.  Strict alternation from ONE issuing thread also orders the weight-gradient accumulations
+// of the two halves into their shared TMEM accumulators.
+constexpr int TR_GRP = 256, TR_THREADS = 2 * TR_GRP + 32, HS = NS / 2;
+// (Registers are allocated per 4 warps, so the 17th warp costs as much as four: 96 registers per thread.  Handing the
+// issuer's share to the epilogue warps with setmaxnreg is bounded by the CTA's LAUNCH allocation, not the SM's file --
+// 4 x 128 x 112 + 128 x 40 exceeds 640 x 96 and the last warpgroup's setmaxnreg.inc never returns -- and an issuer at
+// the 24 registers that would fit cannot hold its descriptors; not used.)
+struct TrCtrl {
+    uint64_t bar_w, done[2], ready[2];
+    uint32_t tmem_slot, pad;
+};
+__device__ __forceinline__ void grp_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(TR_GRP) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// sample-half g of an operand: MN-major (samples on N: 4 chunks of 8) / K-major over samples (2 k-steps of 16)
+__device__ __forceinline__ tc::Operand half_n(tc::Operand o, int g) { o.addr += (uint32_t)g * 4u * o.sbo; return o; }
+__device__ __forceinline__ tc::Operand half_k(tc::Operand o, int g) { o.addr += (uint32_t)g * 2u * o.kstep; return o; }
+
+// group side: publish this group's smem image writes / TMEM reads and hand its half to the issuer; wait for the GEMMs
+#define TR_READY() { tc::fence_async_smem(); tc::tc_fence_before(); grp_sync(g); if (tg == 0) bar_arrive(&ct->ready[g]); }
+#define TR_WAIT() { tc::mbar_wait(&ct->done[g], dpar); dpar ^= 1u; tc::tc_fence_after(); }
+// issuer side: one link of the chain for half 0, then for half 1
+#define TR_ISSUE(...)                                          \
+    {                                                          \
+        _Pragma("unroll 1")                                    \
+        for (int g = 0; g < 2; ++g) {                          \
+            tc::mbar_wait(&ct->ready[g], rpar);                \
+            tc::tc_fence_after();                              \
+            if (tc::elect_one()) {                             \
+                __VA_ARGS__                                    \
+                tc::mma_commit(&ct->done[g]);                  \
+            }                                                  \
+            __syncwarp();                                      \
+        }                                                      \
+        rpar ^= 1u;                                            \
+    }
+
+__device__ __forceinline__ void tr_init(TrCtrl *ct, const Tid &t, uint32_t tmem_cols) {
+    if (t.tid == 0) {
+        tc::mbar_init(&ct->bar_w, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&ct->done[i], 1); tc::mbar_init(&ct->ready[i], 1); }
+        tc::mbar_fence_init();
+    }
+    if (t.warp == 0) tc::tmem_alloc(&ct->tmem_slot, tmem_cols);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+}
 
 // ------------------------------------------------------------------------------------------------
 // forward: out[S, n_out] and (WITH_GRAD) g0[S, n_in] = d out[:,0] / d h0
@@ -283,113 +341,116 @@ constexpr uint32_t F_H0 = W_END, F_BIGA = F_H0 + IMG_S_BYTES, F_BIGB = F_BIGA + 
                    F_CTRL = F_BIGB + IMG_B_BYTES, F_SMEM = F_CTRL + 64;
 
 template <bool WITH_GRAD, bool SPLIT>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(TR_THREADS, 1)
 sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *__restrict__ sdf,
                float *__restrict__ g0a, float *__restrict__ g0b) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    Ctrl *ct = reinterpret_cast<Ctrl *>(smem + F_CTRL);
+    TrCtrl *ct = reinterpret_cast<TrCtrl *>(smem + F_CTRL);
     uint8_t *h0_img = smem + F_H0, *big_a = smem + F_BIGA, *big_b = smem + F_BIGB;
     Tid t = make_tid();
-    if (t.tid == 0) {
-        tc::mbar_init(&ct->bar_w, 1);
-        tc::mbar_init(&ct->bar_mma, 1);
-        tc::mbar_fence_init();
-    }
-    if (t.warp == 0) tc::tmem_alloc(&ct->tmem_slot, 256);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
+    tr_init(ct, t, 256);
     const uint32_t tmem = ct->tmem_slot;
-    t.tl = tmem + ((uint32_t)(t.q * 32) << 16);
-    load_weights(smem, net, ct, t.tid);
-    const float b1f = net.b1[t.f], b2f = net.b2[t.f], w30f = net.w3r0[t.f];
-    const float b3f = t.f < net.n_out ? net.b3[t.f] : 0.0f;
-    tc::mbar_wait(&ct->bar_w, 0);
-
-    const uint32_t sW1 = tc::smem_u32(smem + W1_OFF), sW2 = tc::smem_u32(smem + W2_OFF),
-                   sW3 = tc::smem_u32(smem + W3_OFF), sH0 = tc::smem_u32(h0_img), sA = tc::smem_u32(big_a),
-                   sB = tc::smem_u32(big_b);
-    const uint32_t id_kn = tc::instr_desc(128, NS, false, true);    // A K-major (W),   B MN-major (image)
-    const uint32_t id_tn = tc::instr_desc(128, NS, true, true);     // A MN-major (W^T), B MN-major
+    load_weights(smem, net, &ct->bar_w, t.tid);
     constexpr uint32_t Z1 = 0, Z2 = 64, T0 = 128, T1 = 192;
-    uint32_t mma_phase = 0;
-    PROF_DECL()
     const int n_tiles = (in.S + NS - 1) / NS;
-    const RowSrc src_h = row_src(in.in0, in.w0, in.sc0, in.sh0, in.in1, in.w1, t.tid & 63);
-    float hv[8];
-    if ((int)blockIdx.x < n_tiles) load_chunk8(src_h, t.tid, blockIdx.x * NS, in.S, hv);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int s0 = tile * NS;
-        store_chunk8<SPLIT>(h0_img, t, hv);
-        // P1: Z1 = W1 h0
-        PHASE_BEGIN()
-            gemm3<KP / 16, SPLIT>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
-        PHASE_END()
-        // prefetch the next tile's inputs; they land while this tile computes
-        if (tile + (int)gridDim.x < n_tiles) load_chunk8(src_h, t.tid, (tile + gridDim.x) * NS, in.S, hv);
-        {
-            float v[16];
-            ld16(t, Z1, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
-            st16<SPLIT>(big_a, t, v);
+    if (t.warp == 2 * TR_GRP / 32) {
+        // ---- MMA issuer -----------------------------------------------------------------------------------
+        const uint32_t sW1 = tc::smem_u32(smem + W1_OFF), sW2 = tc::smem_u32(smem + W2_OFF),
+                       sW3 = tc::smem_u32(smem + W3_OFF), sH0 = tc::smem_u32(h0_img), sA = tc::smem_u32(big_a),
+                       sB = tc::smem_u32(big_b);
+        const uint32_t id_kn = tc::instr_desc(128, HS, false, true);    // A K-major (W),   B MN-major (image half)
+        const uint32_t id_tn = tc::instr_desc(128, HS, true, true);     // A MN-major (W^T), B MN-major
+        tc::mbar_wait(&ct->bar_w, 0);
+        uint32_t rpar = 0u;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t z = opaque_zero();
+            const tc::Operand W1k = tc::op_kmajor(sW1 + z, W1_PLANE, HID), W2k = tc::op_kmajor(sW2 + z, W2_PLANE, HID),
+                              W3k = tc::op_kmajor(sW3 + z, W3_PLANE, KP), W1t = tc::op_mnmajor(sW1 + z, W1_PLANE, HID),
+                              W2t = tc::op_mnmajor(sW2 + z, W2_PLANE, HID);
+            const tc::Operand H0n = tc::op_mnmajor(sH0 + z, IMG_S_PLANE, KP), An = tc::op_mnmajor(sA + z, IMG_B_PLANE, HID),
+                              Bn = tc::op_mnmajor(sB + z, IMG_B_PLANE, HID);
+            // P1: Z1 = W1 h0
+            TR_ISSUE(gemm3r<KP / 16, SPLIT>(tmem + Z1 + HS * g, W1k, half_n(H0n, g), id_kn, false);)
+            // P2: Z2 = W2 a1
+            TR_ISSUE(gemm3r<HID / 16, SPLIT>(tmem + Z2 + HS * g, W2k, half_n(An, g), id_kn, false);)
+            // P3: out = W3 a2 (lanes >= 48 are don't-care);  v1 = W2^T u2
+            TR_ISSUE(gemm3r<HID / 16, SPLIT>(tmem + T0 + HS * g, W3k, half_n(An, g), id_kn, false);
+                     if (WITH_GRAD) gemm3r<HID / 16, SPLIT>(tmem + T1 + HS * g, W2t, half_n(Bn, g), id_tn, false);)
+            // P4: g0 = W1^T u1 (lanes >= 48 don't-care)
+            if (WITH_GRAD) TR_ISSUE(gemm3r<HID / 16, SPLIT>(tmem + T0 + HS * g, W1t, half_n(An, g), id_tn, false);)
         }
-        // P2: Z2 = W2 a1
-        PHASE_BEGIN()
-            gemm3<HID / 16, SPLIT>(tmem + Z2, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
-        PHASE_END()
-        {
-            float v[16], u[16];
-            ld16(t, Z2, v);
+    } else {
+        // ---- epilogue group g: thread = feature row f x 16 of the half's 32 sample columns -----------------
+        const int g = t.warp >> 3, tg = t.tid & (TR_GRP - 1);
+        t.tl = tmem + ((uint32_t)(t.q * 32) << 16);
+        const float b1f = net.b1[t.f], b2f = net.b2[t.f], w30f = net.w3r0[t.f];
+        const float b3f = t.f < net.n_out ? net.b3[t.f] : 0.0f;
+        uint32_t dpar = 0u;
+        const RowSrc src_h = row_src(in.in0, in.w0, in.sc0, in.sh0, in.in1, in.w1, t.tid & 63);
+        float hv[8];
+        if ((int)blockIdx.x < n_tiles) load_chunk8(src_h, t.tid, blockIdx.x * NS, in.S, hv);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int s0 = tile * NS;
+            store_chunk8<SPLIT>(h0_img, t, hv);
+            TR_READY()                                               // P1
+            // prefetch the next tile's inputs; they land while this tile computes
+            if (tile + (int)gridDim.x < n_tiles) load_chunk8(src_h, t.tid, (tile + gridDim.x) * NS, in.S, hv);
+            TR_WAIT()
+            {
+                float v[16];
+                ld16(t, Z1, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float a, sg, ds;
-                sp_all(v[j] + b2f, a, sg, ds);
-                v[j] = a;
-                u[j] = sg * w30f;
+                for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
+                st16<SPLIT>(big_a, t, v);
             }
-            st16<SPLIT>(big_a, t, v);                            // a2 (a1's MMA has drained)
-            if (WITH_GRAD) st16<SPLIT>(big_b, t, u);             // u2 = s2 . W3[0,:]
-        }
-        // P3: out = W3 a2 (lanes >= 48 are don't-care);  v1 = W2^T u2
-        PHASE_BEGIN()
-            gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_kmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
-            if (WITH_GRAD)
-                gemm3<HID / 16, SPLIT>(tmem + T1, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
-        PHASE_END()
-        store_rows(out, net.n_out, 1.0f, nullptr, 0, s0, in.S, t, T0, b3f, nullptr);
-        if (sdf && t.q == 0) {            // the sdf head (feature row 0) once more as its own [S] array
-            float v[16];
-            ld16(t, T0, v);
-            if (t.f == 0) {
-                const int sb = s0 + t.col0;
-                if (sb + 16 <= in.S) {
+            TR_READY()                                               // P2
+            TR_WAIT()
+            {
+                float v[16], u[16];
+                ld16(t, Z2, v);
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4 *>(sdf + sb + j) =
-                            make_float4(v[j] + b3f, v[j + 1] + b3f, v[j + 2] + b3f, v[j + 3] + b3f);
-                } else {
+                for (int j = 0; j < 16; ++j) {
+                    float a, sg, ds;
+                    sp_all(v[j] + b2f, a, sg, ds);
+                    v[j] = a;
+                    u[j] = sg * w30f;
+                }
+                st16<SPLIT>(big_a, t, v);                            // a2 (a1's MMA has drained)
+                if (WITH_GRAD) st16<SPLIT>(big_b, t, u);             // u2 = s2 . W3[0,:]
+            }
+            TR_READY()                                               // P3
+            TR_WAIT()
+            store_rows(out, net.n_out, 1.0f, nullptr, 0, s0, in.S, t, T0, b3f, nullptr);
+            if (sdf && t.q == 0) {            // the sdf head (feature row 0) once more as its own [S] array
+                float v[16];
+                ld16(t, T0, v);
+                if (t.f == 0) {
+                    const int sb = s0 + t.col0;
+                    if (sb + 16 <= in.S) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (sb + j < in.S) sdf[sb + j] = v[j] + b3f;
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4 *>(sdf + sb + j) =
+                                make_float4(v[j] + b3f, v[j + 1] + b3f, v[j + 2] + b3f, v[j + 3] + b3f);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (sb + j < in.S) sdf[sb + j] = v[j] + b3f;
+                    }
                 }
             }
-        }
-        if (WITH_GRAD) {
-            float v[16], z[16];
-            ld16(t, T1, v);
-            ld16(t, Z1, z);
+            if (WITH_GRAD) {
+                float v[16], z[16];
+                ld16(t, T1, v);
+                ld16(t, Z1, z);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] *= sp_sig(z[j] + b1f);
-            st16<SPLIT>(big_a, t, v);                            // u1 = s1 . v1
-            // P4: g0 = W1^T u1 (lanes >= 48 don't-care)
-            PHASE_BEGIN()
-                gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
-            PHASE_END()
-            store_rows(g0a, in.w0, 1.0f, g0b, in.w1, s0, in.S, t, T0, 0.0f, nullptr);
+                for (int j = 0; j < 16; ++j) v[j] *= sp_sig(z[j] + b1f);
+                st16<SPLIT>(big_a, t, v);                            // u1 = s1 . v1
+                TR_READY()                                           // P4
+                TR_WAIT()
+                store_rows(g0a, in.w0, 1.0f, g0b, in.w1, s0, in.S, t, T0, 0.0f, nullptr);
+            }
         }
     }
-    PROF_FLUSH()
     tc::tc_fence_before();
     __syncthreads();
     if (t.warp == 0) tc::tmem_free(tmem, 256);
@@ -412,10 +473,10 @@ struct Grads {
 // CHAIN = false: no cotangent reaches g0 (plain first-order backward, e.g. the finite-difference evaluations
 // of the split-sum config): the gradient-chain GEMMs and three of the seven epilogue passes drop out.
 template <bool CHAIN, bool SPLIT>
-__global__ void __launch_bounds__(THREADS, 1)
-sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
+__global__ void __launch_bounds__(TR_THREADS, 1)
+sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    Ctrl *ct = reinterpret_cast<Ctrl *>(smem + B_CTRL);
+    TrCtrl *ct = reinterpret_cast<TrCtrl *>(smem + B_CTRL);
     uint32_t *smax = reinterpret_cast<uint32_t *>(smem + B_CTRL + 64);   // [64] per-sample |cotangent| max (bits)
     float *ssc = reinterpret_cast<float *>(smax + NS);                    // [64] 2^k_s
     float *sinv = ssc + NS;                                               // [64] 2^-k_s
@@ -423,223 +484,238 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
     uint8_t *h0_img = smem + B_H0, *h0w_img = smem + B_H0W, *go_img = smem + B_GO, *gg_img = smem + B_GG,
             *big_a = smem + B_BIGA, *big_b = smem + B_BIGB;
     Tid t = make_tid();
-    if (t.tid == 0) {
-        tc::mbar_init(&ct->bar_w, 1);
-        tc::mbar_init(&ct->bar_mma, 1);
-        tc::mbar_fence_init();
-    }
     if (t.tid < NS) smax[t.tid] = 0u;
-    if (t.warp == 0) tc::tmem_alloc(&ct->tmem_slot, 512);
+    tr_init(ct, t, 512);
+    const uint32_t tmem = ct->tmem_slot;
+    t.tl = tmem + ((uint32_t)((t.q & 3) * 32) << 16);
+    load_weights(smem, net, &ct->bar_w, t.tid);
+    constexpr uint32_t AW2 = 0, AW1 = 128, AW3 = 176, Z1 = 224, Z2 = 288, T0 = 352, T1 = 416;
+    constexpr int KS = HS / 16;           // k-steps of a half's sample contraction
+    const int n_tiles = (in.S + NS - 1) / NS;
+    const int exp_g = (int)((__ldg(g_.amax) >> 23) & 0xFFu);   // launch-wide exponent: 2^K * gmax in [1, 2)
+    float b1acc = 0.0f, b2acc = 0.0f, b3acc = 0.0f, w3acc = 0.0f;
+    int it = 0;
+    if (t.warp == 2 * TR_GRP / 32) {
+        // ---- MMA issuer -----------------------------------------------------------------------------------
+        const uint32_t sW1 = tc::smem_u32(smem + W1_OFF), sW2 = tc::smem_u32(smem + W2_OFF),
+                       sW3 = tc::smem_u32(smem + W3_OFF), sH0 = tc::smem_u32(h0_img), sH0W = tc::smem_u32(h0w_img),
+                       sGO = tc::smem_u32(go_img), sGG = tc::smem_u32(gg_img), sA = tc::smem_u32(big_a),
+                       sB = tc::smem_u32(big_b);
+        const uint32_t id_kn = tc::instr_desc(128, HS, false, true);
+        const uint32_t id_tn = tc::instr_desc(128, HS, true, true);
+        const uint32_t id_g48 = tc::instr_desc(128, KP, false, false);    // weight-gradient products (contract samples)
+        const uint32_t id_g128 = tc::instr_desc(128, HID, false, false);
+        tc::mbar_wait(&ct->bar_w, 0);
+        uint32_t rpar = 0u;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t z = opaque_zero();
+            const tc::Operand W1k = tc::op_kmajor(sW1 + z, W1_PLANE, HID), W2k = tc::op_kmajor(sW2 + z, W2_PLANE, HID),
+                              W1t = tc::op_mnmajor(sW1 + z, W1_PLANE, HID), W2t = tc::op_mnmajor(sW2 + z, W2_PLANE, HID),
+                              W3t = tc::op_mnmajor(sW3 + z, W3_PLANE, KP);
+            // activation / cotangent images: MN-major view (layer GEMMs, samples on N) and K-major view (weight gradients)
+            const tc::Operand H0n = tc::op_mnmajor(sH0 + z, IMG_S_PLANE, KP), GOn = tc::op_mnmajor(sGO + z, IMG_S_PLANE, KP),
+                              GGn = tc::op_mnmajor(sGG + z, IMG_S_PLANE, KP), An = tc::op_mnmajor(sA + z, IMG_B_PLANE, HID),
+                              Bn = tc::op_mnmajor(sB + z, IMG_B_PLANE, HID);
+            const tc::Operand H0Wk = tc::op_kmajor(sH0W + z, IMG_S_PLANE, KP), GOk = tc::op_kmajor(sGO + z, IMG_S_PLANE, KP),
+                              GGk = tc::op_kmajor(sGG + z, IMG_S_PLANE, KP), Ak = tc::op_kmajor(sA + z, IMG_B_PLANE, HID),
+                              Bk = tc::op_kmajor(sB + z, IMG_B_PLANE, HID);
+            const bool acc = it > 0;
+            // P1: Z1 = W1 h0
+            TR_ISSUE(gemm3r<KP / 16, SPLIT>(tmem + Z1 + HS * g, W1k, half_n(H0n, g), id_kn, false);)
+            // P2: Z2 = W2 a1
+            TR_ISSUE(gemm3r<HID / 16, SPLIT>(tmem + Z2 + HS * g, W2k, half_n(An, g), id_kn, false);)
+            // P3: gW3^T += a2 g_out^T ; v1 = W2^T u2 ; ub1 = W1 g_g0   (no chain: ab2 = W3^T g_out right away)
+            TR_ISSUE(gemm3r<KS, SPLIT>(tmem + AW3, half_k(Ak, g), half_k(GOk, g), id_g48, acc || g);
+                     if (CHAIN) {
+                         gemm3r<HID / 16, SPLIT>(tmem + T0 + HS * g, W2t, half_n(Bn, g), id_tn, false);
+                         gemm3r<KP / 16, SPLIT>(tmem + T1 + HS * g, W1k, half_n(GGn, g), id_kn, false);
+                     } else {
+                         gemm3r<KP / 16, SPLIT>(tmem + T1 + HS * g, W3t, half_n(GOn, g), id_tn, false);
+                     })
+            if (CHAIN) {
+                // P4: gW1 += u1 g_g0^T
+                TR_ISSUE(gemm3r<KS, SPLIT>(tmem + AW1, half_k(Ak, g), half_k(GGk, g), id_g48, acc || g);)
+                // P5: gW2 += u2 vb1^T ; ub2 = W2 vb1 ; ab2 = W3^T g_out
+                TR_ISSUE(gemm3r<KS, SPLIT>(tmem + AW2, half_k(Bk, g), half_k(Ak, g), id_g128, acc || g);
+                         gemm3r<HID / 16, SPLIT>(tmem + T0 + HS * g, W2k, half_n(An, g), id_kn, false);
+                         gemm3r<KP / 16, SPLIT>(tmem + T1 + HS * g, W3t, half_n(GOn, g), id_tn, false);)
+            }
+            // P6: gW2 += zb2 a1^T ; ab1 = W2^T zb2
+            TR_ISSUE(gemm3r<KS, SPLIT>(tmem + AW2, half_k(Ak, g), half_k(Bk, g), id_g128, CHAIN || acc || g);
+                     gemm3r<HID / 16, SPLIT>(tmem + T0 + HS * g, W2t, half_n(An, g), id_tn, false);)
+            // P7: gW1 += zb1 h0^T ; d/d h0 = W1^T zb1
+            TR_ISSUE(gemm3r<KS, SPLIT>(tmem + AW1, half_k(Ak, g), half_k(H0Wk, g), id_g48, CHAIN || acc || g);
+                     gemm3r<HID / 16, SPLIT>(tmem + T0 + HS * g, W1t, half_n(An, g), id_tn, false);)
+        }
+    } else {
+        // ---- epilogue group g -----------------------------------------------------------------------------
+        const int g = t.warp >> 3, tg = t.tid & (TR_GRP - 1);
+        const float b1f = net.b1[t.f], b2f = net.b2[t.f], w30f = net.w3r0[t.f];
+        uint32_t dpar = 0u;
+        const int cs = t.tid >> 6;            // the 8-sample chunk this thread stages (chunks 4g .. 4g+3 in group g)
+        const RowSrc src_h = row_src(in.in0, in.w0, in.sc0, in.sh0, in.in1, in.w1, t.tid & 63);
+        const RowSrc src_go = row_src(g_.g_out, net.n_out, 1.0f, 0.0f, nullptr, 0, t.tid & 63);
+        const RowSrc src_gg = row_src(g_.g_g0a, in.w0, 1.0f, 0.0f, g_.g_g0b, in.w1, t.tid & 63);
+        const bool add_sdf = g_.g_sdf != nullptr && (t.tid & 63) == 0;      // g_sdf joins feature row 0 of g_out
+        float hv[8], gov[8], ggv[8];
+        auto load_tile = [&](int s0) {
+            load_chunk8(src_h, t.tid, s0, in.S, hv);
+            load_chunk8<false>(src_go, t.tid, s0, in.S, gov);
+            load_chunk8<false>(src_gg, t.tid, s0, in.S, ggv);
+            if (add_sdf) {
+                const int sb = s0 + 8 * cs;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (sb + j < in.S) gov[j] += __ldg(g_.g_sdf + sb + j);
+            }
+        };
+        if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x * NS);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s0 = tile * NS;
+            // ---- per-sample cotangent scale -----------------------------------------------------------
+            {
+                // per-sample max over the feature rows: a warp holds 32 rows of the same 8 samples, so one
+                // redux.sync per sample and a single shared atomic per warp (48 same-address atomics per
+                // sample serialise into ~3000 bank-conflict wavefronts per tile otherwise)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    b3acc += gov[j];
+                    const float m = fmaxf(fabsf(gov[j]), fabsf(ggv[j]));
+                    const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+                    if (t.lane == 0 && wm != 0u) atomicMax(&smax[8 * cs + j], wm);
+                }
+                grp_sync(g);
+                if (tg < HS) {
+                    const int sl = HS * g + tg;
+                    const int e = (int)((smax[sl] >> 23) & 0xFFu);         // biased exponent of the sample's max
+                    float sc = 1.0f, inv = 1.0f, wsc = 0.0f;
+                    if (e > 0 && e < 254) {
+                        sc = __uint_as_float((uint32_t)(254 - e) << 23);   // 2^(127 - e): max -> [1, 2)
+                        inv = __uint_as_float((uint32_t)e << 23);
+                        const int d = e - exp_g;                           // <= 0 (+1 when g_sdf adds onto g_out[:,0])
+                        wsc = d < -126 ? 0.0f : __uint_as_float((uint32_t)(127 + min(d, 8)) << 23);
+                    }
+                    ssc[sl] = sc; sinv[sl] = inv; swsc[sl] = wsc;
+                    smax[sl] = 0u;
+                }
+                grp_sync(g);
+                float hw[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float sc = ssc[8 * cs + j];
+                    gov[j] *= sc; ggv[j] *= sc;
+                    hw[j] = hv[j] * swsc[8 * cs + j];
+                }
+                store_chunk8<SPLIT>(h0_img, t, hv);
+                store_chunk8<SPLIT>(h0w_img, t, hw);
+                store_chunk8<SPLIT>(go_img, t, gov);
+                store_chunk8<SPLIT>(gg_img, t, ggv);
+            }
+            TR_READY()                                               // P1
+            if (tile + (int)gridDim.x < n_tiles) load_tile((tile + gridDim.x) * NS);      // prefetch the next tile's rows
+            TR_WAIT()
+            const float *wsc = swsc + t.col0, *inv = sinv + t.col0;    // per-sample factors (smem broadcasts)
+            {
+                float v[16];
+                ld16(t, Z1, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
+                st16<SPLIT>(big_a, t, v);                            // a1
+            }
+            TR_READY()                                               // P2
+            TR_WAIT()
+            {
+                float v[16], u[16];
+                ld16(t, Z2, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float a, sg, ds;
+                    sp_all(v[j] + b2f, a, sg, ds);
+                    v[j] = a * wsc[j];
+                    u[j] = sg * w30f;
+                }
+                st16<SPLIT>(big_a, t, v);                            // a2 * 2^(K-k_s)  (weight-gradient operand only)
+                if (CHAIN) st16<SPLIT>(big_b, t, u);                 // u2
+            }
+            TR_READY()                                               // P3
+            TR_WAIT()
+            float zp[16], vb[16];                             // z1-bar (chain part) and v1-bar, kept in registers
+            if (CHAIN) {
+                float v[16], ub[16], z[16];
+                ld16(t, T0, v);
+                ld16(t, T1, ub);
+                ld16(t, Z1, z);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float sg, ds;
+                    sp_sig_dsig(z[j] + b1f, sg, ds);
+                    vb[j] = sg * ub[j];
+                    zp[j] = v[j] * ub[j] * ds;
+                    v[j] *= sg * wsc[j];
+                }
+                st16<SPLIT>(big_a, t, v);                            // u1 * 2^(K-k_s) = s1 . v1  (weight-gradient operand)
+                ld16(t, Z2, z);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) z[j] = sp_sig(z[j] + b2f) * w30f * wsc[j];
+                st16<SPLIT>(big_b, t, z);                            // u2 * 2^(K-k_s)  (v1's MMA has drained)
+                TR_READY()                                           // P4
+                TR_WAIT()
+                st16<SPLIT>(big_a, t, vb);                           // v1-bar
+                TR_READY()                                           // P5
+                TR_WAIT()
+            }
+            {
+                float ub[16], ab[16], z[16];
+                if (CHAIN) {
+                    ld16(t, T0, ub);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ub[j] = 0.0f;
+                }
+                ld16(t, T1, ab);
+                ld16(t, Z2, z);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float sg, ds;
+                    sp_sig_dsig(z[j] + b2f, sg, ds);
+                    w3acc = fmaf(sg * ub[j], inv[j], w3acc);
+                    const float zb = fmaf(ub[j] * w30f, ds, ab[j] * sg);
+                    b2acc = fmaf(zb, inv[j], b2acc);
+                    z[j] = zb;
+                }
+                st16<SPLIT>(big_a, t, z);                            // z2-bar
+                ld16(t, Z1, z);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) z[j] = sp_act(z[j] + b1f) * wsc[j];
+                st16<SPLIT>(big_b, t, z);                            // a1 * 2^(K-k_s)
+            }
+            TR_READY()                                               // P6
+            TR_WAIT()
+            {
+                float ab[16], z[16];
+                ld16(t, T0, ab);
+                ld16(t, Z1, z);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float zb = fmaf(ab[j], sp_sig(z[j] + b1f), CHAIN ? zp[j] : 0.0f);
+                    b1acc = fmaf(zb, inv[j], b1acc);
+                    z[j] = zb;
+                }
+                st16<SPLIT>(big_a, t, z);                            // z1-bar
+            }
+            TR_READY()                                               // P7
+            TR_WAIT()
+            if (g_.g_in0 || g_.g_in1) store_rows(g_.g_in0, in.w0, in.sc0, g_.g_in1, in.w1, s0, in.S, t, T0, 0.0f, sinv);
+            grp_sync(g);                                      // sinv/swsc are rewritten by the next tile
+        }
+    }
+    // every MMA has completed once group 1 is past its last wait; publish that to the whole CTA before the flush
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem = ct->tmem_slot;
-    t.tl = tmem + ((uint32_t)(t.q * 32) << 16);
-    load_weights(smem, net, ct, t.tid);
-    const float b1f = net.b1[t.f], b2f = net.b2[t.f], w30f = net.w3r0[t.f];
-    // launch-wide exponent: 2^K * gmax in [1, 2)
-    const int exp_g = (int)((__ldg(g.amax) >> 23) & 0xFFu);
-    tc::mbar_wait(&ct->bar_w, 0);
-
-    const uint32_t sW1 = tc::smem_u32(smem + W1_OFF), sW2 = tc::smem_u32(smem + W2_OFF),
-                   sW3 = tc::smem_u32(smem + W3_OFF), sH0 = tc::smem_u32(h0_img), sH0W = tc::smem_u32(h0w_img),
-                   sGO = tc::smem_u32(go_img), sGG = tc::smem_u32(gg_img), sA = tc::smem_u32(big_a),
-                   sB = tc::smem_u32(big_b);
-    const uint32_t id_kn = tc::instr_desc(128, NS, false, true);
-    const uint32_t id_tn = tc::instr_desc(128, NS, true, true);
-    const uint32_t id_g48 = tc::instr_desc(128, KP, false, false);    // weight-gradient products (contract samples)
-    const uint32_t id_g128 = tc::instr_desc(128, HID, false, false);
-    constexpr uint32_t AW2 = 0, AW1 = 128, AW3 = 176, Z1 = 224, Z2 = 288, T0 = 352, T1 = 416;
-    constexpr int KS = NS / 16;           // k-steps of a sample contraction
-    uint32_t mma_phase = 0;
-    PROF_DECL()
-    float b1acc = 0.0f, b2acc = 0.0f, b3acc = 0.0f, w3acc = 0.0f;
-    const int n_tiles = (in.S + NS - 1) / NS;
-    const int cs = t.tid >> 6;            // the 8-sample chunk this thread stages
-    const RowSrc src_h = row_src(in.in0, in.w0, in.sc0, in.sh0, in.in1, in.w1, t.tid & 63);
-    const RowSrc src_go = row_src(g.g_out, net.n_out, 1.0f, 0.0f, nullptr, 0, t.tid & 63);
-    const RowSrc src_gg = row_src(g.g_g0a, in.w0, 1.0f, 0.0f, g.g_g0b, in.w1, t.tid & 63);
-    const bool add_sdf = g.g_sdf != nullptr && (t.tid & 63) == 0;      // g_sdf joins feature row 0 of g_out
-    float hv[8], gov[8], ggv[8];
-    auto load_tile = [&](int s0) {
-        load_chunk8(src_h, t.tid, s0, in.S, hv);
-        load_chunk8<false>(src_go, t.tid, s0, in.S, gov);
-        load_chunk8<false>(src_gg, t.tid, s0, in.S, ggv);
-        if (add_sdf) {
-            const int sb = s0 + 8 * cs;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (sb + j < in.S) gov[j] += __ldg(g.g_sdf + sb + j);
-        }
-    };
-    if ((int)blockIdx.x < n_tiles) load_tile(blockIdx.x * NS);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s0 = tile * NS;
-        const bool acc = it > 0;
-        // ---- per-sample cotangent scale -----------------------------------------------------------
-        {
-            // per-sample max over the feature rows: a warp holds 32 rows of the same 8 samples, so one
-            // redux.sync per sample and a single shared atomic per warp (48 same-address atomics per
-            // sample serialise into ~3000 bank-conflict wavefronts per tile otherwise)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                b3acc += gov[j];
-                const float m = fmaxf(fabsf(gov[j]), fabsf(ggv[j]));
-                const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
-                if (t.lane == 0 && wm != 0u) atomicMax(&smax[8 * cs + j], wm);
-            }
-            __syncthreads();
-            if (t.tid < NS) {
-                const int e = (int)((smax[t.tid] >> 23) & 0xFFu);      // biased exponent of the sample's max
-                float sc = 1.0f, inv = 1.0f, wsc = 0.0f;
-                if (e > 0 && e < 254) {
-                    sc = __uint_as_float((uint32_t)(254 - e) << 23);   // 2^(127 - e): max -> [1, 2)
-                    inv = __uint_as_float((uint32_t)e << 23);
-                    const int d = e - exp_g;                           // <= 0 (+1 when g_sdf adds onto g_out[:,0])
-                    wsc = d < -126 ? 0.0f : __uint_as_float((uint32_t)(127 + min(d, 8)) << 23);
-                }
-                ssc[t.tid] = sc; sinv[t.tid] = inv; swsc[t.tid] = wsc;
-                smax[t.tid] = 0u;
-            }
-            __syncthreads();
-            float hw[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float sc = ssc[8 * cs + j];
-                gov[j] *= sc; ggv[j] *= sc;
-                hw[j] = hv[j] * swsc[8 * cs + j];
-            }
-            store_chunk8<SPLIT>(h0_img, t, hv);
-            store_chunk8<SPLIT>(h0w_img, t, hw);
-            store_chunk8<SPLIT>(go_img, t, gov);
-            store_chunk8<SPLIT>(gg_img, t, ggv);
-        }
-        // P1: Z1 = W1 h0
-        PHASE_BEGIN()
-            gemm3<KP / 16, SPLIT>(tmem + Z1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sH0, IMG_S_PLANE, KP), id_kn, false);
-        PHASE_END()
-        if (tile + (int)gridDim.x < n_tiles) load_tile((tile + gridDim.x) * NS);      // prefetch the next tile's rows
-        const float *wsc = swsc + t.col0, *inv = sinv + t.col0;    // per-sample factors (smem broadcasts)
-        {
-            float v[16];
-            ld16(t, Z1, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = sp_act(v[j] + b1f);
-            st16<SPLIT>(big_a, t, v);                            // a1
-        }
-        // P2: Z2 = W2 a1
-        PHASE_BEGIN()
-            gemm3<HID / 16, SPLIT>(tmem + Z2, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
-        PHASE_END()
-        {
-            float v[16], u[16];
-            ld16(t, Z2, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float a, sg, ds;
-                sp_all(v[j] + b2f, a, sg, ds);
-                v[j] = a * wsc[j];
-                u[j] = sg * w30f;
-            }
-            st16<SPLIT>(big_a, t, v);                            // a2 * 2^(K-k_s)  (weight-gradient operand only)
-            if (CHAIN) st16<SPLIT>(big_b, t, u);                 // u2
-        }
-        // P3: gW3^T += a2 g_out^T ; v1 = W2^T u2 ; ub1 = W1 g_g0   (no chain: ab2 = W3^T g_out right away)
-        PHASE_BEGIN()
-            gemm3<KS, SPLIT>(tmem + AW3, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGO, IMG_S_PLANE, KP), id_g48, acc);
-            if (CHAIN) {
-                gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sB, IMG_B_PLANE, HID), id_tn, false);
-                gemm3<KP / 16, SPLIT>(tmem + T1, tc::op_kmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sGG, IMG_S_PLANE, KP), id_kn, false);
-            } else {
-                gemm3<KP / 16, SPLIT>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
-            }
-        PHASE_END()
-        float zp[16], vb[16];                             // z1-bar (chain part) and v1-bar, kept in registers
-        if (CHAIN) {
-            float v[16], ub[16], z[16];
-            ld16(t, T0, v);
-            ld16(t, T1, ub);
-            ld16(t, Z1, z);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float sg, ds;
-                sp_sig_dsig(z[j] + b1f, sg, ds);
-                vb[j] = sg * ub[j];
-                zp[j] = v[j] * ub[j] * ds;
-                v[j] *= sg * wsc[j];
-            }
-            st16<SPLIT>(big_a, t, v);                            // u1 * 2^(K-k_s) = s1 . v1  (weight-gradient operand)
-            ld16(t, Z2, z);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = sp_sig(z[j] + b2f) * w30f * wsc[j];
-            st16<SPLIT>(big_b, t, z);                            // u2 * 2^(K-k_s)  (v1's MMA has drained)
-        }
-        if (CHAIN) {
-            // P4: gW1 += u1 g_g0^T
-            PHASE_BEGIN()
-                gemm3<KS, SPLIT>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sGG, IMG_S_PLANE, KP), id_g48, acc);
-            PHASE_END()
-            st16<SPLIT>(big_a, t, vb);                           // v1-bar
-            // P5: gW2 += u2 vb1^T ; ub2 = W2 vb1 ; ab2 = W3^T g_out
-            PHASE_BEGIN()
-                gemm3<KS, SPLIT>(tmem + AW2, tc::op_kmajor(sB, IMG_B_PLANE, HID), tc::op_kmajor(sA, IMG_B_PLANE, HID), id_g128, acc);
-                gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_kmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_kn, false);
-                gemm3<KP / 16, SPLIT>(tmem + T1, tc::op_mnmajor(sW3, W3_PLANE, KP), tc::op_mnmajor(sGO, IMG_S_PLANE, KP), id_tn, false);
-            PHASE_END()
-        }
-        {
-            float ub[16], ab[16], z[16];
-            if (CHAIN) {
-                ld16(t, T0, ub);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) ub[j] = 0.0f;
-            }
-            ld16(t, T1, ab);
-            ld16(t, Z2, z);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float sg, ds;
-                sp_sig_dsig(z[j] + b2f, sg, ds);
-                w3acc = fmaf(sg * ub[j], inv[j], w3acc);
-                const float zb = fmaf(ub[j] * w30f, ds, ab[j] * sg);
-                b2acc = fmaf(zb, inv[j], b2acc);
-                z[j] = zb;
-            }
-            st16<SPLIT>(big_a, t, z);                            // z2-bar
-            ld16(t, Z1, z);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) z[j] = sp_act(z[j] + b1f) * wsc[j];
-            st16<SPLIT>(big_b, t, z);                            // a1 * 2^(K-k_s)
-        }
-        // P6: gW2 += zb2 a1^T ; ab1 = W2^T zb2
-        PHASE_BEGIN()
-            gemm3<KS, SPLIT>(tmem + AW2, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sB, IMG_B_PLANE, HID), id_g128, CHAIN || acc);
-            gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_mnmajor(sW2, W2_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
-        PHASE_END()
-        {
-            float ab[16], z[16];
-            ld16(t, T0, ab);
-            ld16(t, Z1, z);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float zb = fmaf(ab[j], sp_sig(z[j] + b1f), CHAIN ? zp[j] : 0.0f);
-                b1acc = fmaf(zb, inv[j], b1acc);
-                z[j] = zb;
-            }
-            st16<SPLIT>(big_a, t, z);                            // z1-bar
-        }
-        // P7: gW1 += zb1 h0^T ; d/d h0 = W1^T zb1
-        PHASE_BEGIN()
-            gemm3<KS, SPLIT>(tmem + AW1, tc::op_kmajor(sA, IMG_B_PLANE, HID), tc::op_kmajor(sH0W, IMG_S_PLANE, KP), id_g48, CHAIN || acc);
-            gemm3<HID / 16, SPLIT>(tmem + T0, tc::op_mnmajor(sW1, W1_PLANE, HID), tc::op_mnmajor(sA, IMG_B_PLANE, HID), id_tn, false);
-        PHASE_END()
-        if (g.g_in0 || g.g_in1) store_rows(g.g_in0, in.w0, in.sc0, g.g_in1, in.w1, s0, in.S, t, T0, 0.0f, sinv);
-        __syncthreads();                                  // sinv/swsc are rewritten by the next tile
-    }
+    const Grads &g = g_;
     // ---- flush the weight-gradient accumulators (x 2^-K; one atomic per element per CTA) ------------
-    if (it > 0) {
+    if (it > 0 && t.warp < 2 * TR_GRP / 32) {
         const float ginv = (exp_g > 0 && exp_g < 255) ? __uint_as_float((uint32_t)exp_g << 23) : 0.0f;
         float v[32];
         {                                                 // gW2[f][32*cq + j]
@@ -672,7 +748,6 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g) {
         const int fo = t.tid & 63;
         if (fo < net.n_out) atomicAdd(g.gb3 + fo, b3acc);
     }
-    PROF_FLUSH()
     tc::tc_fence_before();
     __syncthreads();
     if (t.warp == 0) tc::tmem_free(tmem, 512);
@@ -925,7 +1000,7 @@ int rsdf_sdf_mlp_fwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
     {                                                                                                            \
         e = cudaFuncSetAttribute(sdf_fwd_kernel<G, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM); \
         if (e != cudaSuccess) return (int)e;                                                                     \
-        sdf_fwd_kernel<G, SP><<<grid, THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, g0a, g0b); \
+        sdf_fwd_kernel<G, SP><<<grid, TR_THREADS, F_SMEM, (cudaStream_t)stream>>>(to_net(net), in, out, sdf, g0a, g0b); \
     }
     if (g0a) {
         if (net->precision) RSDF_FWD(true, false) else RSDF_FWD(true, true)
@@ -953,7 +1028,7 @@ int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
                      const float *g_g0a, const float *g_g0b, const uint32_t *amax_bits, float *g_in0, float *g_in1,
                      float *gW1, float *gb1, float *gW2, float *gb2, float *gW3, float *gb3, void *stream) {
     if (n_samples == 0) return 0;
-    if (!check_net(net) || !in0 || !g_out || !amax_bits || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) ||
+    if (!check_net(net) || !in0 || (!g_out && !g_sdf) || !amax_bits || w0 < 1 || w1 < 0 || (w1 > 0 && !in1) ||
         w0 + w1 != net->n_in || !gW1 || !gb1 || !gW2 || !gb2 || !gW3 || !gb3)
         return RSDF_EBADARG;
     const Inputs in{in0, in1, w0, w1, scale0, shift0, n_samples};
@@ -965,7 +1040,7 @@ int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
     {                                                                                                            \
         e = cudaFuncSetAttribute(sdf_bwd_kernel<C, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM); \
         if (e != cudaSuccess) return (int)e;                                                                     \
-        sdf_bwd_kernel<C, SP><<<grid, THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);               \
+        sdf_bwd_kernel<C, SP><<<grid, TR_THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);               \
     }
     if (g_g0a || g_g0b) {
         if (net->precision) RSDF_BWD(true, false) else RSDF_BWD(true, true)

@@ -59,7 +59,10 @@ class VolumeSDF(nn.Module):
             return None
         inner, mask = comp.encoding, None
         if isinstance(inner, ProgressiveBandHashGrid):
-            inner, mask = inner.encoding, inner.mask
+            # all levels switched on (global_step >= start_step + (n_level - start_level) * update_steps): the mask is
+            # exactly 1.0 everywhere and multiplying by it -- [S,32] forward and backward per field evaluation -- is
+            # a bit-exact no-op, skipped
+            inner, mask = inner.encoding, (None if inner.all_levels_on else inner.mask)
         if not (isinstance(inner, tcnn.Encoding) and inner.kind == "hashgrid"):
             return None
         return inner, mask
@@ -96,10 +99,10 @@ class VolumeSDF(nn.Module):
             if torch.is_grad_enabled():
                 if VanillaMLP.tc_training and VanillaMLP.fused_training:
                     y = inner(x01)
-                    out, _ = sdf_field.fused_sdf(self.network, x01, comp.xyz_scale, comp.xyz_offset,
-                                                 y if mask is None else y * mask, want_g0=False)
-                    out = self.network.output_activation(out)
-                    return out[..., 0] if sdf_only else out
+                    out, sdf, _, _ = sdf_field.fused_sdf_parts(self.network, x01, comp.xyz_scale, comp.xyz_offset,
+                                                               y if mask is None else y * mask, want_g0=False,
+                                                               sdf_only=sdf_only)
+                    return sdf if sdf_only else out        # (_fused_parts: the output activation is the identity)
             elif VanillaMLP.fused_inference:
                 y = inner(x01)
                 if mask is not None:

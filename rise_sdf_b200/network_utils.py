@@ -101,14 +101,18 @@ class ProgressiveBandHashGrid(nn.Module):
         self.current_level = self.start_level
         self.register_buffer("mask", torch.zeros(self.n_level * self.n_features_per_level), persistent=False)
 
+    all_levels_on = False       # host-side: mask == 1 everywhere (set by update_step, the only writer of the mask)
+
     def forward(self, x):
-        return self.encoding(x) * self.mask
+        y = self.encoding(x)
+        return y if self.all_levels_on else y * self.mask
 
     def update_step(self, epoch, global_step):
         current_level = min(self.start_level + max(global_step - self.start_step, 0) // self.update_steps,
                             self.n_level)
         self.current_level = current_level
         self.mask[: self.current_level * self.n_features_per_level] = 1.0
+        self.all_levels_on = current_level >= self.n_level
 
 
 class CompositeEncoding(nn.Module):

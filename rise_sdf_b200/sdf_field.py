@@ -62,7 +62,7 @@ class _FusedSDF(torch.autograd.Function):
     [S,48] / [S,35]) appears in the graph: the backward kernel takes the four cotangents directly."""
 
     @staticmethod
-    def forward(ctx, in0, in1, W1, b1, W2, b2, W3, b3, scale0, shift0, want_g0):
+    def forward(ctx, in0, in1, W1, b1, W2, b2, W3, b3, scale0, shift0, want_g0, sdf_only=False):
         L.require_cuda(in0, in1, W1)
         in0 = in0.contiguous().float()
         in1 = None if in1 is None else in1.contiguous().float()
@@ -70,16 +70,24 @@ class _FusedSDF(torch.autograd.Function):
         w1 = 0 if in1 is None else in1.shape[1]
         dev = in0.device
         net, keep = _net_struct(W1, b1, W2, b2, W3, b3)
-        out = torch.empty(S, W3.shape[0], device=dev, dtype=torch.float32)
+        # sdf_only (the six finite-difference neighbours of the split-sum config, models/geometry.py:229-240): only
+        # out[:, 0] is wanted -- the 48-wide output is neither written here nor read back as a (zero) cotangent
+        sdf_only = bool(sdf_only) and not want_g0
+        out = None if sdf_only else torch.empty(S, W3.shape[0], device=dev, dtype=torch.float32)
         sdf = torch.empty(S, device=dev, dtype=torch.float32)
         g0a = torch.empty(S, w0, device=dev, dtype=torch.float32) if want_g0 else None
         g0b = torch.empty(S, w1, device=dev, dtype=torch.float32) if (want_g0 and w1) else None
-        if S:
+        if S and sdf_only and not net.precision and PackedSDF.tensor_memory_operands:
+            L.call("rsdf_sdf_mlp_eval", ctypes.byref(net), L.ptr(in0), w0, float(scale0), float(shift0), L.ptr(in1), w1, S,
+                   None, L.ptr(sdf), L.stream())
+        elif S:
             L.call("rsdf_sdf_mlp_fwd", ctypes.byref(net), L.ptr(in0), w0, float(scale0), float(shift0), L.ptr(in1), w1,
                    S, L.ptr(out), L.ptr(sdf), L.ptr(g0a), L.ptr(g0b), L.stream())
         ctx.save_for_backward(in0, in1, W1, b1, W2, b2, W3, b3)
         ctx.net, ctx.keep, ctx.scale0, ctx.shift0, ctx.want_g0 = net, keep, float(scale0), float(shift0), bool(want_g0)
         empty = []
+        if out is None:
+            out = in0.new_zeros(0); empty.append(out)
         if g0a is None:
             g0a = in0.new_zeros(0); empty.append(g0a)
         if g0b is None:
@@ -135,7 +143,7 @@ class _FusedSDF(torch.autograd.Function):
                 got = torch.autograd.grad(outs, [tensors[i] for i in idx], cots, create_graph=True, allow_unused=True)
                 for i, g in zip(idx, got):
                     grads[i] = g
-        return (*grads, None, None, None)
+        return (*grads, None, None, None, None)
 
     @staticmethod
     def backward(ctx, g_out, g_sdf, g_g0a, g_g0b):
@@ -147,8 +155,8 @@ class _FusedSDF(torch.autograd.Function):
         dev = in0.device
         prep = lambda g: None if (g is None or g.numel() == 0) else g.contiguous().float()
         g_out, g_sdf, g_g0a, g_g0b = prep(g_out), prep(g_sdf), prep(g_g0a), prep(g_g0b)
-        if g_out is None:
-            g_out = torch.zeros(S, W3.shape[0], device=dev, dtype=torch.float32)
+        if g_out is None and g_sdf is None:
+            g_sdf = torch.zeros(S, device=dev, dtype=torch.float32)
         g_in0 = torch.empty(S, w0, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         g_in1 = torch.empty(S, w1, device=dev, dtype=torch.float32) if (ctx.needs_input_grad[1] and w1) else None
         gW1, gb1, gW2, gb2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2)
@@ -158,16 +166,16 @@ class _FusedSDF(torch.autograd.Function):
             L.call("rsdf_sdf_mlp_bwd", ctypes.byref(ctx.net), L.ptr(in0), w0, ctx.scale0, ctx.shift0, L.ptr(in1), w1, S,
                    L.ptr(g_out), L.ptr(g_sdf), L.ptr(g_g0a), L.ptr(g_g0b), L.ptr(amax), L.ptr(g_in0), L.ptr(g_in1),
                    L.ptr(gW1), L.ptr(gb1), L.ptr(gW2), L.ptr(gb2), L.ptr(gW3), L.ptr(gb3), L.stream())
-        return g_in0, g_in1, gW1, gb1, gW2, gb2, gW3, gb3, None, None, None
+        return g_in0, g_in1, gW1, gb1, gW2, gb2, gW3, gb3, None, None, None, None
 
 
-def fused_sdf_parts(mlp, in0, scale0=1.0, shift0=0.0, in1=None, want_g0=True):
-    """-> (out [S, dim_out], sdf [S], g0a [S, w0] | None, g0b [S, w1] | None)."""
+def fused_sdf_parts(mlp, in0, scale0=1.0, shift0=0.0, in1=None, want_g0=True, sdf_only=False):
+    """-> (out [S, dim_out] | None with sdf_only, sdf [S], g0a [S, w0] | None, g0b [S, w1] | None)."""
     (W1, b1), (W2, b2), (W3, b3) = mlp.effective_weights()
     out, sdf, g0a, g0b = _FusedSDF.apply(in0, in1, W1.float(), b1.float(), W2.float(), b2.float(), W3.float(),
-                                         b3.float(), scale0, shift0, want_g0)
+                                         b3.float(), scale0, shift0, want_g0, sdf_only)
     if not want_g0:
-        return out, sdf, None, None
+        return (None if sdf_only else out), sdf, None, None
     return out, sdf, g0a, (g0b if in1 is not None else None)
 
 

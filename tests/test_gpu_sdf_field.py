@@ -160,3 +160,30 @@ def test_double_backward_through_the_fused_node(want_g0):
     assert abs(float(l) - float(lr)) <= 1e-5 * abs(float(lr))
     for n, a, b in zip(["h0"] + [n for n, _ in m.named_parameters()], got, want):
         assert rel(a, b) <= 5e-5, (n, rel(a, b))
+
+
+@pytest.mark.parametrize("S", [77, 64 * 148 + 3])
+def test_sdf_only_training_node(S):
+    """The finite-difference neighbours of the split-sum config only need out[:, 0] (models/geometry.py:229-240): the
+    sdf-only node writes no 48-wide output, takes no 48-wide cotangent, and must give the gradients of the full node
+    driven through its sdf output (same backward kernel; here also against fp64)."""
+    m = make_mlp()
+    g = torch.Generator().manual_seed(S)
+    x01 = torch.rand(S, 3, generator=g).cuda()
+    enc = (torch.randn(S, 32, generator=g) * 0.1).cuda().requires_grad_(True)
+    cot = (torch.randn(S, generator=g) / S).cuda()
+    res = []
+    for sdf_only in (True, False):
+        m.zero_grad(set_to_none=True)
+        enc.grad = None
+        out, sdf, _, _ = sdf_field.fused_sdf_parts(m, x01, 2.0, -1.0, enc, want_g0=False, sdf_only=sdf_only)
+        assert (out is None) == sdf_only
+        (sdf * cot).sum().backward()
+        res.append((sdf.detach(), enc.grad.clone(), [p.grad.clone() for p in m.parameters() if p.grad is not None]))
+    (sa, ea, pa), (sb, eb, pb) = res
+    ro, _ = ref64(m, x01.double(), enc.detach().double(), want_g0=False)
+    assert rel(sa, ro[:, 0].detach()) <= 2e-6 and rel(sb, ro[:, 0].detach()) <= 2e-6
+    assert rel(ea, eb) <= 1e-6
+    assert len(pa) == len(pb) > 0
+    for x, y in zip(pa, pb):
+        assert rel(x, y) <= 1e-5
