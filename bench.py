@@ -25,6 +25,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# dynamic sample counts: see rise_sdf_b200/__init__.py (must be set before torch's first CUDA allocation)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 N_RAYS = 8192
 METRIC = "train_rays_per_s"

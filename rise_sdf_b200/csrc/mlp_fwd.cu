@@ -8,9 +8,10 @@
 //   * the accumulator lives in TMEM (128 lanes = 128 samples, <=128 fp32 columns);
 //   * layer weights stream L2 -> smem through a 2-deep ring of bulk async copies, so layer l+1's
 //     blob lands while layer l computes;  biases sit in smem for the whole kernel;
-//   * 8 warps: warp w owns TMEM lane quadrant w%4 (rows 32*(w%4)..+31) and column half w/4, so two
+//   * 16 warps: warp w owns TMEM lane quadrant w%4 (rows 32*(w%4)..+31) and column quarter w/4, so four
 //     threads share every sample row and the epilogue (bias, activation, fp16 split, 16-byte
-//     chunk stores) runs 256 wide; one elected thread issues the 3-term split MMAs.
+//     chunk stores) runs 512 wide -- the epilogue, not the tensor pipe, is what a layer waits for;
+//     one elected thread issues the 3-product split MMAs (hi*hi + hi*lo + lo*hi, as the training kernels).
 // No activation ever touches HBM between layers.
 #include "common.cuh"
 #include "tc.cuh"
@@ -19,7 +20,7 @@ namespace {
 
 constexpr int TM = 128;
 constexpr int MLP_MAX_LAYERS = RSDF_MLP_MAX_LAYERS;
-constexpr int THREADS = 256;
+constexpr int THREADS = 512, PARTS = THREADS / 128;
 
 struct MlpLayerDesc {
     const uint8_t *blob;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fwd_kernel(const __grid_consta
     uint8_t *w_img[2] = {smem + 65536, smem + 131072};       // 2 x 64 KB weight ring
     MlpSmem *sm = reinterpret_cast<MlpSmem *>(smem + 196608);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, part = warp >> 2;
     const int row = quad * 32 + lane;                        // sample row of this thread
 
     if (tid == 0) {
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fwd_kernel(const __grid_consta
             const float *r0 = p.in[0] + (size_t)s * w0;
             const float *r1 = p.n_in > 1 ? p.in[1] + (size_t)s * w1 : nullptr;
             const float *r2 = p.n_in > 2 ? p.in[2] + (size_t)s * w2 : nullptr;
-            for (int c = half; c < k_pad0 / 8; c += 2) {
+            for (int c = part; c < k_pad0 / 8; c += PARTS) {
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fwd_kernel(const __grid_consta
                 const uint32_t idesc = tc::instr_desc(128, n_pad, false, false);
                 tc::gemm_split3(tmem, tc::op_kmajor(tc::smem_u32(a_img), TM * k_pad * 2, TM),
                                 tc::op_kmajor(tc::smem_u32(w_img[job & 1]), (uint32_t)n_pad * k_pad * 2, n_pad),
-                                k_pad / 16, idesc, false);
+                                k_pad / 16, idesc, false, /*keep_lo_lo=*/false);
                 tc::mma_commit(&sm->bar_mma);
                 if (job + 1 < total_jobs) issue_w(job + 1);   // other ring slot: its last reader has drained
             }
@@ -174,8 +175,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fwd_kernel(const __grid_consta
             tc::tc_fence_after();
             // ---- epilogue: this thread's half of the 16-column chunks ---------------------------
             const bool last = (l == p.n_layers - 1);
-            const int n_chunks = n_pad / 16, split = (n_chunks + 1) / 2;
-            const int c_begin = half == 0 ? 0 : split, c_end = half == 0 ? split : n_chunks;
+            const int n_chunks = n_pad / 16, per = (n_chunks + PARTS - 1) / PARTS;
+            const int c_begin = min(part * per, n_chunks), c_end = min(c_begin + per, n_chunks);
             const float *bias = sm->bias[l];
             if (!last) {
                 const uint32_t next_plane = TM * n_pad * 2;

@@ -242,18 +242,19 @@ struct Operand {
     uint32_t addr, plane, lbo, sbo, kstep;
 };
 __device__ __forceinline__ void gemm_split3(uint32_t tmem_d, const Operand &A, const Operand &B, int ksteps,
-                                            uint32_t idesc, bool accumulate) {
-    // order: lo*lo, lo*hi, hi*lo, hi*hi (small terms first into the accumulator).  The lo*lo term
-    // (~2^-22 of the product) is kept: it halves the residual error and the tensor pipe is not the
-    // bottleneck of these kernels.
+                                            uint32_t idesc, bool accumulate, bool keep_lo_lo = true) {
+    // order: lo*lo, lo*hi, hi*lo, hi*hi (small terms first into the accumulator).  The lo*lo term (~2^-22 of the
+    // product) halves the residual error; callers whose tensor time matters drop it (keep_lo_lo = false: the same
+    // three products as the training kernels).
+    const int first = keep_lo_lo ? 0 : 1;
 #pragma unroll 1
-    for (int term = 0; term < 4; ++term) {
+    for (int term = first; term < 4; ++term) {
         const uint32_t a0 = A.addr + (term < 2 ? A.plane : 0u);
         const uint32_t b0 = B.addr + ((term == 0 || term == 2) ? B.plane : 0u);
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k) {
             mma_f16(tmem_d, smem_desc(a0 + k * A.kstep, A.lbo, A.sbo), smem_desc(b0 + k * B.kstep, B.lbo, B.sbo),
-                     idesc, accumulate || term > 0 || k > 0);
+                     idesc, accumulate || term > first || k > 0);
         }
     }
 }
