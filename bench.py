@@ -51,24 +51,25 @@ KERNEL_WORK = {
     # first + second order table scatter in one pass: x, v, dL_dy, g2, one atomic RMW per corner
     "rsdf_hashgrid_bwd_table2": ("hbm", 12 + 12 + 128 + 128 + 2048, "hashgrid_bwd_table2_kernel"),
     "rsdf_hashgrid_jvp": ("hbm", 384 + 12 + 128, "hashgrid_jvp_kernel"),
-    "rsdf_sdf_mlp_fwd": ("tensor", _F_FWD + _F_CHAIN, "sdf_fwd_kernel<true>"),
-    "rsdf_sdf_mlp_bwd": ("tensor", _F_BWD, "sdf_bwd_kernel"),
+    "rsdf_sdf_mlp_fwd": ("tensor", _F_FWD + _F_CHAIN, "sdf_fwd_kernel<true, true>"),
+    "rsdf_sdf_mlp_bwd": ("tensor", _F_BWD, "sdf_bwd_kernel<true, true>"),
     # radiance MLP 67 -> 128 x4 -> 3 (a TENSOR kernel, 116 224 flop/sample forward, 2x that backward),
     # five launches each way: per-launch average.  4th entry = algorithmic HBM bytes/sample of the whole net (inputs
     # in, colours out / cotangents in, input gradients out) for the traffic-over-algorithmic ratio.
     "rsdf_relu_layer_fwd": ("tensor", _F_RAD / 5.0, "relu_layer_fwd_kernel", (268 + 12) / 5.0),
     "rsdf_relu_layer_bwd": ("tensor", 2 * _F_RAD / 5.0, "relu_layer_bwd_kernel", (12 + 268 + 268) / 5.0),
-    "rsdf_neus_render_fwd": ("hbm", 64, "neus_render_fwd_kernel"),
-    "rsdf_neus_render_bwd": ("hbm", 64 + 32, "neus_render_bwd_kernel"),
+    "rsdf_neus_render_fwd": ("hbm", 64, "sdf_render_fwd_kernel<3, true, false>"),
+    "rsdf_neus_render_bwd": ("hbm", 64 + 32, "sdf_render_bwd_kernel<3, true, false>"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/kernels_r01_full.txt, 3 339 366 samples), expressed per sample; per-launch averages for the
-# multi-launch entry points
-NCU_TRAFFIC_SOURCE = "profiles/kernels_r01_full.txt (ncu --set full, one capture; not re-measured by this run)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of THIS round's
+# kernels (profiles/kernels_r02_full.txt: one training step of `bench.py --steps 2`, 3 374 096 samples), expressed per
+# sample; per-launch averages for the multi-launch entry points
+NCU_TRAFFIC_SOURCE = "profiles/kernels_r02_full.txt (ncu --set full, one capture; not re-measured by this run)"
 NCU_TRAFFIC_PER_SAMPLE = {
-    "rsdf_hashgrid_fwd": 694, "rsdf_hashgrid_bwd_input": 529, "rsdf_hashgrid_jvp": 520, "rsdf_hashgrid_bwd_table2": 324,
-    "rsdf_sdf_mlp_fwd": 466, "rsdf_sdf_mlp_bwd": 602,
-    "rsdf_relu_layer_fwd": (1085 + 3 * 1012 + 525) / 5.0, "rsdf_relu_layer_bwd": (1025 + 3 * 1530 + 1095) / 5.0,
+    "rsdf_hashgrid_fwd": 686, "rsdf_hashgrid_bwd_input": 526, "rsdf_hashgrid_jvp": 520, "rsdf_hashgrid_bwd_table2": 322,
+    "rsdf_sdf_mlp_fwd": 461, "rsdf_sdf_mlp_bwd": 604,
+    "rsdf_relu_layer_fwd": (1087 + 3 * 1013 + 527) / 5.0, "rsdf_relu_layer_bwd": (1026 + 3 * 1532 + 1034) / 5.0,
+    "rsdf_neus_render_fwd": 43.4, "rsdf_neus_render_bwd": 74.5,
 }
 
 

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librsdf_b200.so")
+LIB_PATH = os.environ.get("RSDF_LIB_PATH") or os.path.join(_HERE, "librsdf_b200.so")   # override: developer experiments
 _lib = None
 
 c_p, c_i, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float

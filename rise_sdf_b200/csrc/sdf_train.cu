@@ -68,8 +68,21 @@ struct Tid {
 };
 
 __device__ __forceinline__ void ld16(const Tid &t, int col, float *v) {
+#ifdef RSDF_EXP_NO_LDST         // developer experiment: the chain's synchronisation skeleton alone
+    for (int j = 0; j < 16; ++j) v[j] = (float)col;
+    return;
+#endif
     tc::tmem_ld16(t.tl + (uint32_t)(col + t.col0), v);
     tc::tmem_ld_wait();
+}
+// several TMEM regions wanted together: issue the loads back to back and wait once (one TMEM round trip instead of
+// one per region on the critical path of the GEMM -> epilogue chain)
+__device__ __forceinline__ void ld16_issue(const Tid &t, int col, float *v) {
+#ifdef RSDF_EXP_NO_LDST
+    for (int j = 0; j < 16; ++j) v[j] = (float)col;
+    return;
+#endif
+    tc::tmem_ld16(t.tl + (uint32_t)(col + t.col0), v);
 }
 // SPLIT = true : fp32-class arithmetic, every operand an fp16 hi|lo pair and every GEMM three products (tc.cuh)
 // SPLIT = false: the reduced-precision VARIANT -- single fp16 plane, one product per GEMM (a third of the tensor work,
@@ -77,6 +90,10 @@ __device__ __forceinline__ void ld16(const Tid &t, int col, float *v) {
 // this thread's 16 samples of feature row f -> two 16-byte chunks per plane of a [128 x 64] image
 template <bool SPLIT = true>
 __device__ __forceinline__ void st16(uint8_t *img, const Tid &t, const float *v) {
+#ifdef RSDF_EXP_NO_LDST
+    if (v[0] == 12345.678f) img[0] = 1;
+    return;
+#endif
     const int c = t.col0 >> 3;
     if (SPLIT) {
         tc::store_chunk(img, IMG_B_PLANE, HID, t.f, c, v);
@@ -111,6 +128,9 @@ __device__ __forceinline__ void gemm3(uint32_t d, const tc::Operand &A, const tc
 template <int KSTEPS, bool SPLIT>
 __device__ __forceinline__ void gemm3r(uint32_t d, const tc::Operand &A, const tc::Operand &B, uint32_t idesc,
                                        bool accumulate) {
+#ifdef RSDF_EXP_NO_MMA          // developer experiment (scripts/exp_sdf_chain.sh): the chain without tensor work
+    return;
+#endif
     // the address is the low 14 bits of the descriptor's low word and never carries out of it: stepping a descriptor
     // is ONE 32-bit add, the high word (LBO | SBO | version) is per-operand constant
     const uint64_t a0 = tc::smem_desc(A.addr, A.lbo, A.sbo), b0 = tc::smem_desc(B.addr, B.lbo, B.sbo);
@@ -150,6 +170,12 @@ __device__ __forceinline__ float exp2f_fast(float x) {
 // exactly as torch's threshold branch does; only sigmoid' needs the explicit select.
 constexpr float SP_K = 100.0f * 1.4426950408889634f;          // beta * log2(e)
 constexpr float SP_L = 0.01f * 0.6931471805599453f;           // ln(2) / beta
+#ifdef RSDF_EXP_NO_MATH         // developer experiment: the chain without the transcendental epilogue math
+__device__ __forceinline__ void sp_sig_dsig(float z, float &s, float &ds) { s = z; ds = z; }
+__device__ __forceinline__ void sp_all(float z, float &a, float &s, float &ds) { a = z; s = z; ds = z; }
+__device__ __forceinline__ float sp_act(float z) { return z; }
+__device__ __forceinline__ float sp_sig(float z) { return z; }
+#else
 __device__ __forceinline__ void sp_sig_dsig(float z, float &s, float &ds) {
     const float e = exp2f_fast(-fabsf(z) * SP_K);
     const float r = __fdividef(1.0f, 1.0f + e);
@@ -173,6 +199,7 @@ __device__ __forceinline__ float sp_sig(float z) {
     const float r = __fdividef(1.0f, 1.0f + e);
     return z >= 0.0f ? r : e * r;
 }
+#endif
 
 // Row-major global -> registers: thread (f = tid % 64, c = tid / 64) fetches the 8-sample chunk
 // (samples s0 + 8c .. +7) of feature row f; a warp reads 32 consecutive floats of one sample row per
@@ -440,8 +467,9 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
             }
             if (WITH_GRAD) {
                 float v[16], z[16];
-                ld16(t, T1, v);
-                ld16(t, Z1, z);
+                ld16_issue(t, T1, v);
+                ld16_issue(t, Z1, z);
+                tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] *= sp_sig(z[j] + b1f);
                 st16<SPLIT>(big_a, t, v);                            // u1 = s1 . v1
@@ -642,9 +670,10 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
             float zp[16], vb[16];                             // z1-bar (chain part) and v1-bar, kept in registers
             if (CHAIN) {
                 float v[16], ub[16], z[16];
-                ld16(t, T0, v);
-                ld16(t, T1, ub);
-                ld16(t, Z1, z);
+                ld16_issue(t, T0, v);
+                ld16_issue(t, T1, ub);
+                ld16_issue(t, Z1, z);
+                tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float sg, ds;
@@ -667,13 +696,14 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
             {
                 float ub[16], ab[16], z[16];
                 if (CHAIN) {
-                    ld16(t, T0, ub);
+                    ld16_issue(t, T0, ub);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) ub[j] = 0.0f;
                 }
-                ld16(t, T1, ab);
-                ld16(t, Z2, z);
+                ld16_issue(t, T1, ab);
+                ld16_issue(t, Z2, z);
+                tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float sg, ds;
@@ -693,8 +723,9 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
             TR_WAIT()
             {
                 float ab[16], z[16];
-                ld16(t, T0, ab);
-                ld16(t, Z1, z);
+                ld16_issue(t, T0, ab);
+                ld16_issue(t, Z1, z);
+                tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float zb = fmaf(ab[j], sp_sig(z[j] + b1f), CHAIN ? zp[j] : 0.0f);

@@ -26,3 +26,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     torch.cuda.synchronize()
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="device_time_total", row_limit=70, max_name_column_width=48,
                                                          max_shapes_column_width=70))
+print("==== by host time, no shape grouping")
+ka = prof.key_averages()
+for e in sorted(ka, key=lambda e: -e.self_cpu_time_total)[:70]:
+    print(f"{e.self_cpu_time_total / 1e3:8.2f} ms self-host  {e.count:5d} x  {e.key[:90]}")
