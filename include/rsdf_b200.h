@@ -450,6 +450,26 @@ int rsdf_occ_update(float *occs, const float *snapshot, const long long *indices
 int rsdf_occ_threshold(const float *occs, long long n_cells, float occ_thre, uint8_t *binaries, uint32_t *bits,
                        float *partials, void *stream);
 
+/* NeuS alpha without autograd (visibility filter of `sampling`, eval): models/neus.py:128-150 ==
+ * models/split_mixed_occ.py:151-177 in one launch, in the torch chain's op order (no contraction).
+ * normals / dirs [n,3], sdf / dists [n], inv_s: device scalar (clipped to [1e-6, 1e6] inside). */
+int rsdf_neus_alpha(const float *sdf, const float *normals, const float *dirs, const float *dists, const float *inv_s,
+                    float cos_anneal_ratio, int n, float *alpha, void *stream);
+/* One round of the front-to-back visibility pass (lib/nerfacc/ray_marching.py:198-218 evaluated in rounds; see
+ * rise_sdf_b200/nerfacc.py::_alphas_front_to_back):
+ *   lens    : per ray, how many of its candidates [done, done + chunk) are evaluated this round (0 when the ray has
+ *             fewer than `done`, or trans[base + done] < early_stop_eps; trans may be NULL when done == 0)
+ *   fill    : with the inclusive prefix sum of lens, the round's candidate list in ray order: idx (row in the marched
+ *             arrays), gathered t_starts / t_ends and the ray index
+ *   scatter : alphas[idx[i]] = alphas_round[i], rows[idx[i]] = n_evaluated_before + i */
+int rsdf_vis_round_lens(const int32_t *packed_info, const float *trans, int done, int chunk, float early_stop_eps,
+                        int n_rays, long long n_samples, long long *lens, void *stream);
+int rsdf_vis_round_fill(const int32_t *packed_info, const long long *lens, const long long *lens_cumsum, int done,
+                        int n_rays, const float *t_starts, const float *t_ends, long long *idx, float *t_starts_sel,
+                        float *t_ends_sel, long long *ray_indices_sel, void *stream);
+int rsdf_vis_round_scatter(const long long *idx, const float *alphas_round, long long n_evaluated_before, long long total,
+                           float *alphas, long long *rows, void *stream);
+
 /* ---------------------------------------------------------------- optimizer */
 /* systems/utils.py:309-320 `parse_optimizer` -> torch.optim.Adam with per-group lr
  * (configs/neus-blender.yaml:92-104, configs/split-mixed-occ-tensoir.yaml:153-166): ONE launch over flat

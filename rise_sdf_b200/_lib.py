@@ -131,6 +131,10 @@ _SIGS = {
     "rsdf_occ_points": [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p, c_p],
     "rsdf_occ_update": [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_f, c_p],
     "rsdf_occ_threshold": [c_p, ctypes.c_longlong, c_f, c_p, c_p, c_p, c_p],
+    "rsdf_neus_alpha": [c_p, c_p, c_p, c_p, c_p, c_f, c_i, c_p, c_p],
+    "rsdf_vis_round_lens": [c_p, c_p, c_i, c_i, c_f, c_i, ctypes.c_longlong, c_p, c_p],
+    "rsdf_vis_round_fill": [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "rsdf_vis_round_scatter": [c_p, c_p, ctypes.c_longlong, ctypes.c_longlong, c_p, c_p, c_p],
     "rsdf_tc_gemm_test": [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 

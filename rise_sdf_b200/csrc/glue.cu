@@ -237,6 +237,78 @@ occ_threshold_kernel(const float *__restrict__ occs, long long n_cells, const fl
     if (bits) bits[w] = word;
 }
 
+// ---- NeuS alpha for the no-grad passes (visibility filter of `sampling`, eval) -------------------------------
+// models/neus.py:128-150 == models/split_mixed_occ.py:151-177 as ONE launch instead of ~20, in the op order of the
+// torch chain (no contraction: every product and sum rounded on its own, IEEE division, accurate expf), so that the
+// visibility masks are the ones the op-by-op path produces.
+__device__ __forceinline__ float sigmoid_rn(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+__global__ void neus_alpha_kernel(const float *__restrict__ sdf, const float *__restrict__ normals,
+                                  const float *__restrict__ dirs, const float *__restrict__ dists,
+                                  const float *__restrict__ inv_s_ptr, float ratio, float one_minus_ratio, int n,
+                                  float *__restrict__ alpha) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float inv_s = fminf(fmaxf(__ldg(inv_s_ptr), 1e-6f), 1e6f);
+    const float p0 = __fmul_rn(dirs[3 * (size_t)i], normals[3 * (size_t)i]);
+    const float p1 = __fmul_rn(dirs[3 * (size_t)i + 1], normals[3 * (size_t)i + 1]);
+    const float p2 = __fmul_rn(dirs[3 * (size_t)i + 2], normals[3 * (size_t)i + 2]);
+    const float c = __fadd_rn(__fadd_rn(p0, p1), p2);
+    const float t1 = fmaxf(__fadd_rn(__fmul_rn(-c, 0.5f), 0.5f), 0.0f);
+    const float t2 = fmaxf(-c, 0.0f);
+    const float iter_cos = -__fadd_rn(__fmul_rn(t1, one_minus_ratio), __fmul_rn(t2, ratio));
+    const float h = __fmul_rn(__fmul_rn(iter_cos, dists[i]), 0.5f);
+    const float s = sdf[i];
+    const float prev_cdf = sigmoid_rn(__fmul_rn(__fsub_rn(s, h), inv_s));
+    const float next_cdf = sigmoid_rn(__fmul_rn(__fadd_rn(s, h), inv_s));
+    const float a = __fdiv_rn(__fadd_rn(__fsub_rn(prev_cdf, next_cdf), 1e-5f), __fadd_rn(prev_cdf, 1e-5f));
+    alpha[i] = fminf(fmaxf(a, 0.0f), 1.0f);
+}
+
+// ---- front-to-back visibility rounds (nerfacc._alphas_front_to_back) -----------------------------------------
+// lens[r] = number of candidates of ray r evaluated in this round: the next `chunk` samples after the first `done`,
+// unless the ray has fewer, or its transmittance at sample `done` (T from the scan kernel) is already below eps.
+__global__ void vis_round_lens_kernel(const int32_t *__restrict__ packed, const float *__restrict__ T, int done,
+                                      int chunk, float eps, int n_rays, long long S0, long long *__restrict__ lens) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const int base = packed[2 * r], count = packed[2 * r + 1];
+    bool active = count > done;
+    if (active && done > 0 && T) {
+        long long j = (long long)base + done;
+        if (j > S0 - 1) j = S0 - 1;
+        active = T[j] >= eps;
+    }
+    lens[r] = active ? (long long)min(count - done, chunk) : 0;
+}
+// warp per ray: the round's candidates of ray r, packed in ray order at first[r] = csum[r] - lens[r]
+__global__ void vis_round_fill_kernel(const int32_t *__restrict__ packed, const long long *__restrict__ lens,
+                                      const long long *__restrict__ csum, int done, int n_rays,
+                                      const float *__restrict__ ts, const float *__restrict__ te,
+                                      long long *__restrict__ idx, float *__restrict__ ts_sel,
+                                      float *__restrict__ te_sel, long long *__restrict__ ri_sel) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n_rays) return;
+    const int len = (int)lens[r];
+    if (len == 0) return;
+    const long long first = csum[r] - len, src0 = (long long)packed[2 * r] + done;
+    for (int j = lane; j < len; j += 32) {
+        idx[first + j] = src0 + j;
+        ts_sel[first + j] = ts[src0 + j];
+        te_sel[first + j] = te[src0 + j];
+        ri_sel[first + j] = r;
+    }
+}
+__global__ void vis_round_scatter_kernel(const long long *__restrict__ idx, const float *__restrict__ a,
+                                         long long n_eval, long long total, float *__restrict__ alphas,
+                                         long long *__restrict__ rows) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long d = idx[i];
+    alphas[d] = a[i];
+    rows[d] = n_eval + i;
+}
+
 }  // namespace
 
 extern "C" {
@@ -352,6 +424,51 @@ int rsdf_occ_threshold(const float *occs, long long n_cells, float occ_thre, uin
     sum4_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p4 + 1, nb, p4);
     const long long words = (n_cells + 31) / 32;
     occ_threshold_kernel<<<rsdf_div_up(words, 256), 256, 0, (cudaStream_t)stream>>>(occs, n_cells, p4, occ_thre, binaries, bits);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_neus_alpha(const float *sdf, const float *normals, const float *dirs, const float *dists, const float *inv_s,
+                    float cos_anneal_ratio, int n, float *alpha, void *stream) {
+    if (n == 0) return 0;
+    if (!sdf || !normals || !dirs || !dists || !inv_s || !alpha) return RSDF_EBADARG;
+    // (1.0 - ratio) is a Python double in the reference, rounded to fp32 when it meets the tensor
+    const float omr = (float)(1.0 - (double)cos_anneal_ratio);
+    neus_alpha_kernel<<<rsdf_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(sdf, normals, dirs, dists, inv_s,
+                                                                             cos_anneal_ratio, omr, n, alpha);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_vis_round_lens(const int32_t *packed_info, const float *trans, int done, int chunk, float early_stop_eps,
+                        int n_rays, long long n_samples, long long *lens, void *stream) {
+    if (n_rays == 0) return 0;
+    if (!packed_info || !lens || chunk < 1 || done < 0) return RSDF_EBADARG;
+    vis_round_lens_kernel<<<rsdf_div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(packed_info, trans, done, chunk,
+                                                                                    early_stop_eps, n_rays, n_samples, lens);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_vis_round_fill(const int32_t *packed_info, const long long *lens, const long long *lens_cumsum, int done,
+                        int n_rays, const float *t_starts, const float *t_ends, long long *idx, float *t_starts_sel,
+                        float *t_ends_sel, long long *ray_indices_sel, void *stream) {
+    if (n_rays == 0) return 0;
+    if (!packed_info || !lens || !lens_cumsum || !t_starts || !t_ends || !idx || !t_starts_sel || !t_ends_sel ||
+        !ray_indices_sel)
+        return RSDF_EBADARG;
+    vis_round_fill_kernel<<<rsdf_div_up(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(
+        packed_info, lens, lens_cumsum, done, n_rays, t_starts, t_ends, idx, t_starts_sel, t_ends_sel, ray_indices_sel);
+    RSDF_LAUNCH_CHECK();
+    return 0;
+}
+
+int rsdf_vis_round_scatter(const long long *idx, const float *alphas_round, long long n_evaluated_before, long long total,
+                           float *alphas, long long *rows, void *stream) {
+    if (total == 0) return 0;
+    if (!idx || !alphas_round || !alphas || !rows) return RSDF_EBADARG;
+    vis_round_scatter_kernel<<<rsdf_div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(idx, alphas_round,
+                                                                                       n_evaluated_before, total, alphas, rows);
     RSDF_LAUNCH_CHECK();
     return 0;
 }

@@ -195,28 +195,35 @@ def _alphas_front_to_back(alpha_fn, packed, ri, ts, te, early_stop_eps):
     over the rounds (-1: never evaluated)."""
     S0, dev = ts.shape[0], ts.device
     n_rays = packed.shape[0]
-    base, count = packed[:, 0].long(), packed[:, 1].long()
+    packed = packed.contiguous()
+    ts_flat, te_flat = ts.reshape(-1).contiguous(), te.reshape(-1).contiguous()
     alphas = torch.zeros(S0, 1, device=dev, dtype=torch.float32)
     rows = torch.full((S0,), -1, device=dev, dtype=torch.int64)
-    ray_ids = torch.arange(n_rays, device=dev)
-    max_count = int(count.max())
+    lens = torch.empty(n_rays, device=dev, dtype=torch.int64)
+    max_count = int(packed[:, 1].max())
     done = n_eval = k = 0
+    st = L.stream()
     while done < max_count:
         chunk = VISIBILITY_CHUNKS[k] if k < len(VISIBILITY_CHUNKS) else max_count
-        active = count > done
-        if done > 0:
-            active &= _transmittance(packed, alphas)[(base + done).clamp(max=S0 - 1)] >= early_stop_eps
-        lens = torch.where(active, (count - done).clamp(max=chunk), torch.zeros_like(count))
-        total = int(lens.sum())
+        # csrc/glue.cu: who is still alive (1 launch), prefix sum, the round's candidate list with its gathered
+        # t-values and ray indices (1 launch), and after alpha_fn the scatter of its results (1 launch) -- instead of
+        # ~25 torch launches per round on the critical path right after the round's read-back
+        T = _transmittance(packed, alphas) if done > 0 else None
+        L.call("rsdf_vis_round_lens", L.ptr(packed), L.ptr(T), done, min(chunk, 2 ** 30), float(early_stop_eps), n_rays, S0,
+               L.ptr(lens), st)
+        csum = torch.cumsum(lens, 0)
+        total = int(csum[-1])
         if total == 0:
             break
-        first = torch.cumsum(lens, 0) - lens
-        ray_of = torch.repeat_interleave(ray_ids, lens, output_size=total)
-        idx = (base + done)[ray_of] + (torch.arange(total, device=dev) - first[ray_of])
-        a = alpha_fn(ts[idx], te[idx], ri[idx])
+        idx = torch.empty(total, device=dev, dtype=torch.int64)
+        ts_sel = torch.empty(total, 1, device=dev, dtype=torch.float32)
+        te_sel = torch.empty(total, 1, device=dev, dtype=torch.float32)
+        ri_sel = torch.empty(total, device=dev, dtype=torch.int64)
+        L.call("rsdf_vis_round_fill", L.ptr(packed), L.ptr(lens), L.ptr(csum), done, n_rays, L.ptr(ts_flat), L.ptr(te_flat),
+               L.ptr(idx), L.ptr(ts_sel), L.ptr(te_sel), L.ptr(ri_sel), st)
+        a = alpha_fn(ts_sel, te_sel, ri_sel)
         assert a.shape == (total, 1), f"alphas must have shape of (N, 1)! Got {a.shape}"
-        alphas[idx] = a.float()
-        rows[idx] = torch.arange(n_eval, n_eval + total, device=dev)
+        L.call("rsdf_vis_round_scatter", L.ptr(idx), L.ptr(a.float().contiguous()), n_eval, total, L.ptr(alphas), L.ptr(rows), st)
         n_eval += total
         done += chunk
         k += 1

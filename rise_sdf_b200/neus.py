@@ -126,6 +126,18 @@ class _NeusRender(torch.autograd.Function):
 
 
 @torch.no_grad()
+def neus_alpha(sdf, normal, dirs, dists, inv_s, cos_anneal_ratio):
+    """get_alpha (models/neus.py:128-150 == models/split_mixed_occ.py:151-177) without autograd, one launch; same op
+    order as the torch chain (tests/test_gpu_glue.py compares them)."""
+    n = sdf.shape[0]
+    alpha = torch.empty(n, device=sdf.device, dtype=torch.float32)
+    L.call("rsdf_neus_alpha", L.ptr(sdf.reshape(-1).contiguous().float()), L.ptr(normal.contiguous().float()),
+           L.ptr(dirs.contiguous().float()), L.ptr(dists.reshape(-1).contiguous().float()),
+           L.ptr(inv_s.detach().reshape(1).contiguous().float()), float(cos_anneal_ratio), n, L.ptr(alpha), L.stream())
+    return alpha
+
+
+@torch.no_grad()
 def sample_setup(rays_o, rays_d, ray_indices, t_starts, t_ends):
     """models/neus.py:247-252 in one launch -> (positions [S,3], t_dirs [S,3], midpoints [S,1], dists [S])."""
     S = ray_indices.shape[0]
@@ -214,6 +226,8 @@ class NeuSModel(nn.Module):
     # ------------------------------------------------------------------ alpha (un-fused path)
     def get_alpha(self, sdf, normal, dirs, dists):
         """models/neus.py:128-150."""
+        if sdf.is_cuda and not torch.is_grad_enabled() and sdf.shape[0] > 0:
+            return neus_alpha(sdf, normal, dirs, dists, self.variance.inv_s, self.cos_anneal_ratio)
         inv_s = self.variance(torch.zeros([1, 3]))[:, :1].clip(1e-6, 1e6)
         inv_s = inv_s.expand(sdf.shape[0], 1)
         true_cos = (dirs * normal).sum(-1, keepdim=True)

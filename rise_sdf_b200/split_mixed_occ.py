@@ -14,7 +14,7 @@ from .geometry import VolumeSDF
 from .light import EnvironmentLightMipCube, rgb_to_srgb
 from .nerfacc import ContractionType, OccGridEstimator, accumulate_along_rays, pack_info
 from .network_utils import Config, update_module_step
-from .neus import VarianceNetwork, chunk_batch, normalize3
+from .neus import VarianceNetwork, chunk_batch, neus_alpha, normalize3, sample_setup
 from .split_shade import split_render
 from .texture import VolumeMixedMipSplitOcc
 from .volrend import rendering_with_normals_sdf, secondary_rendering
@@ -103,6 +103,8 @@ class SplitMixedOCCModel(nn.Module):
 
     def get_alpha(self, sdf, normal, dirs, dists):
         """models/split_mixed_occ.py:151-177 (identical to models/neus.py:128-150)."""
+        if sdf.is_cuda and not torch.is_grad_enabled() and sdf.shape[0] > 0:
+            return neus_alpha(sdf, normal, dirs, dists, self.variance.inv_s, self.cos_anneal_ratio)
         inv_s = self.variance(torch.zeros([1, 3]))[:, :1].clip(1e-6, 1e6)
         inv_s = inv_s.expand(sdf.shape[0], 1)
         true_cos = (dirs * normal).sum(-1, keepdim=True)
@@ -140,18 +142,22 @@ class SplitMixedOCCModel(nn.Module):
         (:228-240 / compute_indirect_radiance :183-191), which for a no-grad pass recomputes exactly the same
         numbers -- the caller gathers them by the rows `sampling(..., _return_mask=True)` reports instead."""
         def alpha_fn(t_starts, t_ends, ray_indices):
-            t_origins = rays_o[ray_indices]
-            t_dirs = rays_d[ray_indices]
-            positions = t_origins + t_dirs * (t_starts + t_ends)[..., None] / 2.0
-            if t_origins.shape[0] == 0:
-                return torch.zeros((0,), device=t_origins.device)
+            if ray_indices.shape[0] == 0:
+                return torch.zeros((0,), device=rays_o.device)
+            if rays_o.is_cuda and not torch.is_grad_enabled():
+                # one launch: gathered directions, positions (same op order as below), interval lengths
+                positions, t_dirs, _, dists = sample_setup(rays_o, rays_d, ray_indices, t_starts, t_ends)
+            else:
+                t_origins = rays_o[ray_indices]
+                t_dirs = rays_d[ray_indices]
+                positions = t_origins + t_dirs * (t_starts + t_ends)[..., None] / 2.0
+                dists = (t_ends - t_starts)[..., None]
             feature = None
             if keep is not None and with_feature:
                 sdf, sdf_grad, feature = self.geometry(positions, with_grad=True, with_feature=True)
             else:
                 sdf, sdf_grad = self.geometry(positions, with_grad=True, with_feature=False)
             normal = normalize3(sdf_grad, eps=1e-6)
-            dists = (t_ends - t_starts)[..., None]
             alphas = self.get_alpha(sdf, normal, t_dirs, dists)
             if keep is not None:
                 keep.append(dict(sdf=sdf, sdf_grad=sdf_grad, normal=normal, alphas=alphas, feature=feature))

