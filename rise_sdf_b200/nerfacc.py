@@ -163,12 +163,14 @@ def ray_marching(rays_o: Tensor, rays_d: Tensor, t_min: Optional[Tensor] = None,
             assert alphas.shape == ts.shape, f"alphas must have shape of (N, 1)! Got {alphas.shape}"
         masks = render_visibility(alphas, packed_info=packed, early_stop_eps=early_stop_eps,
                                   alpha_thre=alpha_thre)
-        ri, ts, te = ri[masks], ts[masks], te[masks]
+        # ONE compaction (one host read-back) shared by the four gathers: `x[bool_mask]` runs nonzero + a sync each time
+        keep_idx = torch.nonzero(masks.reshape(-1))[:, 0]
+        ri, ts, te = ri[keep_idx], ts[keep_idx], te[keep_idx]
         packed = None
     rv = (ri, ts, te) + ((packed,) if _return_packed else ())
     if _return_mask:
         # row of every surviving sample in the concatenation of alpha_fn's outputs over its calls
-        rv += (None if masks is None else (rows[masks] if rows is not None else torch.nonzero(masks)[:, 0]),)
+        rv += (None if masks is None else (rows[keep_idx] if rows is not None else keep_idx),)
     return rv
 
 

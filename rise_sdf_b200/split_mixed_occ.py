@@ -285,7 +285,10 @@ class SplitMixedOCCModel(nn.Module):
                 if not relighting:
                     spec_rgb_pbr_map[valid_indices] = tr * spec_rgb_pbr_map[valid_indices] + (1 - tr) * secondary_rgb
                 else:
-                    roughness_mask = (roughness_map[valid_indices] <= self.config.relighting_threshold)[..., 0]
+                    # (integer rows computed once -- roughness does not depend on the env map -- instead of seven
+                    # boolean-mask gathers, each of which is a nonzero + host read-back)
+                    roughness_mask = self._memo("rough_rows", lambda: torch.nonzero(
+                        (roughness_map[valid_indices] <= self.config.relighting_threshold)[..., 0])[:, 0])
                     third_rays_o = secondary_rays_o[roughness_mask] + secondary_depth[roughness_mask] * secondary_rays_d[roughness_mask]
                     third_dirs = secondary_rays_d[roughness_mask]
 
