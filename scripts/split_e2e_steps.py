@@ -27,14 +27,25 @@ model.render_step_size = rs
 for i in range(5):
     trainer.step(*batches[i % 2])
 torch.cuda.synchronize()
-for rep in range(3):
-    ts = []
+for rep in range(4):
+    sync = rep % 2 == 0
+    ts, evs = [], [torch.cuda.Event(enable_timing=True) for _ in range(17)]
+    torch.cuda.synchronize()
+    evs[0].record()
     for i in range(16):
-        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        b = tuple(t.to(dev, non_blocking=True) for t in host[i % 2])
+        if sync:
+            b = tuple(t.to(dev, non_blocking=True) for t in host[i % 2])
+        else:
+            b = batches[i % 2]
         loss, out = trainer.step(*b)
-        float(loss.item())
+        if sync:
+            float(loss.item())
+        evs[i + 1].record()
         ts.append((time.perf_counter() - t0) * 1e3)
-    print(" ".join(f"{t:6.1f}" for t in ts), " step", trainer.global_step, " reserved GB", torch.cuda.memory_reserved() / 2**30,
-          "mallocs", torch.cuda.memory_stats()["num_device_alloc"])
+    torch.cuda.synchronize()
+    dev_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(16)]
+    print("sync " if sync else "async", "host:", " ".join(f"{t:5.0f}" for t in ts))
+    print("      ", "dev: ", " ".join(f"{t:5.0f}" for t in dev_ms), " step", trainer.global_step, " reserved GB",
+          round(torch.cuda.memory_reserved() / 2**30, 1), "segments", torch.cuda.memory_stats()["num_device_alloc"],
+          "samples", int(out["num_samples"].sum()))
