@@ -40,10 +40,21 @@ def my_pixels(n_rays, rank, world):
     return slice(rank, n_rays, world)
 
 
-def balanced_tile(n_rays, world, max_tile=32768, per_rank=1):
+# rays per forward_ call.  Every tile pays a fixed ~4 ms of host read-backs and launch latency (16 syncs, ~400 launches),
+# so fewer, larger tiles are faster: 32768 -> 4.45, 65536 -> 5.0, 131072 -> 5.2-5.3 frames/s at 1 GPU; 65536 keeps the
+# march's interval scratch under its 1 GiB budget and the per-round element counts where they have been tested.
+# NOTE (reference quirk, models/split_mixed_occ.py:306-332): when relighting, `spec_rgb_phys = spec_ref_map *
+# spec_light_map` is applied to EVERY ray of a batch that contains at least one ray with opacity > 0.5, and to none of a
+# batch without one -- so silhouette rays (0 < opacity <= 0.5) depend on what else is in their batch (the reference's
+# batches are 4096-ray chunks).  With tiles this large every tile that sees the object takes the first branch.
+MAX_TILE = 65536
+
+
+def balanced_tile(n_rays, world, max_tile=None, per_rank=1):
     """Tile size for a rank's shard of ceil(n_rays / world) rays: the fewest tiles of at most max_tile rays (every
     tile pays ~25 host read-backs; interleaved pixels already balance the ranks), all (almost) equal, a multiple of
-    64: 640 000 rays -> 20 tiles of 32 000 on 1 GPU, 3 tiles of 26 688 for the 80 000-ray shard of 8 GPUs."""
+    64: 640 000 rays -> 10 tiles of 64 000 on 1 GPU, 2 tiles of 40 000 for the 80 000-ray shard of 8 GPUs."""
+    max_tile = max_tile or MAX_TILE
     n = -(-n_rays // world)
     t = min(max_tile, -(-n // per_rank))
     t = -(-t // 64) * 64

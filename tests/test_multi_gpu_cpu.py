@@ -61,11 +61,11 @@ def test_flat_bucket_allreduce_and_tile_sharding():
 
 
 def test_balanced_tile_counts():
-    from rise_sdf_b200.relight import balanced_tile, my_pixels, my_tiles
+    from rise_sdf_b200.relight import MAX_TILE, balanced_tile, my_pixels, my_tiles
     for world in (1, 2, 3, 4, 8):
         t = balanced_tile(640000, world)
         shard = [len(range(640000)[my_pixels(640000, r, world)]) for r in range(world)]
         counts = [len(my_tiles(n, t, 0, 1)) for n in shard]
         assert sum(shard) == 640000 and max(shard) - min(shard) <= 1
-        assert t % 64 == 0 and t <= 32768 and len(set(counts)) == 1 and counts[0] * t >= max(shard)
-        assert (counts[0] - 1) * 32768 < max(shard)                       # no more tiles than the cap requires
+        assert t % 64 == 0 and t <= MAX_TILE and len(set(counts)) == 1 and counts[0] * t >= max(shard)
+        assert (counts[0] - 1) * MAX_TILE < max(shard)                       # no more tiles than the cap requires
