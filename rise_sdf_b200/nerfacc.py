@@ -184,6 +184,46 @@ def _transmittance(packed, alphas):
     return T
 
 
+def _round_plan_kernels(packed, T, done, chunk, eps, ts_flat, te_flat):
+    """One visibility round on the device (csrc/glue.cu): who is still alive (1 launch), prefix sum, the round's candidate
+    list with its gathered t-values and ray indices (1 launch) -- instead of the ~25 torch launches of
+    `_round_plan_torch`, which sit on the critical path right after the round's read-back.
+    -> (idx int64[total], t_starts[total,1], t_ends[total,1], ray_indices int64[total]) or None when nothing is left."""
+    n_rays, S0, dev, st = packed.shape[0], ts_flat.shape[0], packed.device, L.stream()
+    lens = torch.empty(n_rays, device=dev, dtype=torch.int64)
+    L.call("rsdf_vis_round_lens", L.ptr(packed), L.ptr(T), done, min(chunk, 2 ** 30), float(eps), n_rays, S0, L.ptr(lens), st)
+    csum = torch.cumsum(lens, 0)
+    total = int(csum[-1])
+    if total == 0:
+        return None
+    idx = torch.empty(total, device=dev, dtype=torch.int64)
+    ts_sel = torch.empty(total, 1, device=dev, dtype=torch.float32)
+    te_sel = torch.empty(total, 1, device=dev, dtype=torch.float32)
+    ri_sel = torch.empty(total, device=dev, dtype=torch.int64)
+    L.call("rsdf_vis_round_fill", L.ptr(packed), L.ptr(lens), L.ptr(csum), done, n_rays, L.ptr(ts_flat), L.ptr(te_flat),
+           L.ptr(idx), L.ptr(ts_sel), L.ptr(te_sel), L.ptr(ri_sel), st)
+    return idx, ts_sel, te_sel, ri_sel
+
+
+def _round_plan_torch(packed, T, done, chunk, eps, ts_flat, te_flat):
+    """The same bookkeeping as index arithmetic: the executable specification of the two kernels above
+    (tests/test_host_logic.py pins it on the CPU, tests/test_gpu_glue.py compares the kernels with it).  `sampling`
+    itself only accepts CUDA rays."""
+    n_rays, S0, dev = packed.shape[0], ts_flat.shape[0], packed.device
+    base, count = packed[:, 0].long(), packed[:, 1].long()
+    active = count > done
+    if done > 0:
+        active &= T[(base + done).clamp(max=S0 - 1)] >= eps
+    lens = torch.where(active, (count - done).clamp(max=chunk), torch.zeros_like(count))
+    total = int(lens.sum())
+    if total == 0:
+        return None
+    first = torch.cumsum(lens, 0) - lens
+    ray_of = torch.repeat_interleave(torch.arange(n_rays, device=dev), lens, output_size=total)
+    idx = (base + done)[ray_of] + (torch.arange(total, device=dev) - first[ray_of])
+    return idx, ts_flat[idx][:, None], te_flat[idx][:, None], ray_of
+
+
 def _alphas_front_to_back(alpha_fn, packed, ri, ts, te, early_stop_eps):
     """The visibility pass of lib/nerfacc/ray_marching.py:198-218 evaluates `alpha_fn` on every marched candidate
     and then masks the ones behind `T < early_stop_eps`.  A sample's transmittance depends only on the samples in
@@ -201,31 +241,25 @@ def _alphas_front_to_back(alpha_fn, packed, ri, ts, te, early_stop_eps):
     ts_flat, te_flat = ts.reshape(-1).contiguous(), te.reshape(-1).contiguous()
     alphas = torch.zeros(S0, 1, device=dev, dtype=torch.float32)
     rows = torch.full((S0,), -1, device=dev, dtype=torch.int64)
-    lens = torch.empty(n_rays, device=dev, dtype=torch.int64)
     max_count = int(packed[:, 1].max())
     done = n_eval = k = 0
-    st = L.stream()
     while done < max_count:
         chunk = VISIBILITY_CHUNKS[k] if k < len(VISIBILITY_CHUNKS) else max_count
-        # csrc/glue.cu: who is still alive (1 launch), prefix sum, the round's candidate list with its gathered
-        # t-values and ray indices (1 launch), and after alpha_fn the scatter of its results (1 launch) -- instead of
-        # ~25 torch launches per round on the critical path right after the round's read-back
         T = _transmittance(packed, alphas) if done > 0 else None
-        L.call("rsdf_vis_round_lens", L.ptr(packed), L.ptr(T), done, min(chunk, 2 ** 30), float(early_stop_eps), n_rays, S0,
-               L.ptr(lens), st)
-        csum = torch.cumsum(lens, 0)
-        total = int(csum[-1])
-        if total == 0:
+        plan = (_round_plan_kernels if packed.is_cuda else _round_plan_torch)(packed, T, done, chunk, early_stop_eps,
+                                                                             ts_flat, te_flat)
+        if plan is None:
             break
-        idx = torch.empty(total, device=dev, dtype=torch.int64)
-        ts_sel = torch.empty(total, 1, device=dev, dtype=torch.float32)
-        te_sel = torch.empty(total, 1, device=dev, dtype=torch.float32)
-        ri_sel = torch.empty(total, device=dev, dtype=torch.int64)
-        L.call("rsdf_vis_round_fill", L.ptr(packed), L.ptr(lens), L.ptr(csum), done, n_rays, L.ptr(ts_flat), L.ptr(te_flat),
-               L.ptr(idx), L.ptr(ts_sel), L.ptr(te_sel), L.ptr(ri_sel), st)
+        idx, ts_sel, te_sel, ri_sel = plan
+        total = idx.shape[0]
         a = alpha_fn(ts_sel, te_sel, ri_sel)
         assert a.shape == (total, 1), f"alphas must have shape of (N, 1)! Got {a.shape}"
-        L.call("rsdf_vis_round_scatter", L.ptr(idx), L.ptr(a.float().contiguous()), n_eval, total, L.ptr(alphas), L.ptr(rows), st)
+        if packed.is_cuda:
+            L.call("rsdf_vis_round_scatter", L.ptr(idx), L.ptr(a.float().contiguous()), n_eval, total, L.ptr(alphas),
+                   L.ptr(rows), L.stream())
+        else:
+            alphas[idx] = a.float()
+            rows[idx] = torch.arange(n_eval, n_eval + total, device=dev)
         n_eval += total
         done += chunk
         k += 1
