@@ -256,10 +256,10 @@ def run_relight(args, dev, world, rank, variance, n_frames=2):
     frames = [r.to(dev) for r in host_rays]
     n_env = len(envs.maps)
     host_frames = [[torch.zeros(640000, 3).pin_memory() for _ in range(n_env)] for _ in range(n_frames)]
-    # warm-up: one full frame of another pose at a 10 % finer march, so that the caching allocator already holds
+    # warm-up: one full frame of another pose at a 25 % finer march, so that the caching allocator already holds
     # blocks for every tile size of the timed frames (a first-time size is a cudaMalloc in the timed region)
     rs = model.render_step_size
-    model.render_step_size = rs / 1.1
+    model.render_step_size = rs / 1.25
     render_frame_shard(model, syn.frame_rays(50, poses, dirs).to(dev), envs, rank, world)
     model.render_step_size = rs
 
