@@ -57,7 +57,7 @@ def pack_bits(grid_binary: Tensor) -> Tensor:
     return bits
 
 
-KEEP_BUDGET_BYTES = 1 << 30      # scratch of the one-march path: n_rays * cap * 8 bytes
+KEEP_BUDGET_BYTES = 2 << 30      # scratch of the one-march path: n_rays * cap * 8 bytes (131 072 rays x 1026 slots: 1.08 GB)
 
 
 @torch.no_grad()

@@ -41,25 +41,28 @@ def my_pixels(n_rays, rank, world):
 
 
 # rays per forward_ call.  Every tile pays a fixed ~4 ms of host read-backs and launch latency (16 syncs, ~400 launches),
-# so fewer, larger tiles are faster: 32768 -> 4.45, 65536 -> 5.0, 131072 -> 5.2-5.3 frames/s at 1 GPU; 65536 keeps the
-# march's interval scratch under its 1 GiB budget and the per-round element counts where they have been tested.
-# NOTE (reference quirk, models/split_mixed_occ.py:306-332): when relighting, `spec_rgb_phys = spec_ref_map *
-# spec_light_map` is applied to EVERY ray of a batch that contains at least one ray with opacity > 0.5, and to none of a
-# batch without one -- so silhouette rays (0 < opacity <= 0.5) depend on what else is in their batch (the reference's
-# batches are 4096-ray chunks).  With tiles this large every tile that sees the object takes the first branch.
-MAX_TILE = 65536
+# so fewer, larger tiles are faster: 32768 -> 4.45, 65536 -> 5.0, 131072 -> 5.2-5.3 frames/s at 1 GPU, and the 80 000-ray
+# shard of an 8-GPU run is one tile.  (Geometry is bit-identical across tile sizes; the largest evaluation batch at the
+# config's initial variance, 28 M samples = 5.4 G feature elements, is beyond int32 element counts: offsets are 64-bit.)
+# Tiles are multiples of the reference's 4096-ray chunk: its relighting recombination is decided per chunk
+# (split_mixed_occ.py, "recombined"), and a tile boundary inside a chunk would change that decision.
+MAX_TILE = 131072
+REF_CHUNK = 4096
 
 
 def balanced_tile(n_rays, world, max_tile=None, per_rank=1):
     """Tile size for a rank's shard of ceil(n_rays / world) rays: the fewest tiles of at most max_tile rays (every
-    tile pays ~25 host read-backs; interleaved pixels already balance the ranks), all (almost) equal, a multiple of
-    64: 640 000 rays -> 10 tiles of 64 000 on 1 GPU, 2 tiles of 40 000 for the 80 000-ray shard of 8 GPUs."""
+    tile pays ~16 host read-backs; interleaved pixels already balance the ranks), all (almost) equal, whole reference
+    chunks of 4096 rays: 640 000 rays -> 5 tiles of 131 072 on 1 GPU, one 81 920-ray tile for the 80 000-ray shard of 8
+    GPUs."""
     max_tile = max_tile or MAX_TILE
     n = -(-n_rays // world)
     t = min(max_tile, -(-n // per_rank))
     t = -(-t // 64) * 64
     k = -(-n // t)
-    return -(-(-(-n // k)) // 64) * 64
+    t = -(-(-(-n // k)) // 64) * 64
+    up = -(-t // REF_CHUNK) * REF_CHUNK          # whole reference chunks, if that does not add a tile's worth of rays
+    return up if up <= max_tile else t
 
 
 @torch.no_grad()

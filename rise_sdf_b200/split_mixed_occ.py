@@ -305,7 +305,20 @@ class SplitMixedOCCModel(nn.Module):
                     slv = spec_light_map[valid_indices]
                     slv[roughness_mask] = tr[roughness_mask] * slv[roughness_mask] + (1 - tr[roughness_mask]) * third_rgb
                     spec_light_map[valid_indices] = slv
-                    spec_rgb_pbr_map = spec_ref_map * spec_light_map
+                    # models/split_mixed_occ.py:332 recombines EVERY ray of the batch -- and a batch without a single
+                    # valid ray never gets here.  The reference's batches are `ray_chunk`-ray chunks (models/utils.py:
+                    # 14-51), so for a larger batch the rule is applied per reference chunk: a ray is recombined iff
+                    # ITS 4096-ray chunk holds a ray with opacity > 0.5 (batches start on a chunk boundary: relight.py).
+                    recombined = spec_ref_map * spec_light_map
+                    rc = int(self.config.get("ray_chunk", 0) or 0)
+                    if rc and n_rays > rc and not self.training:
+                        n_chunks = -(-n_rays // rc)
+                        flags = torch.zeros(n_chunks * rc, dtype=torch.bool, device=rays.device)
+                        flags[valid_indices] = True
+                        in_live_chunk = flags.view(n_chunks, rc).any(1).repeat_interleave(rc)[:n_rays]
+                        spec_rgb_pbr_map = torch.where(in_live_chunk[:, None], recombined, spec_rgb_pbr_map)
+                    else:
+                        spec_rgb_pbr_map = recombined
 
         rgb_full = diff_rgb_map + spec_rgb_map
         out = {

@@ -334,3 +334,41 @@ def test_relighting_reuse_is_bit_identical(monkeypatch):
         outs.append(m(rays[:200]))
     for k in ("comp_rgb_full", "comp_rgb_phys_full", "opacity"):
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_relighting_recombination_follows_the_reference_chunks():
+    """models/split_mixed_occ.py:332 sets spec_rgb_phys = spec_ref_map * spec_light_map for EVERY ray of a batch that
+    holds a valid ray (opacity > 0.5) and leaves a batch without one alone; the reference's batches are its `ray_chunk`
+    chunks (models/utils.py:14-51).  A large tile must reproduce the chunked render bit for bit -- including the
+    silhouette rays of chunks that never see a valid ray."""
+    from rise_sdf_b200 import synthetic as syn
+    from rise_sdf_b200.neus import chunk_batch
+    from rise_sdf_b200.relight import EnvSet
+    m = _split_model().eval()
+    with torch.no_grad():
+        m.variance.variance.fill_(0.3)                     # a soft surface: plenty of rays with 0 < opacity <= 0.5
+    m.update_step(0, 20000)
+    m.background_color = torch.ones(3, device="cuda")
+    m.occupancy_grid.binaries = syn.analytic_grid("ball")[None].cuda()
+    m.render_step_size = 1.732 * 2 * 1.5 / 128
+    envs = EnvSet(m, [torch.rand(32, 64, 3, generator=torch.Generator().manual_seed(5)) * 2.0])
+    envs.use(0)
+    # a 24-pixel-wide vertical strip of a frame, row-major: chunks of 4 rows walk across the silhouette
+    frame = syn.frame_rays(3, syn.camera_poses(), syn.ray_directions()).view(800, 800, 6)
+    rays = frame[::4, 388:412].reshape(-1, 6).contiguous().cuda()
+    rc = 96
+    m.config["ray_chunk"] = rc
+    with torch.no_grad():
+        chunked = chunk_batch(m.forward_, rc, False, rays, True)           # the reference's order
+        whole = m.forward_(rays, relighting=True)
+    op = chunked["opacity"][:, 0]
+    per_chunk_valid = torch.nn.functional.pad(op > 0.5, (0, -len(op) % rc)).view(-1, rc).any(1)
+    lonely = (~per_chunk_valid.repeat_interleave(rc)[:len(op)]) & (op > 0)
+    assert int(lonely.sum()) > 0, "the strip must contain silhouette rays in a chunk without a valid ray"
+    for k in ("comp_rgb_phys", "comp_spec_rgb_phys", "comp_rgb_phys_full", "comp_rgb", "opacity", "depth"):
+        assert torch.equal(chunked[k], whole[k]), k
+    # and the rule matters: recombining those rays as well gives different pixels
+    m.config["ray_chunk"] = 1 << 30
+    with torch.no_grad():
+        naive = m.forward_(rays, relighting=True)
+    assert not torch.equal(naive["comp_spec_rgb_phys"][lonely], whole["comp_spec_rgb_phys"][lonely])
