@@ -119,7 +119,11 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fwd_kernel(const __grid_consta
 
     auto issue_w = [&](int job) {     // thread 0 only
         const MlpLayerDesc &L = p.layer[job % p.n_layers];
+#ifdef RSDF_EXP_NO_WLOAD             // developer experiment: only the first blobs are ever copied
+        const uint32_t bytes = job < 2 ? 4u * (uint32_t)L.n_pad * (uint32_t)L.k_pad : 16u;
+#else
         const uint32_t bytes = 4u * (uint32_t)L.n_pad * (uint32_t)L.k_pad;
+#endif
         tc::mbar_expect_tx(&sm->bar_w[job & 1], bytes);
         tc::bulk_g2s(w_img[job & 1], L.blob, bytes, &sm->bar_w[job & 1]);
     };
@@ -133,26 +137,59 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fwd_kernel(const __grid_consta
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int s = tile * TM + row;
         const bool row_ok = s < p.S;
-        // ---- stage the input row: the two threads of a row split the 16-byte chunks ------------
+        // ---- stage the input tile ---------------------------------------------------------------------------
+        // A thread owns one sample ROW of the operand image, but a row-per-lane read of row-major inputs is 32
+        // different 128-byte lines per load.  The tile's rows are one contiguous block per input segment, so the CTA
+        // copies them with fully coalesced loads into an fp32 scratch -- the weight-ring slot that is idle until the
+        // first layer's MMAs are committed (its last reader, the previous job, has drained) -- and the rows are split
+        // into the image from there (row stride padded by 4 floats: conflict-free 16-byte reads).
         {
             const uint32_t plane = TM * k_pad0 * 2;
-            const float *r0 = p.in[0] + (size_t)s * w0;
-            const float *r1 = p.n_in > 1 ? p.in[1] + (size_t)s * w1 : nullptr;
-            const float *r2 = p.n_in > 2 ? p.in[2] + (size_t)s * w2 : nullptr;
-            for (int c = part; c < k_pad0 / 8; c += PARTS) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = c * 8 + j;
-                    float x = 0.0f;
-                    if (row_ok) {
-                        if (k < w0) x = fmaf(__ldg(r0 + k), p.in_scale[0], p.in_shift[0]);
-                        else if (k < w0 + w1) x = fmaf(__ldg(r1 + (k - w0)), p.in_scale[1], p.in_shift[1]);
-                        else if (k < w0 + w1 + w2) x = fmaf(__ldg(r2 + (k - w0 - w1)), p.in_scale[2], p.in_shift[2]);
+            const int ld = k_pad0 + 4;
+            if (k_pad0 <= 112) {
+                float *scr = reinterpret_cast<float *>(w_img[(job + 1) & 1]);
+                const int rows = min(TM, p.S - tile * TM);
+                int off = 0;
+                for (int g = 0; g < p.n_in; ++g) {
+                    const int w = p.in_w[g];
+                    const float *src = p.in[g] + (size_t)tile * TM * w;
+                    const float sc = p.in_scale[g], sh = p.in_shift[g];
+                    for (int i = tid; i < rows * w; i += THREADS) {
+                        const int r = i / w, c = i - r * w;
+                        scr[r * ld + off + c] = fmaf(__ldg(src + i), sc, sh);
                     }
-                    v[j] = x;
+                    off += w;
                 }
-                tc::store_chunk(a_img, plane, TM, row, c, v);
+                // zero padding: columns [kin, k_pad0) of every row, and the rows past the end of the batch
+                const int padw = k_pad0 - off;
+                for (int i = tid; i < TM * padw; i += THREADS) scr[(i / padw) * ld + off + i % padw] = 0.0f;
+                for (int i = tid; i < (TM - rows) * off; i += THREADS) scr[(rows + i / off) * ld + i % off] = 0.0f;
+                __syncthreads();
+                for (int c = part; c < k_pad0 / 8; c += PARTS) {
+                    const float4 a = *reinterpret_cast<const float4 *>(scr + row * ld + 8 * c);
+                    const float4 b = *reinterpret_cast<const float4 *>(scr + row * ld + 8 * c + 4);
+                    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    tc::store_chunk(a_img, plane, TM, row, c, v);
+                }
+            } else {
+                const float *r0 = p.in[0] + (size_t)s * w0;
+                const float *r1 = p.n_in > 1 ? p.in[1] + (size_t)s * w1 : nullptr;
+                const float *r2 = p.n_in > 2 ? p.in[2] + (size_t)s * w2 : nullptr;
+                for (int c = part; c < k_pad0 / 8; c += PARTS) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = c * 8 + j;
+                        float x = 0.0f;
+                        if (row_ok) {
+                            if (k < w0) x = fmaf(__ldg(r0 + k), p.in_scale[0], p.in_shift[0]);
+                            else if (k < w0 + w1) x = fmaf(__ldg(r1 + (k - w0)), p.in_scale[1], p.in_shift[1]);
+                            else if (k < w0 + w1 + w2) x = fmaf(__ldg(r2 + (k - w0 - w1)), p.in_scale[2], p.in_shift[2]);
+                        }
+                        v[j] = x;
+                    }
+                    tc::store_chunk(a_img, plane, TM, row, c, v);
+                }
             }
         }
         for (int l = 0; l < p.n_layers; ++l, ++job) {
@@ -164,9 +201,11 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fwd_kernel(const __grid_consta
                 if (job & 1) w_phase1 ^= 1; else w_phase0 ^= 1;
                 tc::tc_fence_after();
                 const uint32_t idesc = tc::instr_desc(128, n_pad, false, false);
+#ifndef RSDF_EXP_NO_MMA
                 tc::gemm_split3(tmem, tc::op_kmajor(tc::smem_u32(a_img), TM * k_pad * 2, TM),
                                 tc::op_kmajor(tc::smem_u32(w_img[job & 1]), (uint32_t)n_pad * k_pad * 2, n_pad),
                                 k_pad / 16, idesc, false, /*keep_lo_lo=*/false);
+#endif
                 tc::mma_commit(&sm->bar_mma);
                 if (job + 1 < total_jobs) issue_w(job + 1);   // other ring slot: its last reader has drained
             }
@@ -178,6 +217,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fwd_kernel(const __grid_consta
             const int n_chunks = n_pad / 16, per = (n_chunks + PARTS - 1) / PARTS;
             const int c_begin = min(part * per, n_chunks), c_end = min(c_begin + per, n_chunks);
             const float *bias = sm->bias[l];
+#ifdef RSDF_EXP_NO_EPI
+            if (!last) {
+            } else
+#endif
             if (!last) {
                 const uint32_t next_plane = TM * n_pad * 2;
                 for (int c = c_begin; c < c_end; ++c)

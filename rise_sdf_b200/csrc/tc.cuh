@@ -247,15 +247,19 @@ __device__ __forceinline__ void gemm_split3(uint32_t tmem_d, const Operand &A, c
     // product) halves the residual error; callers whose tensor time matters drop it (keep_lo_lo = false: the same
     // three products as the training kernels).
     const int first = keep_lo_lo ? 0 : 1;
+    // the address is the low 14 bits of a descriptor's low word and never carries out of it: a K step is ONE 32-bit add
+    // per operand (building a descriptor from scratch per instruction costs more issue time than the MMA takes to run)
+    const uint64_t a_d = smem_desc(A.addr, A.lbo, A.sbo), b_d = smem_desc(B.addr, B.lbo, B.sbo);
+    const uint32_t a_hi32 = (uint32_t)(a_d >> 32), b_hi32 = (uint32_t)(b_d >> 32);
+    const uint32_t ak = A.kstep >> 4, bk = B.kstep >> 4;
 #pragma unroll 1
     for (int term = first; term < 4; ++term) {
-        const uint32_t a0 = A.addr + (term < 2 ? A.plane : 0u);
-        const uint32_t b0 = B.addr + ((term == 0 || term == 2) ? B.plane : 0u);
+        uint32_t a = (uint32_t)a_d + (term < 2 ? (A.plane >> 4) : 0u);
+        uint32_t b = (uint32_t)b_d + ((term == 0 || term == 2) ? (B.plane >> 4) : 0u);
 #pragma unroll 1
-        for (int k = 0; k < ksteps; ++k) {
-            mma_f16(tmem_d, smem_desc(a0 + k * A.kstep, A.lbo, A.sbo), smem_desc(b0 + k * B.kstep, B.lbo, B.sbo),
-                     idesc, accumulate || term > first || k > 0);
-        }
+        for (int k = 0; k < ksteps; ++k, a += ak, b += bk)
+            mma_f16(tmem_d, ((uint64_t)a_hi32 << 32) | a, ((uint64_t)b_hi32 << 32) | b, idesc,
+                    accumulate || term > first || k > 0);
     }
 }
 

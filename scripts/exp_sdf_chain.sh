@@ -11,3 +11,9 @@ for v in NO_MMA NO_MATH SKELETON; do
   objs=$(ls rise_sdf_b200/build/*.o | grep -v sdf_train.o)
   nvcc -shared -Wno-deprecated-gpu-targets -o scripts/_dbg/librsdf_$v.so $objs scripts/_dbg/sdf_train_$v.o
 done
+# the same for the inference MLP chain (csrc/mlp_fwd.cu; time with scripts/bench_mlp.py)
+for v in NO_MMA NO_EPI NO_WLOAD; do
+  nvcc $FLAGS -DRSDF_EXP_$v -c rise_sdf_b200/csrc/mlp_fwd.cu -o scripts/_dbg/mlp_fwd_$v.o
+  objs=$(ls rise_sdf_b200/build/*.o | grep -v mlp_fwd.o)
+  nvcc -shared -Wno-deprecated-gpu-targets -o scripts/_dbg/librsdf_mlp_$v.so $objs scripts/_dbg/mlp_fwd_$v.o
+done

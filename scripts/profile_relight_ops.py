@@ -38,6 +38,9 @@ for e in prof.events():
 print(f"device {sum(v[1] for v in rows.values()) / 1e3:.2f} ms over {sum(v[0] for v in rows.values())} launches")
 for k, (c, t) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:25]:
     print(f"{t / 1e3:8.3f} ms {c:4d} x {k}")
+print("== device kernels by launch count")
+for k, (c, t) in sorted(rows.items(), key=lambda kv: -kv[1][0])[:40]:
+    print(f"{c:4d} x {t / 1e3:8.3f} ms {k}")
 print("== host")
 for e in sorted(prof.key_averages(), key=lambda e: -e.self_cpu_time_total)[:45]:
     print(f"{e.self_cpu_time_total / 1e3:8.2f} ms  {e.count:5d} x  {e.key[:90]}")
