@@ -169,8 +169,19 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int s = s0 + 8 * (cr + 4 * k) + j;
-                const float x = __ldg(rbase + (size_t)min(s, p.S - 1) * rstride);
-                rv[k][j] = (rvalid && s < p.S) ? fmaf(x, rsc, rsh) : 0.0f;
+                rv[k][j] = __ldg(rbase + (size_t)min(s, p.S - 1) * rstride);     // RAW: nothing here waits for the load
+            }
+        (void)0;
+    };
+    // affine + tail masking of the prefetched values, applied where they are consumed (a use inside load_rows would
+    // park the warp on 16 HBM latencies per tile right after the prefetch is issued)
+    auto finish_rows = [&](int s0) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int s = s0 + 8 * (cr + 4 * k) + j;
+                rv[k][j] = (rvalid && s < p.S) ? fmaf(rv[k][j], rsc, rsh) : 0.0f;
             }
         (void)0;
     };
@@ -184,6 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_fwd_kernel(const __grid
         if (t.tid == 0) bulk_wait_read1();
         __syncthreads();
         if (rows_in) {
+            finish_rows(s0);
             if (fr < p.k_pad) {
                 store_in_chunk(in_img, in_plane, p.k_pad, fr, cr, rv[0], p.fp16);
                 store_in_chunk(in_img, in_plane, p.k_pad, fr, cr + 4, rv[1], p.fp16);
@@ -311,8 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int s = s0 + 8 * cr + j;
-            const float x = __ldg(p.g_rows + (size_t)min(s, p.S - 1) * p.r_real + min(fr, p.r_real - 1));
-            gv[j] = (t.tid < 128 && fr < p.r_real && s < p.S) ? x : 0.0f;
+            gv[j] = __ldg(p.g_rows + (size_t)min(s, p.S - 1) * p.r_real + min(fr, p.r_real - 1));   // raw: masked at its use
         }
     };
     if (rows_in && (int)blockIdx.x < n_tiles) load_g(blockIdx.x * NS);
@@ -340,7 +351,11 @@ __global__ void __launch_bounds__(THREADS, 1) relu_layer_bwd_kernel(const __grid
         if (t.tid == 0 && tile + (int)gridDim.x < n_tiles) issue_loads(tile + gridDim.x, st ^ 1);
         if (rows_in && t.tid < 128) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { bself += gv[j]; gv[j] *= gsc; }
+            for (int j = 0; j < 8; ++j) {
+                if (!(fr < p.r_real && s0 + 8 * cr + j < p.S)) gv[j] = 0.0f;
+                bself += gv[j];
+                gv[j] *= gsc;
+            }
             store_in_chunk(zb_img, zb_plane, p.r_pad, fr, cr, gv, p.fp16);
         }
         tc::mbar_wait(&ct->bar_in[st], (uint32_t)(it >> 1) & 1u);
