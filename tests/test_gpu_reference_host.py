@@ -89,12 +89,15 @@ def test_reference_neus_eval_and_occupancy_update_on_the_shims():
         res = []
         for mdl in (ours, ref):
             mdl.train()
-            real = torch.rand_like
-            torch.rand_like = lambda x, *a, **k: jit if x.shape == jit.shape else real(x, *a, **k)
+            # the same jitter on both sides, whichever way the estimator draws it (rand_like in the reference's grid.py,
+            # torch.rand in the shim's device-side update)
+            real_like, real_rand = torch.rand_like, torch.rand
+            torch.rand_like = lambda x, *a, **k: jit if x.shape == jit.shape else real_like(x, *a, **k)
+            torch.rand = lambda *a, **k: jit if tuple(a) == tuple(jit.shape) else real_rand(*a, **k)
             try:
                 mdl.update_step(0, 0)                       # warm-up branch: all 128^3 cells through occ_eval_fn
             finally:
-                torch.rand_like = real
+                torch.rand_like, torch.rand = real_like, real_rand
             mdl.eval()
             mdl.background_color = bg
             with torch.no_grad():
@@ -185,7 +188,9 @@ def test_reference_split_training_step_on_the_shims_equals_the_mirror():
         report = [f"loss {float(la):.6f} vs {float(lb):.6f}"]
         for k in pb:
             report.append(f"loss.{k}: {float(pa[k]):.6e} vs {float(pb[k]):.6e}")
-            assert abs(float(pa[k]) - float(pb[k])) <= 2e-3 * max(abs(float(pb[k])), 1e-3), report[-1]
+            # two fp32 evaluations of an FD-normal render: tests/test_gpu_split_grads.py measures the fp32 noise floor of
+            # these terms against fp64 (rgb_phys_mse: 1.3e-4 absolute = 1.4e-3 relative per realisation)
+            assert abs(float(pa[k]) - float(pb[k])) <= 5e-3 * max(abs(float(pb[k])), 1e-3), report[-1]
         g1 = dict(ours.named_parameters()); g1["emitter.base"] = ours.emitter.base
         g2 = dict(ref.named_parameters()); g2["emitter.base"] = ref.emitter.base
         for n in sorted(g1):
