@@ -340,7 +340,9 @@ __device__ __forceinline__ tc::Operand half_n(tc::Operand o, int g) { o.addr += 
 __device__ __forceinline__ tc::Operand half_k(tc::Operand o, int g) { o.addr += (uint32_t)g * 2u * o.kstep; return o; }
 
 // group side: publish this group's smem image writes / TMEM reads and hand its half to the issuer; wait for the GEMMs
-#define TR_READY() { tc::fence_async_smem(); tc::tc_fence_before(); grp_sync(g); if (tg == 0) bar_arrive(&ct->ready[g]); }
+// (one arrival per WARP -- ready[g] counts the group's 8 warps -- instead of a named barrier over the group followed by a
+// single arrival: the group's warps need not meet each other, only the issuer has to see all of them)
+#define TR_READY() { tc::fence_async_smem(); tc::tc_fence_before(); __syncwarp(); if (t.lane == 0) bar_arrive(&ct->ready[g]); }
 #define TR_WAIT() { tc::mbar_wait(&ct->done[g], dpar); dpar ^= 1u; tc::tc_fence_after(); }
 // issuer side: one link of the chain for half 0, then for half 1
 #define TR_ISSUE(...)                                          \
@@ -361,7 +363,7 @@ __device__ __forceinline__ tc::Operand half_k(tc::Operand o, int g) { o.addr += 
 __device__ __forceinline__ void tr_init(TrCtrl *ct, const Tid &t, uint32_t tmem_cols) {
     if (t.tid == 0) {
         tc::mbar_init(&ct->bar_w, 1);
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&ct->done[i], 1); tc::mbar_init(&ct->ready[i], 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&ct->done[i], 1); tc::mbar_init(&ct->ready[i], TR_GRP / 32); }
         tc::mbar_fence_init();
     }
     if (t.warp == 0) tc::tmem_alloc(&ct->tmem_slot, tmem_cols);
