@@ -213,3 +213,33 @@ def test_split_model_fused_stages_equal_op_by_op_training_step():
         # the 1e-6 shift of depth it causes, the DISCRETE sample set of the reflection bounce on a few rays (see above),
         # which a scalar gradient like `variance` feels at the 3e-3 level (measured); a logic error is O(1)
         assert rel_l2(ga[k].cpu().numpy(), gb[k].cpu().numpy()) <= 1e-2, k
+
+
+def test_fused_stages_edge_cases():
+    """Empty sample sets, rays without samples, a single sample: the fused stages keep the shapes and zeros the op-by-op
+    path produces (the reference's own guards: models/volrend.py:826-834, models/texture.py:331-332)."""
+    from rise_sdf_b200.nerfacc import pack_info
+    from rise_sdf_b200.split_shade import split_render, split_shade
+    tex, light = _texture_and_light(base_res=64)          # 64 -> 32 -> 16: the smallest pyramid get_mip is defined for
+    light.build_mips()
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    out = split_shade(z(0, 6), z(0, 1), z(0, 2), z(0, 3), z(0, 3), z(0, 3), light, tex.FG_LUT, 1)
+    assert out.shape == (0, 24)
+    out0 = split_shade(z(0, 6), z(0, 1), z(0, 2), z(0, 3), z(0, 3), z(0, 3), light, tex.FG_LUT, 0)
+    assert out0.shape == (0, 7)
+    # three rays, only the middle one has (one) sample
+    ri = torch.tensor([1], device="cuda")
+    packed = pack_info(ri, 3)
+    rays_d = torch.nn.functional.normalize(torch.randn(3, 3), dim=-1).cuda()
+    sdf = torch.tensor([0.001], device="cuda", requires_grad=True)
+    n = (-rays_d[1:2]).clone().requires_grad_(True)                  # facing the ray
+    col = torch.rand(1, 24, device="cuda", requires_grad=True)
+    inv_s = torch.tensor(148.4, device="cuda", requires_grad=True)
+    acc, w, alpha = split_render(packed, rays_d, torch.tensor([1.0], device="cuda"), torch.tensor([1.02], device="cuda"), sdf, n,
+                                 col, inv_s, 1.0)
+    assert acc.shape == (3, 30) and float(acc[0].abs().sum()) == 0 and float(acc[2].abs().sum()) == 0
+    assert torch.allclose(acc[1, :24], (w * col)[0]) and torch.allclose(acc[1, 27], w[0]) and float(acc[1, 29]) == 0.0
+    assert 0.0 < float(alpha) <= 1.0 and torch.allclose(w, alpha)      # first sample of its ray: T = 1
+    acc.sum().backward()
+    for t in (sdf, n, col, inv_s):
+        assert t.grad is not None and torch.isfinite(t.grad).all()
