@@ -43,6 +43,23 @@ def update_module_step(m, epoch, global_step):
         m.update_step(epoch, global_step)
 
 
+_FOLD_SCOPE = [0]          # 0: no sharing; otherwise the id of the running training step (see VanillaMLP.effective_weights)
+
+
+class fold_once:
+    """Context manager: within it every VanillaMLP folds its weight-norm parametrisation once."""
+    _next = 0
+
+    def __enter__(self):
+        fold_once._next += 1
+        self._prev, _FOLD_SCOPE[0] = _FOLD_SCOPE[0], fold_once._next
+        return self
+
+    def __exit__(self, *exc):
+        _FOLD_SCOPE[0] = self._prev
+        return False
+
+
 class VanillaFrequency(nn.Module):
     def __init__(self, in_channels, config):
         super().__init__()
@@ -185,7 +202,16 @@ class VanillaMLP(nn.Module):
 
     def effective_weights(self):
         """[(W [out,in], b [out])] with weight-norm folded (differentiable torch ops on the
-        tiny parameter tensors; the big per-sample work happens in the kernels)."""
+        tiny parameter tensors; the big per-sample work happens in the kernels).
+
+        Inside a `fold_once()` scope (one training step: train._Trainer) the folded tensors are computed once and
+        shared by every call -- the split-sum step evaluates the SDF field with autograd four times, each of which used
+        to fold the weights again, forward and backward (~90 tiny launches per step).  Autograd accumulates the calls'
+        weight gradients on the shared tensor and runs the weight-norm backward once: the same sum, one rounding
+        order.  Outside a scope nothing is cached (a graph kept past its backward could not be reused)."""
+        key = (_FOLD_SCOPE[0], torch.is_grad_enabled())
+        if _FOLD_SCOPE[0] and self._folded is not None and self._folded[0] == key:
+            return self._folded[1]
         out = []
         for lin in self.linears():
             if hasattr(lin, "weight_g"):
@@ -194,7 +220,11 @@ class VanillaMLP(nn.Module):
             else:
                 W = lin.weight
             out.append((W, lin.bias))
+        if _FOLD_SCOPE[0]:
+            self._folded = (key, out)
         return out
+
+    _folded = None
 
     def forward(self, x):
         if x.is_cuda and not torch.is_grad_enabled() and x.dim() == 2 and VanillaMLP.fused_inference:

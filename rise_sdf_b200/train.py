@@ -7,6 +7,7 @@ GPUs -- the DDP-equivalent gradient exchange of launch.py:84-97: ONE flat fp32 b
 import torch
 import torch.distributed as dist
 
+from .network_utils import fold_once
 from .optim import FlatAdam
 
 
@@ -206,9 +207,10 @@ class NeusTrainer(_Trainer):
             m.update_step(0, self.global_step)
         m.background_color = background
         self.bucket.zero()
-        out = m(rays)
-        loss, parts = neus_loss(out, rgb, fg_mask)
-        self._finish(loss, optimize)
+        with fold_once():
+            out = m(rays)
+            loss, parts = neus_loss(out, rgb, fg_mask)
+            self._finish(loss, optimize)
         return loss, out
 
 
@@ -242,8 +244,9 @@ class SplitTrainer(_Trainer):
             m.update_step(0, self.global_step)
         m.background_color = background
         self.bucket.zero()
-        m.emitter.build_mips()
-        out = m(rays)
-        loss, parts = split_loss(m, out, rgb, fg_mask)
-        self._finish(loss, optimize)
+        with fold_once():
+            m.emitter.build_mips()
+            out = m(rays)
+            loss, parts = split_loss(m, out, rgb, fg_mask)
+            self._finish(loss, optimize)
         return loss, out
