@@ -500,7 +500,7 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
 // backward.  TMEM columns: ACC_W2 0 (128), ACC_W1 128 (48), ACC_W3T 176 (48), Z1 224, Z2 288, T0 352, T1 416
 constexpr uint32_t B_H0 = W_END, B_H0W = B_H0 + IMG_S_BYTES, B_GO = B_H0W + IMG_S_BYTES, B_GG = B_GO + IMG_S_BYTES,
                    B_BIGA = B_GG + IMG_S_BYTES, B_BIGB = B_BIGA + IMG_B_BYTES, B_CTRL = B_BIGB + IMG_B_BYTES,
-                   B_SMEM = B_CTRL + 64 + 4 * NS * 4;
+                   B_SMEM = B_CTRL + 64 + 5 * NS * 4;
 
 struct Grads {
     const float *g_out, *g_sdf;           // [S, n_out], [S] (added to g_out[:, 0]; may be NULL)
@@ -512,7 +512,11 @@ struct Grads {
 
 // CHAIN = false: no cotangent reaches g0 (plain first-order backward, e.g. the finite-difference evaluations
 // of the split-sum config): the gradient-chain GEMMs and three of the seven epilogue passes drop out.
-template <bool CHAIN, bool SPLIT>
+// SDF_ONLY (with CHAIN = false): the only cotangent is that of out[:, 0] (g_out == NULL, g_sdf given: the six
+// finite-difference neighbours of models/geometry.py:229-240).  Then W3^T g_out = w3[0,:] (x) g_sdf and
+// gW3 = g_sdf (x) a2 on row 0 only: both are rank-1, computed in the softplus epilogue in fp32 -- the P3 link (two GEMMs,
+// a hand-off, an epilogue pass and the cotangent images) disappears: 4 links per tile instead of 5.
+template <bool CHAIN, bool SPLIT, bool SDF_ONLY = false>
 __global__ void __launch_bounds__(TR_THREADS, 1)
 sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -521,6 +525,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
     float *ssc = reinterpret_cast<float *>(smax + NS);                    // [64] 2^k_s
     float *sinv = ssc + NS;                                               // [64] 2^-k_s
     float *swsc = sinv + NS;                                              // [64] 2^(K - k_s)
+    float *sgt = swsc + NS;                                               // [64] SDF_ONLY: the samples' g_sdf (unscaled)
     uint8_t *h0_img = smem + B_H0, *h0w_img = smem + B_H0W, *go_img = smem + B_GO, *gg_img = smem + B_GG,
             *big_a = smem + B_BIGA, *big_b = smem + B_BIGB;
     Tid t = make_tid();
@@ -565,6 +570,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
             // P2: Z2 = W2 a1
             TR_ISSUE(gemm3r<HID / 16, SPLIT>(tmem + Z2 + HS * g, W2k, half_n(An, g), id_kn, false);)
             // P3: gW3^T += a2 g_out^T ; v1 = W2^T u2 ; ub1 = W1 g_g0   (no chain: ab2 = W3^T g_out right away)
+            if (!SDF_ONLY)
             TR_ISSUE(gemm3r<KS, SPLIT>(tmem + AW3, half_k(Ak, g), half_k(GOk, g), id_g48, acc || g);
                      if (CHAIN) {
                          gemm3r<HID / 16, SPLIT>(tmem + T0 + HS * g, W2t, half_n(Bn, g), id_tn, false);
@@ -634,6 +640,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     b3acc += gov[j];
+                    if (SDF_ONLY && add_sdf) sgt[8 * cs + j] = gov[j];
                     const float m = fmaxf(fabsf(gov[j]), fabsf(ggv[j]));
                     const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
                     if (t.lane == 0 && wm != 0u) atomicMax(&smax[8 * cs + j], wm);
@@ -662,8 +669,10 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
                 }
                 store_chunk8<SPLIT>(h0_img, t, hv);
                 store_chunk8<SPLIT>(h0w_img, t, hw);
-                store_chunk8<SPLIT>(go_img, t, gov);
-                store_chunk8<SPLIT>(gg_img, t, ggv);
+                if (!SDF_ONLY) {
+                    store_chunk8<SPLIT>(go_img, t, gov);
+                    store_chunk8<SPLIT>(gg_img, t, ggv);
+                }
             }
             TR_READY()                                               // P1
             if (tile + (int)gridDim.x < n_tiles) prefetch_tile((tile + gridDim.x) * NS);
@@ -678,6 +687,27 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
             }
             TR_READY()                                               // P2
             TR_WAIT()
+            if (SDF_ONLY) {
+                // a2-bar = w3[0,f] g_sdf[s] and gW3[0,f] += a2[f,s] g_sdf[s] without a GEMM; z2-bar and the a1 operand
+                // of P6 right away
+                float v[16], z[16];
+                ld16_issue(t, Z2, v);
+                ld16_issue(t, Z1, z);
+                tc::tmem_ld_wait();
+                const float *gt = sgt + t.col0, *sc = ssc + t.col0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float a, sg, ds;
+                    sp_all(v[j] + b2f, a, sg, ds);
+                    w3acc = fmaf(a, gt[j], w3acc);
+                    const float zb = w30f * (gt[j] * sc[j]) * sg;
+                    b2acc = fmaf(zb, inv[j], b2acc);
+                    v[j] = zb;
+                    z[j] = sp_act(z[j] + b1f) * wsc[j];
+                }
+                st16<SPLIT>(big_a, t, v);                            // z2-bar
+                st16<SPLIT>(big_b, t, z);                            // a1 * 2^(K-k_s)
+            } else {
             {
                 float v[16], u[16];
                 ld16(t, Z2, v);
@@ -693,6 +723,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
             }
             TR_READY()                                               // P3
             TR_WAIT()
+            }
             float zp[16], vb[16];                             // z1-bar (chain part) and v1-bar, kept in registers
             if (CHAIN) {
                 float v[16], ub[16], z[16];
@@ -719,7 +750,7 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
                 TR_READY()                                           // P5
                 TR_WAIT()
             }
-            {
+            if (!SDF_ONLY) {
                 float ub[16], ab[16], z[16];
                 if (CHAIN) {
                     ld16_issue(t, T0, ub);
@@ -791,12 +822,14 @@ sdf_bwd_kernel(const Net net, const Inputs in, const Grads g_) {
                 const int col = 16 * t.cq + j;
                 if (col < net.n_in) atomicAdd(g.gW1 + (size_t)t.f * net.n_in + col, u[j] * ginv);
             }
-            tc::tmem_ld16(t.tl + AW3 + (uint32_t)(16 * t.cq), u);     // gW3[o][f] from ACC_W3T[f][o]
-            tc::tmem_ld_wait();
+            if (!SDF_ONLY) {                              // (SDF_ONLY: row 0 only, carried in w3acc)
+                tc::tmem_ld16(t.tl + AW3 + (uint32_t)(16 * t.cq), u);     // gW3[o][f] from ACC_W3T[f][o]
+                tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int col = 16 * t.cq + j;
-                if (col < net.n_out) atomicAdd(g.gW3 + (size_t)col * HID + t.f, u[j] * ginv);
+                for (int j = 0; j < 16; ++j) {
+                    const int col = 16 * t.cq + j;
+                    if (col < net.n_out) atomicAdd(g.gW3 + (size_t)col * HID + t.f, u[j] * ginv);
+                }
             }
         }
         atomicAdd(g.gW3 + t.f, w3acc);                    // the sdf head also feeds the gradient chain
@@ -1093,14 +1126,17 @@ int rsdf_sdf_mlp_bwd(const rsdf_sdf_mlp *net, const float *in0, int w0, float sc
     const int n_tiles = (n_samples + NS - 1) / NS;
     const int grid = n_tiles < RSDF_NUM_SMS ? n_tiles : RSDF_NUM_SMS;
     cudaError_t e;
-#define RSDF_BWD(C, SP)                                                                                          \
-    {                                                                                                            \
-        e = cudaFuncSetAttribute(sdf_bwd_kernel<C, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM); \
-        if (e != cudaSuccess) return (int)e;                                                                     \
-        sdf_bwd_kernel<C, SP><<<grid, TR_THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g);               \
+#define RSDF_BWD(C, SP, ...)                                                                                          \
+    {                                                                                                                 \
+        e = cudaFuncSetAttribute(sdf_bwd_kernel<C, SP, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 (int)B_SMEM);                                                                        \
+        if (e != cudaSuccess) return (int)e;                                                                          \
+        sdf_bwd_kernel<C, SP, ##__VA_ARGS__><<<grid, TR_THREADS, B_SMEM, (cudaStream_t)stream>>>(to_net(net), in, g); \
     }
     if (g_g0a || g_g0b) {
         if (net->precision) RSDF_BWD(true, false) else RSDF_BWD(true, true)
+    } else if (!g_out) {                 // only the sdf head carries a cotangent
+        if (net->precision) RSDF_BWD(false, false, true) else RSDF_BWD(false, true, true)
     } else {
         if (net->precision) RSDF_BWD(false, false) else RSDF_BWD(false, true)
     }
