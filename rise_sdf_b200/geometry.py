@@ -145,6 +145,25 @@ class VolumeSDF(nn.Module):
         sdf = self._packed_sdf(x01, comp.xyz_scale, comp.xyz_offset, y, sdf_only=True)
         return sdf.view(*points.shape[:-1], 6)
 
+    def _fd6_sdf_train(self, points, eps):
+        """`_fd6_sdf` under autograd (training): the same single hash-grid launch for the six neighbours, differentiable
+        w.r.t. the table, followed by the sdf-only fused MLP node -- instead of building the 6S neighbour positions with
+        torch ops and running the generic hash-grid forward over them.  None when the fused path does not apply."""
+        from . import sdf_field, tinycudann as tcnn
+        from .network_utils import VanillaMLP
+        if not (torch.is_grad_enabled() and points.is_cuda and not points.requires_grad and points.numel() > 0
+                and VanillaMLP.tc_training and VanillaMLP.fused_training):
+            return None
+        parts = self._fused_parts()
+        if parts is None:
+            return None
+        inner, mask = parts
+        comp = self.encoding
+        x01, y = tcnn.hashgrid_fd6_train(inner, points.reshape(-1, 3), eps, self.radius)
+        _, sdf, _, _ = sdf_field.fused_sdf_parts(self.network, x01, comp.xyz_scale, comp.xyz_offset,
+                                                 y if mask is None else y * mask, want_g0=False, sdf_only=True)
+        return sdf.view(*points.shape[:-1], 6)
+
     _packed_sdf = None
     _mask_ones = None           # cached "progressive level mask is all ones" (refreshed in update_step)
 
@@ -184,6 +203,8 @@ class VolumeSDF(nn.Module):
                 elif self.grad_type == "finite_difference":
                     eps = self._finite_difference_eps
                     points_d_sdf = self._fd6_sdf(points_, eps)
+                    if points_d_sdf is None:
+                        points_d_sdf = self._fd6_sdf_train(points_, eps)
                     if points_d_sdf is None:
                         offsets = torch.as_tensor([[eps, 0.0, 0.0], [-eps, 0.0, 0.0], [0.0, eps, 0.0],
                                                    [0.0, -eps, 0.0], [0.0, 0.0, eps], [0.0, 0.0, -eps]]).to(points_)

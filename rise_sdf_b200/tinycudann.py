@@ -219,6 +219,43 @@ def hashgrid_fd6(enc, points, eps, radius):
     return x01, y
 
 
+class _HashGridFD6(torch.autograd.Function):
+    """The training-time twin of `hashgrid_fd6`: (points, table) -> (x01 [6S,3] non-differentiable, y [6S,n_out]); the
+    backward is the ordinary table scatter over the 6S neighbour positions (the points are data on the render path).
+    The forward shares corner gathers between the six neighbours of a sample, which the generic forward over 6S
+    independent points cannot (8.8 M points per split-sum step: 2.3 -> 1.2 ms)."""
+
+    @staticmethod
+    def forward(ctx, points, table, enc, eps, radius):
+        points = points.contiguous().float()
+        S = points.shape[0]
+        x01 = torch.empty(6 * S, 3, device=points.device, dtype=torch.float32)
+        y = torch.empty(6 * S, enc.meta.n_output_dims, device=points.device, dtype=torch.float32)
+        L.call("rsdf_hashgrid_fd6", L.ptr(points), L.ptr(table), enc.meta.ref, S, float(eps), float(radius), L.ptr(x01),
+               L.ptr(y), L.stream())
+        ctx.save_for_backward(x01, table)
+        ctx.meta = enc.meta
+        ctx.mark_non_differentiable(x01)
+        return x01, y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _gx, gy):
+        x01, table = ctx.saved_tensors
+        gt = None
+        if ctx.needs_input_grad[1]:
+            gt = torch.zeros_like(table)
+            L.call("rsdf_hashgrid_bwd_table", L.ptr(x01), L.ptr(gy.contiguous().float()), ctx.meta.ref, x01.shape[0], L.ptr(gt),
+                   L.stream())
+        return None, gt, None, None, None
+
+
+def hashgrid_fd6_train(enc, points, eps, radius):
+    """`hashgrid_fd6` with autograd to the hash table (points [S,3] carry no gradient)."""
+    L.require_cuda(points)
+    return _HashGridFD6.apply(points.detach(), enc.params, enc, eps, radius)
+
+
 class _SHForward(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, degree):
