@@ -349,9 +349,9 @@ def run_split_train(args, dev, world, rank, n_rays=4096):
     trainer.global_step = 19984                      # one untimed occupancy-refresh step (see run_ours)
     trainer.step(*batches[1])
     trainer.global_step = 20001
-    # a full occupancy-refresh period of warm-up: this config's sample count keeps drifting (the model is learning), and
+    # more than two occupancy-refresh periods of warm-up: this config's sample count keeps drifting (the model is learning), and
     # every first-time size is an allocator growth event (measured: one 150-200 ms step in an otherwise 67 ms loop)
-    for i in range(max(args.warmup, 20)):
+    for i in range(max(args.warmup, 40)):
         trainer.step(*batches[i % 2])
     steps = max(3, args.steps // 2)
 
