@@ -80,3 +80,44 @@ def test_frequency_encoding_matches_the_per_band_loop(cfg, step):
     if step is not None:                                                           # the mask follows update_step
         enc.update_step(0, 100)
         assert float((enc(x) - y).abs().max()) > 0
+
+
+def test_fold_once_shares_the_folded_weights_inside_a_step_only():
+    """VanillaMLP.effective_weights(): inside a `fold_once()` scope (one training step) the weight-norm fold is computed
+    once and its gradient accumulates over the uses; outside a scope every call folds again (a graph kept past its
+    backward could not be reused)."""
+    from rise_sdf_b200.network_utils import VanillaMLP, fold_once
+    torch.manual_seed(0)
+    m = VanillaMLP(35, 48, {"n_neurons": 128, "n_hidden_layers": 2, "sphere_init": True, "weight_norm": True,
+                            "output_activation": "none"})
+    a = m.effective_weights()
+    b = m.effective_weights()
+    assert a[0][0] is not b[0][0] and torch.equal(a[0][0], b[0][0])
+    x = torch.randn(7, 35)
+
+    def loss_of(ws):
+        (W1, b1), (W2, b2), (W3, b3) = ws
+        return (torch.relu(torch.relu(x @ W1.T + b1) @ W2.T + b2) @ W3.T + b3).sum()
+
+    ref = [None]
+    for shared in (False, True):
+        m.zero_grad(set_to_none=True)
+        if shared:
+            with fold_once():
+                w1, w2 = m.effective_weights(), m.effective_weights()
+                assert w1[0][0] is w2[0][0]
+                (loss_of(w1) + loss_of(w2)).backward()
+            with fold_once():                                   # a new step: folded afresh (the old graph is gone)
+                w3 = m.effective_weights()
+                assert w3[0][0] is not w1[0][0]
+                loss_of(w3).backward()
+        else:
+            (loss_of(m.effective_weights()) + loss_of(m.effective_weights())).backward()
+            loss_of(m.effective_weights()).backward()
+        grads = [p.grad.clone() for p in m.parameters()]
+        if ref[0] is None:
+            ref[0] = grads
+        else:
+            for g, r in zip(grads, ref[0]):
+                assert torch.allclose(g, r, rtol=1e-5, atol=1e-7)
+    assert m.effective_weights()[0][0] is not m.effective_weights()[0][0]       # no sharing once the scope is left
