@@ -419,7 +419,7 @@ sdf_fwd_kernel(const Net net, const Inputs in, float *__restrict__ out, float *_
         }
     } else {
         // ---- epilogue group g: thread = feature row f x 16 of the half's 32 sample columns -----------------
-        const int g = t.warp >> 3, tg = t.tid & (TR_GRP - 1);
+        const int g = t.warp >> 3;
         t.tl = tmem + ((uint32_t)(t.q * 32) << 16);
         const float b1f = net.b1[t.f], b2f = net.b2[t.f], w30f = net.w3r0[t.f];
         const float b3f = t.f < net.n_out ? net.b3[t.f] : 0.0f;
